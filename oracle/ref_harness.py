@@ -1,0 +1,239 @@
+"""Harness that imports the UNMODIFIED reference env classes from /root/reference.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this file.  It is used
+ (a) by ``tests/golden/make_golden.py`` to generate the committed golden vectors, and
+ (b) by the CPU tests marked ``needs_reference`` that re-check the oracle restatement
+     against the live reference when ``/root/reference`` is present (this container only;
+     the GPU box has no reference tree, so those tests skip there).
+
+The reference needs ``gym`` (0.15.7), ``h5py`` and ``skimage`` which are not installed
+offline.  We put minimal in-memory stand-ins into ``sys.modules``:
+  * ``gym``: ``Env``, ``spaces.{Box,Discrete,Tuple}``, ``register``/``make`` - just enough for
+    the class bodies to execute (reference use: environments/gym_graph/graph.py:1-37,
+    graph/env.py:1-30, environments/gym_ai2thor/envs/cached.py:1-36).
+  * ``h5py.File``: reads from an in-memory dict registry (cached.py:26-32 does
+    ``file['observation'][()]``).
+  * ``skimage.transform.resize``: identity on same-size frames returning float64/255
+    (what skimage does for a same-size uint8 image, cached.py:62-64).
+The package ``environments`` is registered as a *namespace stub* so that importing
+``environments.gym_graph.graph`` does not execute ``environments/__init__.py`` (which pulls
+in the live simulators).
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("VN_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "graph"))
+
+
+# --------------------------------------------------------------------------- gym stand-in
+def _make_gym():
+    gym = types.ModuleType("gym")
+    spaces = types.ModuleType("gym.spaces")
+
+    class Env:
+        metadata = {}
+
+        @property
+        def unwrapped(self):
+            return self
+
+    class Space:
+        pass
+
+    class Box(Space):
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), np.dtype(dtype)
+
+    class Discrete(Space):
+        def __init__(self, n):
+            self.n = n
+
+    class Tuple(Space):
+        def __init__(self, spaces_):
+            self.spaces = tuple(spaces_)
+
+    registry = {}
+
+    def register(id, entry_point=None, max_episode_steps=None, kwargs=None, **_):
+        registry[id] = dict(entry_point=entry_point, max_episode_steps=max_episode_steps, kwargs=kwargs or {})
+
+    spaces.Space, spaces.Box, spaces.Discrete, spaces.Tuple = Space, Box, Discrete, Tuple
+    gym.Env, gym.spaces, gym.register, gym.registry = Env, spaces, register, registry
+    return gym, spaces
+
+
+class _H5Dataset:
+    def __init__(self, arr):
+        self._arr = arr
+
+    def __getitem__(self, key):
+        return self._arr[key]
+
+
+class FakeH5File:
+    """``h5py.File(path, 'r')`` stand-in backed by ``FakeH5File.registry[path]`` (dict of arrays)."""
+    registry = {}
+
+    def __init__(self, path, mode="r"):
+        self._d = FakeH5File.registry[path]
+
+    def __getitem__(self, key):
+        return _H5Dataset(self._d[key])
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def _fake_skimage_resize(image, size, anti_aliasing=True):
+    # skimage.transform.resize on a same-size uint8 image returns float64 in [0,1]
+    assert tuple(image.shape[:2]) == tuple(size), "harness only supports same-size frames"
+    return image.astype(np.float64) / 255.0
+
+
+_installed = False
+
+
+def install():
+    """Put the stand-ins and the reference tree on sys.path / sys.modules (idempotent)."""
+    global _installed
+    if _installed:
+        return
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    gym, spaces = _make_gym()
+    sys.modules.setdefault("gym", gym)
+    sys.modules.setdefault("gym.spaces", spaces)
+    h5 = types.ModuleType("h5py")
+    h5.File = FakeH5File
+    sys.modules.setdefault("h5py", h5)
+    sk = types.ModuleType("skimage")
+    skio = types.ModuleType("skimage.io")
+    skt = types.ModuleType("skimage.transform")
+    skt.resize = _fake_skimage_resize
+    sk.io, sk.transform = skio, skt
+    sys.modules.setdefault("skimage", sk)
+    sys.modules.setdefault("skimage.io", skio)
+    sys.modules.setdefault("skimage.transform", skt)
+    # namespace stubs: do not execute environments/__init__.py (imports live simulators)
+    for name, rel in (("environments", "environments"),
+                      ("environments.gym_graph", "environments/gym_graph"),
+                      ("environments.gym_ai2thor", "environments/gym_ai2thor"),
+                      ("environments.gym_ai2thor.envs", "environments/gym_ai2thor/envs")):
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REFERENCE_ROOT, rel)]
+        sys.modules.setdefault(name, m)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    _installed = True
+
+
+def ref_modules():
+    """Returns the reference modules on the hot path, imported unmodified."""
+    install()
+    m = types.SimpleNamespace()
+    m.util = importlib.import_module("graph.util")
+    m.core = importlib.import_module("graph.core")
+    m.maze_graph = importlib.import_module("graph.maze_graph")
+    m.thor_world = importlib.import_module("graph.multi_graph_no_tp")
+    m.graph_env = importlib.import_module("graph.env")
+    m.gym_graph = importlib.import_module("environments.gym_graph.graph")
+    m.cached = importlib.import_module("environments.gym_ai2thor.envs.cached")
+    return m
+
+
+def ref_aux_trainer():
+    """experiments/ai2_auxiliary/trainer.py with ``deep_rl`` stubbed; ``autocrop_observations``
+    is OUR restatement (oracle.rollout.autocrop_observations) because deep_rl is absent -
+    so only the avg_pool half of compute_auxiliary_target is pinned by the reference."""
+    install()
+    from oracle import rollout as _r
+    import torch
+
+    def _stub(name, **attrs):
+        mod = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+        sys.modules[name] = mod
+        return mod
+
+    class UnrealTrainer:
+        def __init__(self, *a, **k):
+            pass
+
+    def _autocrop(x, cell, output_size=None):
+        return torch.from_numpy(_r.autocrop_observations(x.numpy(), cell, output_size))
+
+    _stub("deep_rl")
+    _stub("deep_rl.a2c_unreal", UnrealTrainer=UnrealTrainer)
+    _stub("deep_rl.a2c_unreal.unreal", without_last_item=lambda x: x)
+    _stub("deep_rl.a2c_unreal.util", autocrop_observations=_autocrop)
+    _stub("deep_rl.common")
+    _stub("deep_rl.common.pytorch", to_tensor=lambda x, d=None: x)
+    for name, rel in (("experiments", "experiments"), ("experiments.ai2_auxiliary", "experiments/ai2_auxiliary")):
+        mod = types.ModuleType(name)
+        mod.__path__ = [os.path.join(REFERENCE_ROOT, rel)]
+        sys.modules.setdefault(name, mod)
+    return importlib.import_module("experiments.ai2_auxiliary.trainer")
+
+
+# --------------------------------------------------------------------------- stream injection
+class InjectedRandom:
+    """Replaces the module-level ``random`` seen by a reference env module so that
+    ``random.choice`` / ``random.randrange`` consume a supplied integer stream
+    (reference: environments/gym_graph/graph.py:47, graph/env.py:181, cached.py:39-42)."""
+
+    def __init__(self, stream):
+        self.stream = list(stream)
+        self.pos = 0
+
+    def _next(self):
+        v = self.stream[self.pos]
+        self.pos += 1
+        return int(v)
+
+    def choice(self, seq):
+        return seq[self._next() % len(seq)]
+
+    def randrange(self, n):
+        return self._next() % n
+
+    def Random(self, x=None):  # cached.py:24 builds random.Random(x=seed)
+        return self
+
+
+class InjectedChoice:
+    """Replacement for ``np.random.choice`` as called by graph/util.py:102,116,132,142.
+    Consumes a stream of uint32 and maps r -> the floor(r * k / 2^32)-th candidate with positive
+    weight (k = number of positive-weight candidates).  Every call is recorded as
+    ``(n, p, idx)`` so the generator can pin the reference's candidate set AND its weights;
+    the chosen start state itself is then injected into the device path, so the r -> idx rule
+    used here does not have to match any device RNG."""
+
+    def __init__(self, stream):
+        self.stream = list(stream)
+        self.pos = 0
+        self.calls = []
+
+    def __call__(self, a, p=None):
+        r = int(self.stream[self.pos]) & 0xFFFFFFFF
+        self.pos += 1
+        n = len(a)
+        if p is None:
+            idx = (r * n) >> 32
+        else:
+            p = np.asarray(p, dtype=np.float64)
+            pos = np.nonzero(p > 0)[0]
+            idx = int(pos[(r * len(pos)) >> 32])
+        self.calls.append((n, None if p is None else p.copy(), int(idx)))
+        return a[idx]

@@ -1,0 +1,165 @@
+"""ORACLE (test infrastructure).  The vectorised-env conventions that live in UN-VENDORED
+third-party code: gym 0.15.7 ``TimeLimit``, baselines-0.1.6-style ``SubprocVecEnv`` auto-reset,
+and deep_rl 0.2.9's ``RewardCollector`` / ``TransposeImage`` / ``ScaledFloatFrame`` /
+``UnrealEnvBaseWrapper`` (call sites: /root/reference/experiments/thor_cached_auxiliary.py:58-71,
+environments/gym_graph/__init__.py:12,21,27).
+
+PARITY UNPINNED for this file: none of that source is under /root/reference and it is not
+installed offline; the behaviour below is restated from the published versions pinned in
+not_explicit_list.txt:11,29,45.  The env classes it drives ARE pinned.
+"""
+import numpy as np
+
+from . import graph_util as gu
+from . import philox
+
+
+class TimeLimit:
+    """gym 0.15.7 wrappers/time_limit.py: after ``max_episode_steps`` steps
+    ``info['TimeLimit.truncated'] = not done; done = True``; counter cleared by reset()."""
+
+    def __init__(self, env, max_episode_steps):
+        self.env = env
+        self._max = max_episode_steps
+        self._elapsed = 0
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self):
+        self._elapsed = 0
+        return self.env.reset()
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        self._elapsed += 1
+        if self._elapsed >= self._max:
+            info["TimeLimit.truncated"] = not done
+            done = True
+        return obs, reward, done, info
+
+
+class RewardCollector:
+    """deep_rl.common.env.RewardCollector [recalled]: accumulates the episode return and length and
+    on done sets ``info['episode'] = {'r': return, 'l': length}``."""
+
+    def __init__(self, env):
+        self.env = env
+        self.ret, self.len = 0.0, 0
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    def reset(self):
+        self.ret, self.len = 0.0, 0
+        return self.env.reset()
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        self.ret = float(np.float32(np.float32(self.ret) + np.float32(reward)))
+        self.len += 1
+        if done:
+            info["episode"] = dict(r=self.ret, l=self.len)
+        return obs, reward, done, info
+
+
+def last_action_reward(action, reward, n_actions):
+    """deep_rl.a2c_unreal.util.UnrealEnvBaseWrapper [recalled]: one_hot(action) ++ [clip(r,-1,1)],
+    float32 [n_actions + 1]; all zeros after reset."""
+    v = np.zeros(n_actions + 1, np.float32)
+    if action is not None and 0 <= action < n_actions:
+        v[action] = 1.0
+    v[-1] = np.clip(reward, -1.0, 1.0)
+    return v
+
+
+def transpose_scale(frame_u8):
+    """TransposeImage then ScaledFloatFrame [recalled]: HWC uint8 -> CHW float32 / 255."""
+    return np.transpose(frame_u8, (2, 0, 1)).astype(np.float32) / np.float32(255.0)
+
+
+class VecEnv:
+    """baselines-style vectorised env [recalled, D1]: per worker
+    ``ob, r, done, info = env.step(a); if done: ob = env.reset()`` - the returned observation is the
+    FIRST observation of the next episode; leaves are stacked on axis 0; ``lar`` is the
+    UnrealEnvBaseWrapper vector (zeros for an env that just reset)."""
+
+    def __init__(self, envs, n_actions=4):
+        self.envs = envs
+        self.n_actions = n_actions
+
+    @staticmethod
+    def _stack(obs_list):
+        first = obs_list[0]
+        if isinstance(first, tuple):
+            return tuple(np.stack([o[i] for o in obs_list]) for i in range(len(first)))
+        if isinstance(first, dict):
+            return {k: np.stack([o[k] for o in obs_list]) for k in first}
+        return np.stack(obs_list)
+
+    def reset(self):
+        obs = [e.reset() for e in self.envs]
+        lar = np.zeros((len(self.envs), self.n_actions + 1), np.float32)
+        return self._stack(obs), lar
+
+    def step(self, actions):
+        obs, rews, dones, infos, lars = [], [], [], [], []
+        for e, a in zip(self.envs, actions):
+            a = int(a)
+            ob, r, d, info = e.step(None if a < 0 else a)
+            if d:
+                ob = e.reset()
+                lars.append(np.zeros(self.n_actions + 1, np.float32))
+            else:
+                lars.append(last_action_reward(a, r, self.n_actions))
+            obs.append(ob)
+            rews.append(r)
+            dones.append(d)
+            infos.append(info)
+        return (self._stack(obs), np.stack(lars)), np.array(rews, np.float32), np.array(dones, bool), infos
+
+
+# --------------------------------------------------------------------------- Philox reset source
+class PhiloxResetSource:
+    """CPU restatement of the DEVICE path's own reset sampling (csrc/vn_kernels.cu: reset_env),
+    built from the oracle's candidate lists (reference order, graph/util.py:119-143 / :88-117),
+    not from the product's compiled tables:
+
+      draws = philox4x32_10(key = seed, ctr = (global_env_id, epoch, 0, 0)); epoch += 1
+      task  = mulhi(draws[0], n_tasks_of_env)
+      candidates of the task sorted (stable) by curriculum distance;
+      oriented:      k = #(dist <= optimal_distance) (all if no curriculum); idx = mulhi(draws[2], k)
+      un-oriented:   P = #(dist <= od), Q = rest; bucket = P if (Q == 0 or draws[1] < 0.9*2^32) else Q;
+                     idx = mulhi(draws[2], |bucket|) (+ P for the far bucket)
+
+    This is the reference's distribution (uniform over the eligible set; 0.9/0.1 two-level for
+    sample_initial_position) with a different, reproducible source of randomness.
+    """
+
+    def __init__(self, seed, env_id, tasks, optimal_distance_fn, two_level):
+        """tasks: list of (potentials, dists) in reference order, one per task of this env."""
+        self.seed, self.env_id, self.epoch = seed, env_id, 0
+        self.sorted = []
+        for pots, dists in tasks:
+            order = np.argsort(np.asarray(dists), kind="stable")
+            self.sorted.append(([pots[i] for i in order], np.asarray(dists)[order]))
+        self.od = optimal_distance_fn
+        self.two_level = two_level
+
+    def __call__(self):
+        d = philox.reset_draws(self.seed, self.env_id, self.epoch)
+        self.epoch += 1
+        t = int(philox.mulhi(d[0], len(self.sorted)))
+        pots, dists = self.sorted[t]
+        od = self.od(t)
+        n = len(pots)
+        p = n if od is None else int(np.searchsorted(dists, od, side="right"))
+        if self.two_level and od is not None:
+            q = n - p
+            if q == 0 or int(d[1]) < philox.BUCKET_THRESHOLD:
+                idx = int(philox.mulhi(d[2], p))
+            else:
+                idx = p + int(philox.mulhi(d[2], q))
+        else:
+            idx = int(philox.mulhi(d[2], p))
+        return t, pots[idx]

@@ -1,0 +1,127 @@
+"""Pins the ORACLE to the golden vectors produced by the unmodified reference classes
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import envs as oenvs
+from oracle import graph_util as gu
+from oracle import philox
+from oracle import rollout as orl
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    f = lambda c, k: [int(x) for x in philox.philox4x32(np.array(c, np.uint32), k)]
+    assert f([0, 0, 0, 0], (0, 0)) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert f([0xffffffff] * 4, (0xffffffff, 0xffffffff)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert f([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], (0xa4093822, 0x299f31d0)) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_shortest_paths_and_candidates_match_reference():
+    g = H.load("graph_util")
+    cs = g["complexities"]
+    for k in range(int(g["n_mazes"])):
+        maze = g["maze%d" % k]
+        dist, act = gu.compute_shortest_path_data(maze)
+        assert np.array_equal(dist, g["dist%d" % k])
+        assert np.array_equal(act, g["act%d" % k])
+        maxd = int(dist.max())
+        for gi, goal in enumerate(g["goals%d" % k]):
+            goal = tuple(int(v) for v in goal)
+            pots, d = gu.initial_state_candidates(maze, dist, act, goal)
+            pots2, d2 = gu.initial_position_candidates(maze, dist, goal[:2])
+            for ci, c in enumerate(cs):
+                od = None if c < 0 else c * (maxd + 4 - 1) + 1
+                w = gu.initial_state_weights(d, od)
+                assert np.array_equal(w, g["w_state_%d_%d_%d" % (k, gi, ci)])
+                od = None if c < 0 else c * (maxd - 1) + 1
+                w = gu.initial_position_weights(d2, od)
+                assert np.array_equal(w, g["w_position_%d_%d_%d" % (k, gi, ci)])
+
+
+def _gym_graph(name, aux):
+    g = H.load(name)
+    scene = H.scene_from_golden(g, True, ("rgb", "depth", "segmentation"))
+    osc = oenvs.OracleScene(scene)
+    goals = [tuple(int(v) for v in x) for x in g["goals"]]
+    goals = goals if bool(g["goals_is_list"]) else goals[0]
+    cls = oenvs.GymGraphAuxiliaryEnv if aux else oenvs.GymGraphEnv
+    rec = H.replay_oracle(g, lambda i: cls(osc, goals=goals, rewards=tuple(g["rewards_cfg"])), 5 if aux else 1)
+    assert int(g["largest_distance"]) == int(np.max(osc.graph))
+    H.assert_record_equal(rec, g)
+
+
+def test_gym_graph_auxiliary_env():
+    _gym_graph("gym_graph_aux", True)
+
+
+def test_gym_graph_oriented_env():
+    _gym_graph("gym_graph_oriented", False)
+
+
+def test_graph_env_simple():
+    g = H.load("graph_env_simple")
+    scene = H.scene_from_golden(g, False, ("rgb",))
+    osc = oenvs.OracleScene(scene)
+    rec = H.replay_oracle(g, lambda i: oenvs.SimpleGraphEnv(osc, rewards=tuple(g["rewards_cfg"])), 1, width=2)
+    H.assert_record_equal(rec, g)
+
+
+def test_graph_env_multiple():
+    g = H.load("graph_env_multiple")
+    oscs = []
+    for k in range(int(g["n_graphs"])):
+        sc = H.scenes.GridScene(g["maze%d" % k], [tuple(int(v) for v in g["goal%d" % k])], False, (84, 84), ("rgb",),
+                                frame_seed=int(g["frame_seed%d" % k]), scene_id=k)
+        oscs.append(oenvs.OracleScene(sc))
+    rec = H.replay_oracle(g, lambda i: oenvs.MultipleGraphEnv(oscs), 1, width=2)
+    H.assert_record_equal(rec, g)
+
+
+def test_graph_env_oriented_never_terminates():
+    g = H.load("graph_env_oriented")
+    scene = H.scene_from_golden(g, True, ("rgb", "depth", "segmentation"))
+    osc = oenvs.OracleScene(scene)
+    goal = tuple(int(v) for v in g["goals"][0])
+    rec = H.replay_oracle(g, lambda i: oenvs.GraphEnvOriented(osc, goal), 1)
+    H.assert_record_equal(rec, g)
+    assert not g["env_dones"].any() and g["truncated"].any()
+
+
+def test_thor_cached_env():
+    g = H.load("thor_cached")
+    scene = H.scene_from_golden(g, True, ("rgb",))
+    dist, _ = gu.compute_shortest_path_data(scene.maze)
+    locs, graph, spd = gu.h5_tables(scene.maze, dist)
+    assert np.array_equal(graph, g["graph"]) and H.crc(spd) == int(g["spd_crc"])
+    obs = scene.plane_frames("rgb")
+    rec = H.replay_oracle(g, lambda i: oenvs.ThorCachedEnv(graph, obs, spd), 2,
+                          state_of=lambda e: e._current_state_idx, width=1)
+    # the reference returns skimage-resized float64 frames (== uint8 / 255 at equal size); the oracle
+    # returns the raw uint8 frames, so compare CRCs of uint8/255 for the observation leaves
+    H.assert_record_equal(rec, g, obs=False)
+    # recompute the crc on float64/255 for a sample of steps
+    e = oenvs.ThorCachedEnv(graph, obs, spd)
+    e.reset_source = H.StreamSource(g["reset_goal"][0], g["reset_start"][0], g["reset_count"][0])
+    ob = e.reset()
+    assert [H.crc(x.astype(np.float64) / 255.0) for x in ob] == [int(v) for v in g["reset_obs_crc"][0]]
+    assert np.signbit(g["rewards"][g["rewards"] == 0]).any()      # the -0.0 of cached.py:84 is in the fixture
+
+
+def test_maze_render_hoist():
+    g = H.load("maze_render")
+    sc = H.scenes.GridScene(g["maze"], [tuple(int(v) for v in g["goal"])], False, (84, 84), ("rgb",))
+    fr = H.scenes.render_maze_frames(sc, tuple(int(v) for v in g["goal"]), (84, 84))
+    assert [H.crc(x) for x in fr] == [int(v) for v in g["resized_u8_crc"]]
+
+
+def test_aux_target_matches_reference_function():
+    g = H.load("aux_target")
+    rng = np.random.RandomState(int(g["x_seed"]))
+    x = rng.randint(0, 256, size=(2, 3, 3, 84, 84)).astype(np.float32) / np.float32(255.0)
+    np.testing.assert_allclose(orl.aux_target(x, 4, (20, 20)), g["y20"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(orl.aux_target(x, 4, None), g["y21"], rtol=1e-6, atol=1e-7)
+    d = rng.randint(0, 256, size=(2, 3, 1, 84, 84)).astype(np.float32) / np.float32(255.0)
+    np.testing.assert_allclose(orl.aux_target(d, 4, (20, 20)), g["yd"], rtol=1e-6, atol=1e-7)
