@@ -1,0 +1,548 @@
+// Vectorised env step / reset and the frame gather (sm_100a).
+//
+// Two launches per vectorised step, in stream order:
+//   K1 vn_step_kernel   one thread per env: adjacency lookup, collision + goal test, reward, TimeLimit,
+//                       done, auto-reset (Philox4x32-10 or injected stream), RewardCollector accumulators,
+//                       last_action_reward, warp-aggregated episode statistics.  ~40 B per env.
+//   K2 vn_gather_*      one CTA per env: copies the env's observation planes (and, only if the env just
+//                       reset, its goal planes) from the HBM store into the contiguous policy batch.
+//                       >99.9 % of the bytes; HBM-bound; two variants (LDG.128 registers / bulk async copy).
+#include <string>
+
+#include "vn_common.cuh"
+
+namespace vn {
+
+static thread_local std::string g_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+int32_t check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return VN_ECUDA;
+    }
+    return VN_OK;
+}
+
+// =====================================================================================================
+// K1: step / reset
+// =====================================================================================================
+struct StepParams {
+    vn_tables_t tab;
+    vn_envs_t env;
+    vn_rules_t rules;
+    vn_inject_t inj;
+    vn_step_out_t out;
+    const int32_t *actions;  // NULL in reset mode
+    const uint8_t *mask;     // reset mode only
+};
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+
+template <bool kReset>
+__global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int flags = p.rules.flags;
+    uint32_t st_episodes = 0, st_len = 0, st_succ = 0, st_coll = 0, st_steps = 0, st_trunc = 0, st_resets = 0;
+    float st_ret = 0.f;
+
+    if (i < p.env.n_envs) {
+        int s = p.env.state[i];
+        int g = p.env.goal[i];
+        float ep_ret = p.env.ep_return[i];
+        int ep_len = p.env.ep_length[i];
+        int elapsed = p.env.elapsed[i];
+        int obs_s = s;
+        bool do_reset;
+
+        if (kReset) {
+            do_reset = p.mask ? (p.mask[i] != 0) : true;
+        } else {
+            const int a = p.actions[i];
+            const int s_old = s;
+            bool terminal = false, collided = false;
+            float r;
+            if ((flags & VN_RULE_NOOP_ACTION) && a < 0) {
+                r = 0.0f;  // graph/env.py:118-120: latest observation, 0.0, not done
+            } else {
+                // graph.util.step + is_valid_state folded into one table lookup; an action outside
+                // [0, 4) has no transition in the reference (step() returns None) and is a collision here
+                const int nxt = (a >= 0 && a < 4) ? __ldg(p.tab.adj + (size_t)s * 4 + a) : -1;
+                collided = nxt < 0;
+                if (!collided) s = nxt;
+                bool at_goal;
+                if (p.rules.goal_compare == VN_GOAL_FULL)
+                    at_goal = (s == g);
+                else if (p.rules.goal_compare == VN_GOAL_POSITION)
+                    at_goal = ((s >> 2) == (g >> 2));
+                else
+                    at_goal = false;
+                terminal = at_goal && !(collided && (flags & VN_RULE_COLLISION_SKIPS_GOAL));
+                r = (flags & VN_RULE_NEG_STEP_REWARD) ? -p.rules.reward_step : p.rules.reward_step;
+                if (terminal) r = p.rules.reward_goal;
+                if (collided) r = p.rules.reward_collision;
+            }
+            bool done = terminal, trunc = false, at_limit = false;
+            elapsed += 1;
+            ep_ret += r;
+            ep_len += 1;
+            if (p.rules.max_episode_steps > 0 && elapsed >= p.rules.max_episode_steps) {
+                at_limit = true;  // gym TimeLimit: info['TimeLimit.truncated'] = not done; done = True
+                trunc = !done;
+                done = true;
+            }
+            do_reset = done && (flags & VN_RULE_AUTO_RESET);
+            obs_s = (terminal && (flags & VN_RULE_TERM_PREV_OBS) && !do_reset) ? s_old : s;
+
+            if (p.out.reward) p.out.reward[i] = r;
+            if (p.out.done) p.out.done[i] = done;
+            if (p.out.truncated) p.out.truncated[i] = at_limit ? (trunc ? 1 : 2) : 0;
+            if (p.out.win) p.out.win[i] = terminal;
+            if (p.out.info_state) p.out.info_state[i] = s;
+            if (done) {
+                if (p.out.episode_return) p.out.episode_return[i] = ep_ret;
+                if (p.out.episode_length) p.out.episode_length[i] = ep_len;
+                st_episodes = 1;
+                st_len = (uint32_t)ep_len;
+                st_ret = ep_ret;
+                st_succ = terminal;
+                st_trunc = trunc;
+            }
+            st_coll = collided;
+            st_steps = 1;
+            if (p.out.last_action_reward) {
+                // UnrealEnvBaseWrapper: one_hot(action) ++ [clip(r, -1, 1)]; zeros right after a reset
+                float *lar = p.out.last_action_reward + (size_t)i * (p.rules.n_actions + 1);
+                for (int k = 0; k < p.rules.n_actions; ++k) lar[k] = (!do_reset && k == a) ? 1.0f : 0.0f;
+                lar[p.rules.n_actions] = do_reset ? 0.0f : fminf(fmaxf(r, -1.0f), 1.0f);
+            }
+        }
+
+        if (do_reset) {
+            const uint32_t e = p.env.epoch[i];
+            const int tlo = p.env.task_lo[i];
+            int t, start;
+            if (p.inj.start) {
+                const uint32_t k = e < (uint32_t)p.inj.stride ? e : (uint32_t)p.inj.stride - 1;
+                const size_t at = (size_t)i * p.inj.stride + k;
+                t = tlo + (p.inj.task ? p.inj.task[at] : 0);
+                start = p.inj.start[at];
+            } else {
+                const Philox4 d = philox4x32_10((uint32_t)(p.env.env_id_base + i), e, 0u, 0u, (uint32_t)p.rules.seed,
+                                                (uint32_t)(p.rules.seed >> 32));
+                t = tlo + (int)__umulhi(d.v[0], (uint32_t)p.env.task_cnt[i]);
+                const int lo = __ldg(p.tab.task_cand_off + t);
+                const int cnt = __ldg(p.tab.task_cand_off + t + 1) - lo;
+                const int pre = __ldg(p.tab.task_prefix + t);
+                int idx;
+                if ((flags & VN_RULE_TWO_LEVEL) && pre < cnt && d.v[1] >= 3865470566u) {
+                    idx = pre + (int)__umulhi(d.v[2], (uint32_t)(cnt - pre));  // the 0.1 bucket, util.py:112-113
+                } else {
+                    idx = (int)__umulhi(d.v[2], (uint32_t)pre);
+                }
+                start = __ldg(p.tab.cand_state + lo + idx);
+            }
+            s = start;
+            g = __ldg(p.tab.task_goal + t);
+            p.env.task[i] = t;
+            p.env.goal[i] = g;
+            p.env.epoch[i] = e + 1;
+            elapsed = 0;
+            ep_ret = 0.f;
+            ep_len = 0;
+            obs_s = s;
+            st_resets = 1;
+            if (kReset && p.out.last_action_reward) {
+                float *lar = p.out.last_action_reward + (size_t)i * (p.rules.n_actions + 1);
+                for (int k = 0; k <= p.rules.n_actions; ++k) lar[k] = 0.0f;
+            }
+        }
+        p.env.state[i] = s;
+        p.env.elapsed[i] = elapsed;
+        p.env.ep_return[i] = ep_ret;
+        p.env.ep_length[i] = ep_len;
+        p.out.obs_state[i] = obs_s;
+        if (p.out.did_reset) p.out.did_reset[i] = do_reset;
+    }
+
+    if (p.out.stats) {
+        // warp-aggregated statistics: one atomic per counter per warp
+        const uint32_t e = warp_sum(st_episodes), l = warp_sum(st_len), su = warp_sum(st_succ), c = warp_sum(st_coll),
+                       n = warp_sum(st_steps), tr = warp_sum(st_trunc), rs = warp_sum(st_resets);
+        float ret = st_ret;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ret += __shfl_xor_sync(0xffffffffu, ret, o);
+        if ((threadIdx.x & 31) == 0) {
+            unsigned long long *st = reinterpret_cast<unsigned long long *>(p.out.stats);
+            if (e) {
+                atomicAdd(st + VN_STAT_EPISODES, (unsigned long long)e);
+                atomicAdd(reinterpret_cast<double *>(st + VN_STAT_RETURN_SUM), (double)ret);
+                atomicAdd(st + VN_STAT_LENGTH_SUM, (unsigned long long)l);
+                if (su) atomicAdd(st + VN_STAT_SUCCESSES, (unsigned long long)su);
+                if (tr) atomicAdd(st + VN_STAT_TRUNCATIONS, (unsigned long long)tr);
+            }
+            if (c) atomicAdd(st + VN_STAT_COLLISIONS, (unsigned long long)c);
+            if (n) atomicAdd(st + VN_STAT_STEPS, (unsigned long long)n);
+            if (rs) atomicAdd(st + VN_STAT_RESETS, (unsigned long long)rs);
+        }
+    }
+}
+
+// =====================================================================================================
+// K2: frame gather
+// =====================================================================================================
+struct GatherParams {
+    vn_store_t store;
+    const int32_t *obs_state;  // [n] record to gather for the observation planes
+    const int32_t *goal;       // [n] record of the goal planes (may be NULL)
+    const uint8_t *did_reset;  // [n] goal planes are rewritten only where set (NULL = always)
+    uint8_t *obs[VN_MAX_PLANES];
+    uint8_t *goal_obs[VN_MAX_PLANES];
+    int32_t n;
+};
+
+// ---- variant A: 16-byte vector loads / stores through registers -------------------------------------
+template <int kThreads, int kUnroll>
+__device__ __forceinline__ void copy_segment16(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int n16) {
+    const int4 *s = reinterpret_cast<const int4 *>(src);
+    int4 *d = reinterpret_cast<int4 *>(dst);
+    int base = threadIdx.x;
+    // full batches: kUnroll independent 16 B loads in flight per thread before the first store
+    for (; base + (kUnroll - 1) * kThreads < n16; base += kUnroll * kThreads) {
+        int4 v[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) v[k] = ld_stream16(s + base + k * kThreads);
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) st_stream16(d + base + k * kThreads, v[k]);
+    }
+    // tail: still issue all loads first
+    int4 v[kUnroll];
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k)
+        if (base + k * kThreads < n16) v[k] = ld_stream16(s + base + k * kThreads);
+#pragma unroll
+    for (int k = 0; k < kUnroll; ++k)
+        if (base + k * kThreads < n16) st_stream16(d + base + k * kThreads, v[k]);
+}
+
+template <int kThreads, int kUnroll>
+__global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherParams p) {
+    for (int env = blockIdx.x; env < p.n; env += gridDim.x) {
+        const int rec = __ldg(p.obs_state + env);
+        const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
+#pragma unroll 1
+        for (int pl = 0; pl < p.store.n_planes; ++pl) {
+            if (p.obs[pl])
+                copy_segment16<kThreads, kUnroll>(src + p.store.plane_off[pl],
+                                                  p.obs[pl] + (size_t)env * p.store.plane_bytes[pl],
+                                                  p.store.plane_bytes[pl] >> 4);
+        }
+        if (p.goal && (!p.did_reset || __ldg(p.did_reset + env))) {
+            const uint8_t *gsrc = p.store.base + (size_t)__ldg(p.goal + env) * p.store.state_pitch;
+#pragma unroll 1
+            for (int pl = 0; pl < p.store.n_planes; ++pl) {
+                if (p.goal_obs[pl])
+                    copy_segment16<kThreads, kUnroll>(gsrc + p.store.plane_off[pl],
+                                                      p.goal_obs[pl] + (size_t)env * p.store.plane_bytes[pl],
+                                                      p.store.plane_bytes[pl] >> 4);
+            }
+        }
+    }
+}
+
+// ---- variant B: bulk async copies (TMA engine), global -> shared -> global ---------------------------
+// One warp per CTA; lane 0 issues one cp.async.bulk per plane into shared memory (completion counted in
+// bytes on an mbarrier), then one cp.async.bulk per plane from shared memory to the batch rows.  No data
+// passes through registers; several CTAs per SM keep ~200 KB of copies in flight.
+__device__ __forceinline__ void bulk_copy_record(const vn_store_t &st, const uint8_t *src, uint8_t *const *dst,
+                                                 int env, uint8_t *smem, uint64_t *bar, uint32_t &parity) {
+    // the previous shared->global reads of this buffer must have drained before it is refilled
+    bulk_wait_read<0>();
+    uint32_t total = 0;
+    for (int pl = 0; pl < st.n_planes; ++pl)
+        if (dst[pl]) total += st.plane_bytes[pl];
+    mbar_expect_tx(bar, total);
+    uint32_t off = 0;
+    for (int pl = 0; pl < st.n_planes; ++pl)
+        if (dst[pl]) {
+            bulk_g2s(smem + off, src + st.plane_off[pl], st.plane_bytes[pl], bar);
+            off += st.plane_bytes[pl];
+        }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    off = 0;
+    for (int pl = 0; pl < st.n_planes; ++pl)
+        if (dst[pl]) {
+            bulk_s2g(dst[pl] + (size_t)env * st.plane_bytes[pl], smem + off, st.plane_bytes[pl]);
+            off += st.plane_bytes[pl];
+        }
+    bulk_commit();
+}
+
+__global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    if (threadIdx.x != 0) return;
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t parity = 0;
+    for (int env = blockIdx.x; env < p.n; env += gridDim.x) {
+        const uint8_t *src = p.store.base + (size_t)p.obs_state[env] * p.store.state_pitch;
+        bulk_copy_record(p.store, src, p.obs, env, smem, &bar, parity);
+        if (p.goal && (!p.did_reset || p.did_reset[env])) {
+            const uint8_t *gsrc = p.store.base + (size_t)p.goal[env] * p.store.state_pitch;
+            bulk_copy_record(p.store, gsrc, p.goal_obs, env, smem, &bar, parity);
+        }
+    }
+    bulk_wait_read<0>();
+}
+
+// =====================================================================================================
+// synthetic store fill
+// =====================================================================================================
+struct FillParams {
+    vn_store_t store;
+    int32_t plane_ids[VN_MAX_PLANES];
+    int32_t record0, n_records, scene, state0;
+    uint64_t seed;
+};
+
+__global__ void __launch_bounds__(256) vn_fill_kernel(const FillParams p) {
+    const int64_t words_per_rec = p.store.state_pitch >> 3;
+    const int64_t total = words_per_rec * p.n_records;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = w / words_per_rec;
+        const int32_t byte = (int32_t)((w - r * words_per_rec) << 3);
+        uint64_t val = 0;  // padding between planes is zero
+#pragma unroll 1
+        for (int pl = 0; pl < p.store.n_planes; ++pl) {
+            const int32_t o = byte - p.store.plane_off[pl];
+            if (o >= 0 && o < p.store.plane_bytes[pl]) {
+                const uint64_t key = frame_key(p.seed, (uint32_t)p.scene, (uint64_t)(p.state0 + r), p.plane_ids[pl]);
+                val = splitmix64(key + (uint64_t)(o >> 3));
+            }
+        }
+        *reinterpret_cast<uint64_t *>(const_cast<uint8_t *>(p.store.base) + (p.record0 + r) * p.store.state_pitch +
+                                      byte) = val;
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+static int32_t validate_store(const vn_store_t *s) {
+    VN_REQUIRE(s && s->base, "store: null");
+    VN_REQUIRE(s->n_planes >= 1 && s->n_planes <= VN_MAX_PLANES, "store: n_planes=%d", s->n_planes);
+    VN_REQUIRE((reinterpret_cast<uintptr_t>(s->base) & 127) == 0, "store: base must be 128-byte aligned");
+    VN_REQUIRE(s->state_pitch > 0 && (s->state_pitch & 127) == 0, "store: state_pitch must be a multiple of 128");
+    for (int i = 0; i < s->n_planes; ++i) {
+        VN_REQUIRE(s->plane_bytes[i] > 0 && (s->plane_bytes[i] & 15) == 0,
+                   "store: plane %d size %d is not a multiple of 16", i, s->plane_bytes[i]);
+        VN_REQUIRE((s->plane_off[i] & 127) == 0 && s->plane_off[i] + (int64_t)s->plane_bytes[i] <= s->state_pitch,
+                   "store: plane %d offset %d", i, s->plane_off[i]);
+    }
+    return VN_OK;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream_t stream) {
+    if (gp.n == 0) return VN_OK;
+    for (int pl = 0; pl < gp.store.n_planes; ++pl) {
+        VN_REQUIRE(!gp.obs[pl] || (reinterpret_cast<uintptr_t>(gp.obs[pl]) & 15) == 0,
+                   "gather: obs[%d] must be 16-byte aligned", pl);
+        VN_REQUIRE(!gp.goal_obs[pl] || (reinterpret_cast<uintptr_t>(gp.goal_obs[pl]) & 15) == 0,
+                   "gather: goal_obs[%d] must be 16-byte aligned", pl);
+    }
+    if (variant == VN_GATHER_AUTO) variant = VN_GATHER_LDG;
+    if (variant == VN_GATHER_LDG) {
+        constexpr int kThreads = 256;
+        vn_gather_ldg_kernel<kThreads, 4><<<gp.n, kThreads, 0, stream>>>(gp);
+        return check_launch("vn_gather_ldg_kernel");
+    }
+    if (variant == VN_GATHER_BULK) {
+        int smem_obs = 0, smem_goal = 0;
+        for (int pl = 0; pl < gp.store.n_planes; ++pl) {
+            if (gp.obs[pl]) smem_obs += gp.store.plane_bytes[pl];
+            if (gp.goal && gp.goal_obs[pl]) smem_goal += gp.store.plane_bytes[pl];
+        }
+        const int smem = max(smem_obs, smem_goal);
+        VN_REQUIRE(smem <= 200 * 1024, "gather(bulk): %d bytes of planes per env exceed shared memory", smem);
+        static int configured = 0;
+        if (smem > configured) {
+            cudaFuncSetAttribute(vn_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            configured = smem;
+        }
+        const int per_sm = max(1, min(32, (220 * 1024) / (smem + 1024)));
+        const int grid = min(gp.n, sm_count() * per_sm);
+        vn_gather_bulk_kernel<<<grid, 32, smem, stream>>>(gp);
+        return check_launch("vn_gather_bulk_kernel");
+    }
+    set_error("gather: unknown variant %d", variant);
+    return VN_EINVAL;
+}
+
+static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
+                          const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask,
+                          const vn_step_out_t *out, void *stream, bool reset) {
+    VN_REQUIRE(tab && tab->adj && tab->task_goal && tab->task_cand_off && tab->task_prefix && tab->cand_state,
+               "tables: null pointer");
+    VN_REQUIRE(tab->n_tasks > 0, "tables: n_tasks=%d", tab->n_tasks);
+    VN_REQUIRE(envs && envs->state && envs->goal && envs->task && envs->elapsed && envs->epoch && envs->ep_return &&
+                   envs->ep_length && envs->task_lo && envs->task_cnt,
+               "envs: null pointer");
+    VN_REQUIRE(envs->n_envs >= 0, "envs: n_envs=%d", envs->n_envs);
+    VN_REQUIRE(rules && rules->n_actions >= 1 && rules->n_actions <= 16, "rules: n_actions");
+    VN_REQUIRE(rules->goal_compare >= 0 && rules->goal_compare <= 2, "rules: goal_compare=%d", rules->goal_compare);
+    VN_REQUIRE(out && out->obs_state, "out: obs_state scratch is required");
+    VN_REQUIRE(reset || actions, "step: actions is null");
+    VN_REQUIRE(!inj || !inj->start || inj->stride > 0, "inject: stride=%d", inj ? inj->stride : 0);
+    if (envs->n_envs == 0) return VN_OK;
+    StepParams sp;
+    sp.tab = *tab;
+    sp.env = *envs;
+    sp.rules = *rules;
+    if (inj)
+        sp.inj = *inj;
+    else
+        sp.inj = vn_inject_t{nullptr, nullptr, 0, 0};
+    sp.out = *out;
+    sp.actions = actions;
+    sp.mask = mask;
+    const int threads = 128;
+    const int blocks = (envs->n_envs + threads - 1) / threads;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (reset)
+        vn_step_kernel<true><<<blocks, threads, 0, st>>>(sp);
+    else
+        vn_step_kernel<false><<<blocks, threads, 0, st>>>(sp);
+    return check_launch("vn_step_kernel");
+}
+
+static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant,
+                          void *stream) {
+    int32_t rc = validate_store(store);
+    if (rc) return rc;
+    VN_REQUIRE(envs && envs->goal && envs->n_envs >= 0, "envs: null pointer");
+    VN_REQUIRE(out && out->obs_state, "out: obs_state is required");
+    GatherParams gp;
+    gp.store = *store;
+    gp.obs_state = out->obs_state;
+    gp.n = envs->n_envs;
+    bool any_goal = false, any_obs = false;
+    for (int pl = 0; pl < VN_MAX_PLANES; ++pl) {
+        gp.obs[pl] = pl < store->n_planes ? out->obs[pl] : nullptr;
+        gp.goal_obs[pl] = pl < store->n_planes ? out->goal_obs[pl] : nullptr;
+        any_goal |= gp.goal_obs[pl] != nullptr;
+        any_obs |= gp.obs[pl] != nullptr;
+    }
+    gp.goal = any_goal ? envs->goal : nullptr;
+    gp.did_reset = out->did_reset;
+    VN_REQUIRE(!any_goal || out->did_reset, "out: did_reset is required when goal planes are emitted");
+    if (!any_goal && !any_obs) return VN_OK;
+    return launch_gather(gp, variant, static_cast<cudaStream_t>(stream));
+}
+
+static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
+                        const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask, const vn_step_out_t *out,
+                        int32_t variant, void *stream, bool reset) {
+    int32_t rc = validate_store(store);  // fail before anything is enqueued
+    if (rc) return rc;
+    rc = run_scalar(tab, envs, rules, inj, actions, mask, out, stream, reset);
+    if (rc) return rc;
+    return run_gather(store, envs, out, variant, stream);
+}
+
+}  // namespace vn
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+int32_t vn_abi_version(void) { return VN_ABI_VERSION; }
+const char *vn_last_error(void) { return vn::g_error.c_str(); }
+
+int32_t vn_fill_store(const vn_store_t *store, int32_t record0, int32_t n_records, uint64_t seed, int32_t scene,
+                      int32_t state0, const int32_t *plane_ids, void *stream) {
+    int32_t rc = vn::validate_store(store);
+    if (rc) return rc;
+    VN_REQUIRE(plane_ids, "fill: plane_ids is null");
+    VN_REQUIRE(record0 >= 0 && n_records >= 0 && record0 + (int64_t)n_records <= store->n_states,
+               "fill: records [%d, %d) outside the store (%d)", record0, record0 + n_records, store->n_states);
+    if (n_records == 0) return VN_OK;
+    vn::FillParams fp;
+    fp.store = *store;
+    for (int i = 0; i < VN_MAX_PLANES; ++i) fp.plane_ids[i] = i < store->n_planes ? plane_ids[i] : 0;
+    fp.record0 = record0;
+    fp.n_records = n_records;
+    fp.scene = scene;
+    fp.state0 = state0;
+    fp.seed = seed;
+    const int64_t total = (store->state_pitch >> 3) * n_records;
+    const int blocks = (int)((total + 255) / 256 < (int64_t)vn::sm_count() * 32 ? (total + 255) / 256
+                                                                                 : (int64_t)vn::sm_count() * 32);
+    vn::vn_fill_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(fp);
+    return vn::check_launch("vn_fill_kernel");
+}
+
+int32_t vn_env_reset(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
+                     const vn_rules_t *rules, const vn_inject_t *inject, const uint8_t *mask,
+                     const vn_step_out_t *out, int32_t gather_variant, void *stream) {
+    return vn::run_step(store, tables, envs, rules, inject, nullptr, mask, out, gather_variant, stream, true);
+}
+
+int32_t vn_env_step(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
+                    const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *actions,
+                    const vn_step_out_t *out, int32_t gather_variant, void *stream) {
+    return vn::run_step(store, tables, envs, rules, inject, actions, nullptr, out, gather_variant, stream, false);
+}
+
+int32_t vn_env_step_scalar(const vn_tables_t *tables, const vn_envs_t *envs, const vn_rules_t *rules,
+                           const vn_inject_t *inject, const int32_t *actions, const vn_step_out_t *out, void *stream) {
+    return vn::run_scalar(tables, envs, rules, inject, actions, nullptr, out, stream, false);
+}
+
+int32_t vn_env_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
+                      int32_t gather_variant, void *stream) {
+    return vn::run_gather(store, envs, out, gather_variant, stream);
+}
+
+int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, uint8_t *out,
+                        int32_t gather_variant, void *stream) {
+    int32_t rc = vn::validate_store(store);
+    if (rc) return rc;
+    VN_REQUIRE(plane >= 0 && plane < store->n_planes, "gather_plane: plane=%d", plane);
+    VN_REQUIRE(idx && out && n >= 0, "gather_plane: null pointer");
+    vn::GatherParams gp;
+    gp.store = *store;
+    gp.obs_state = idx;
+    gp.goal = nullptr;
+    gp.did_reset = nullptr;
+    gp.n = n;
+    for (int pl = 0; pl < VN_MAX_PLANES; ++pl) {
+        gp.obs[pl] = (pl == plane) ? out : nullptr;
+        gp.goal_obs[pl] = nullptr;
+    }
+    return vn::launch_gather(gp, gather_variant, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

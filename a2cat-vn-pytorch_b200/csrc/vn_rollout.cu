@@ -1,0 +1,385 @@
+// Rollout / target builders (sm_100a): n-step returns, discounted back-up, pixel-control reward and
+// auxiliary targets computed straight from the HBM frame store, reward-prediction labels + compaction,
+// and the fused gather -> float32 CHW conversion for the policy input.
+#include "vn_common.cuh"
+
+namespace vn {
+
+// =====================================================================================================
+// n-step returns: one thread per env, serial backward recurrence over T (parallel across envs)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) vn_nstep_returns_kernel(const float *__restrict__ reward,
+                                                               const uint8_t *__restrict__ done,
+                                                               const float *__restrict__ last_value, float gamma, int n,
+                                                               int t, int64_t stride_n, int64_t stride_t,
+                                                               float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t base = (int64_t)i * stride_n;
+    // R_T = (1 - done[T-1]) * V(s_T)
+    float ret = (1.0f - (float)done[base + (int64_t)(t - 1) * stride_t]) * last_value[i];
+    for (int k = t - 1; k >= 0; --k) {
+        const int64_t at = base + (int64_t)k * stride_t;
+        const float nd = 1.0f - (float)done[at];
+        // r + (gamma * R) * nd, evaluated in this order without contraction (nd is 0 or 1, so the
+        // product by nd is exact and an FMA could not change the result either)
+        ret = __fadd_rn(reward[at], __fmul_rn(__fmul_rn(gamma, ret), nd));
+        out[at] = ret;
+    }
+}
+
+// [n][t][d] with trailing feature axis: one thread per (env, feature), coalesced over d
+__global__ void __launch_bounds__(256) vn_backup_kernel(const float *__restrict__ reward,
+                                                        const uint8_t *__restrict__ done,
+                                                        const float *__restrict__ bootstrap, float gamma, int n, int t,
+                                                        int d, float *__restrict__ out) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)n * d) return;
+    const int i = (int)(gid / d), f = (int)(gid - (int64_t)i * d);
+    float ret = bootstrap[(int64_t)i * d + f];
+    for (int k = t - 1; k >= 0; --k) {
+        const int64_t at = ((int64_t)i * t + k) * d + f;
+        const float nd = 1.0f - (float)done[(int64_t)i * t + k];
+        ret = __fadd_rn(reward[at], __fmul_rn(__fmul_rn(gamma, ret), nd));
+        out[at] = ret;
+    }
+}
+
+// =====================================================================================================
+// pixel-control reward and auxiliary targets from the store
+// =====================================================================================================
+// lut[v] = float32(v) / 255.0f with IEEE division: exactly what ScaledFloatFrame produces per pixel.  The
+// table is replicated once per shared-memory bank (index v * 32 + lane) so that the 32 lanes of a warp,
+// each looking up a different byte value, never conflict.
+__device__ __forceinline__ void build_lut(float *lut) {
+    for (int k = threadIdx.x; k < 256 * 32; k += blockDim.x) lut[k] = __fdiv_rn((float)(k >> 5), 255.0f);
+}
+
+__device__ __forceinline__ void load_frame(uint8_t *dst_smem, const uint8_t *src, int nbytes) {
+    const int4 *s = reinterpret_cast<const int4 *>(src);
+    int4 *d = reinterpret_cast<int4 *>(dst_smem);
+    for (int k = threadIdx.x; k < (nbytes >> 4); k += blockDim.x) d[k] = ld_stream16(s + k);
+}
+
+struct PoolGeom {
+    int h, w, c, cell, out_h, out_w, top, left;
+};
+
+// CTA per (env n, chunk of time steps).  Frames of consecutive steps are kept in a 2-slot shared ring so
+// each frame is read from HBM/L2 once per chunk: (chunk + 1) / chunk reads per output.
+template <int kChunk>
+__global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t store, int plane,
+                                                               const int32_t *__restrict__ states, int n, int t,
+                                                               PoolGeom g, float *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int fbytes = g.h * g.w * g.c;
+    float *lut = reinterpret_cast<float *>(smem_raw);
+    uint8_t *frame0 = smem_raw + 256 * 32 * sizeof(float);
+    uint8_t *frame1 = frame0 + ((fbytes + 15) & ~15);
+    const int chunks = (t + kChunk - 1) / kChunk;
+    const int env = blockIdx.x / chunks;
+    const int k0 = (blockIdx.x - env * chunks) * kChunk;
+    const int k1 = min(t, k0 + kChunk);
+    const int lane = threadIdx.x & 31;
+    const int32_t *srow = states + (int64_t)env * (t + 1);
+    const uint8_t *pbase = store.base + store.plane_off[plane];
+
+    build_lut(lut);
+    load_frame(frame0, pbase + (size_t)srow[k0] * store.state_pitch, fbytes);
+    uint8_t *cur = frame0, *nxt = frame1;
+    const int cells = g.out_h * g.out_w;
+    const int row_bytes = g.w * g.c;
+    for (int k = k0; k < k1; ++k) {
+        load_frame(nxt, pbase + (size_t)srow[k + 1] * store.state_pitch, fbytes);
+        __syncthreads();
+        for (int cidx = threadIdx.x; cidx < cells; cidx += blockDim.x) {
+            const int oi = cidx / g.out_w, oj = cidx - oi * g.out_w;
+            float chan_sum = 0.f;
+            for (int ch = 0; ch < g.c; ++ch) {
+                float acc = 0.f;  // F.avg_pool2d: window sum in row-major order, then / cell^2
+                for (int dy = 0; dy < g.cell; ++dy) {
+                    const int rowoff = (g.top + oi * g.cell + dy) * row_bytes + (g.left + oj * g.cell) * g.c + ch;
+                    for (int dx = 0; dx < g.cell; ++dx) {
+                        const float a = lut[(int)nxt[rowoff + dx * g.c] * 32 + lane];
+                        const float b = lut[(int)cur[rowoff + dx * g.c] * 32 + lane];
+                        acc = __fadd_rn(acc, fabsf(__fsub_rn(a, b)));
+                    }
+                }
+                chan_sum = __fadd_rn(chan_sum, __fdiv_rn(acc, (float)(g.cell * g.cell)));
+            }
+            out[((int64_t)env * t + k) * cells + cidx] = __fdiv_rn(chan_sum, (float)g.c);  // mean over channels
+        }
+        __syncthreads();
+        uint8_t *tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+    }
+}
+
+// CTA per gathered frame: out[m][c][out_h][out_w] = avg_pool(crop(frame / 255))
+__global__ void __launch_bounds__(256) vn_aux_target_kernel(const vn_store_t store, int plane,
+                                                            const int32_t *__restrict__ idx, int m, PoolGeom g,
+                                                            float *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int fbytes = g.h * g.w * g.c;
+    float *lut = reinterpret_cast<float *>(smem_raw);
+    uint8_t *frame = smem_raw + 256 * 32 * sizeof(float);
+    const int lane = threadIdx.x & 31;
+    build_lut(lut);
+    const int cells = g.out_h * g.out_w;
+    const int row_bytes = g.w * g.c;
+    for (int f = blockIdx.x; f < m; f += gridDim.x) {
+        __syncthreads();
+        load_frame(frame, store.base + store.plane_off[plane] + (size_t)idx[f] * store.state_pitch, fbytes);
+        __syncthreads();
+        for (int o = threadIdx.x; o < cells * g.c; o += blockDim.x) {
+            const int ch = o / cells, cidx = o - ch * cells;
+            const int oi = cidx / g.out_w, oj = cidx - oi * g.out_w;
+            float acc = 0.f;
+            for (int dy = 0; dy < g.cell; ++dy) {
+                const int rowoff = (g.top + oi * g.cell + dy) * row_bytes + (g.left + oj * g.cell) * g.c + ch;
+                for (int dx = 0; dx < g.cell; ++dx) acc = __fadd_rn(acc, lut[(int)frame[rowoff + dx * g.c] * 32 + lane]);
+            }
+            out[(int64_t)f * cells * g.c + o] = __fdiv_rn(acc, (float)(g.cell * g.cell));
+        }
+    }
+}
+
+// gather + TransposeImage + ScaledFloatFrame: out[i][c][h][w] = float(frame[h][w][c]) / 255
+__global__ void __launch_bounds__(256) vn_gather_f32_chw_kernel(const vn_store_t store, int plane,
+                                                                const int32_t *__restrict__ idx, int n, int h, int w,
+                                                                int c, float *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int fbytes = h * w * c;
+    const int hw = h * w;
+    for (int f = blockIdx.x; f < n; f += gridDim.x) {
+        __syncthreads();
+        load_frame(smem_raw, store.base + store.plane_off[plane] + (size_t)idx[f] * store.state_pitch, fbytes);
+        __syncthreads();
+        float *o = out + (int64_t)f * fbytes;
+        for (int k = threadIdx.x; k < fbytes; k += blockDim.x) {  // k indexes the CHW output: coalesced stores
+            const int ch = k / hw, px = k - ch * hw;
+            o[k] = __fdiv_rn((float)smem_raw[px * c + ch], 255.0f);
+        }
+    }
+}
+
+// =====================================================================================================
+// reward-prediction labels + order-preserving compaction of zero / non-zero positions
+// =====================================================================================================
+constexpr int kRpBlock = 1024;
+
+__global__ void __launch_bounds__(kRpBlock) vn_rp_count_kernel(const float *__restrict__ reward, int n,
+                                                               int8_t *__restrict__ labels,
+                                                               int32_t *__restrict__ block_counts) {
+    __shared__ int warp_nz[kRpBlock / 32];
+    const int i = blockIdx.x * kRpBlock + threadIdx.x;
+    const float r = i < n ? reward[i] : 0.f;
+    const bool nz = i < n && r != 0.f;
+    if (i < n && labels) labels[i] = r > 0.f ? 1 : (r < 0.f ? 2 : 0);
+    const unsigned b = __ballot_sync(0xffffffffu, nz);
+    if ((threadIdx.x & 31) == 0) warp_nz[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < kRpBlock / 32; ++k) s += warp_nz[k];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+// exclusive scan of the per-block non-zero counts (single block; blocks <= 2^24 / 1024 = 16384)
+__global__ void __launch_bounds__(1024) vn_rp_scan_kernel(int32_t *__restrict__ block_counts, int blocks, int n,
+                                                          int32_t *__restrict__ counts) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < blocks; base += 1024) {
+        const int k = base + threadIdx.x;
+        const int v = k < blocks ? block_counts[k] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int wv = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, wv, o);
+                if (lane >= o) wv += y;
+            }
+            warp_tot[lane] = wv;
+        }
+        __syncthreads();
+        const int incl = x + (wid ? warp_tot[wid - 1] : 0);
+        if (k < blocks) block_counts[k] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && counts) {
+        counts[1] = carry;
+        counts[0] = n - carry;
+    }
+}
+
+__global__ void __launch_bounds__(kRpBlock) vn_rp_scatter_kernel(const float *__restrict__ reward, int n,
+                                                                 const int32_t *__restrict__ block_offsets,
+                                                                 int32_t *__restrict__ zero_idx,
+                                                                 int32_t *__restrict__ nonzero_idx) {
+    __shared__ int warp_nz[kRpBlock / 32];
+    const int i = blockIdx.x * kRpBlock + threadIdx.x;
+    const bool valid = i < n;
+    const bool nz = valid && reward[i] != 0.f;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned b = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) warp_nz[wid] = __popc(b);
+    __syncthreads();
+    int before = 0;  // non-zeros in earlier warps of this block
+    for (int k = 0; k < wid; ++k) before += warp_nz[k];
+    const int nz_rank = block_offsets[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
+    if (!valid) return;
+    if (nz) {
+        if (nonzero_idx) nonzero_idx[nz_rank] = i;
+    } else if (zero_idx) {
+        zero_idx[i - nz_rank] = i;  // zeros before i = i - (non-zeros before i)
+    }
+}
+
+static int32_t pool_geom(int h, int w, int c, int cell, int out_h, int out_w, PoolGeom *g) {
+    VN_REQUIRE(h > 0 && w > 0 && c > 0 && cell > 0 && out_h > 0 && out_w > 0, "pool: bad geometry");
+    VN_REQUIRE(out_h * cell <= h && out_w * cell <= w, "pool: output %dx%d * cell %d exceeds frame %dx%d", out_h,
+               out_w, cell, h, w);
+    g->h = h;
+    g->w = w;
+    g->c = c;
+    g->cell = cell;
+    g->out_h = out_h;
+    g->out_w = out_w;
+    g->top = (h - out_h * cell) / 2;   // autocrop_observations: centred, top margin (H - H') // 2
+    g->left = (w - out_w * cell) / 2;
+    return VN_OK;
+}
+
+}  // namespace vn
+
+extern "C" {
+
+int32_t vn_nstep_returns(const float *reward, const uint8_t *done, const float *last_value, float gamma, int32_t n,
+                         int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream) {
+    VN_REQUIRE(reward && done && last_value && out, "nstep_returns: null pointer");
+    VN_REQUIRE(n >= 0 && t >= 1, "nstep_returns: n=%d t=%d", n, t);
+    if (n == 0) return VN_OK;
+    vn::vn_nstep_returns_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reward, done, last_value, gamma, n, t, stride_n, stride_t, out);
+    return vn::check_launch("vn_nstep_returns_kernel");
+}
+
+int32_t vn_discounted_backup(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,
+                             int32_t n, int32_t t, int32_t d, float *out, void *stream) {
+    VN_REQUIRE(reward && done && bootstrap && out, "discounted_backup: null pointer");
+    VN_REQUIRE(n >= 0 && t >= 1 && d >= 1, "discounted_backup: n=%d t=%d d=%d", n, t, d);
+    if (n == 0) return VN_OK;
+    const int64_t total = (int64_t)n * d;
+    vn::vn_backup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reward, done, bootstrap, gamma, n, t, d, out);
+    return vn::check_launch("vn_backup_kernel");
+}
+
+static int32_t check_plane(const vn_store_t *store, int32_t plane, int h, int w, int c, const char *who) {
+    VN_REQUIRE(store && store->base, "%s: store is null", who);
+    VN_REQUIRE(plane >= 0 && plane < store->n_planes, "%s: plane=%d", who, plane);
+    VN_REQUIRE(store->plane_bytes[plane] == h * w * c, "%s: plane holds %d bytes, geometry says %d", who,
+               store->plane_bytes[plane], h * w * c);
+    VN_REQUIRE((store->plane_bytes[plane] & 15) == 0 && (store->state_pitch & 15) == 0 &&
+                   (store->plane_off[plane] & 15) == 0,
+               "%s: store is not 16-byte aligned", who);
+    return VN_OK;
+}
+
+int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
+                         int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out,
+                         void *stream) {
+    int32_t rc = check_plane(store, plane, h, w, c, "pixel_control");
+    if (rc) return rc;
+    VN_REQUIRE(states && out && n >= 0 && t >= 1, "pixel_control: bad arguments");
+    vn::PoolGeom g;
+    rc = vn::pool_geom(h, w, c, cell, out_h, out_w, &g);
+    if (rc) return rc;
+    if (n == 0) return VN_OK;
+    constexpr int kChunk = 16;
+    const int fb = (h * w * c + 15) & ~15;
+    const int smem = 256 * 32 * 4 + 2 * fb;
+    VN_REQUIRE(smem <= 220 * 1024, "pixel_control: frame too large for shared memory");
+    static int configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(vn::vn_pixel_control_kernel<kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = smem;
+    }
+    const int64_t blocks = (int64_t)n * ((t + kChunk - 1) / kChunk);
+    VN_REQUIRE(blocks < (1ll << 31), "pixel_control: too many blocks");
+    vn::vn_pixel_control_kernel<kChunk><<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        *store, plane, states, n, t, g, out);
+    return vn::check_launch("vn_pixel_control_kernel");
+}
+
+int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t m, int32_t h, int32_t w,
+                      int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out, void *stream) {
+    int32_t rc = check_plane(store, plane, h, w, c, "aux_target");
+    if (rc) return rc;
+    VN_REQUIRE(idx && out && m >= 0, "aux_target: bad arguments");
+    vn::PoolGeom g;
+    rc = vn::pool_geom(h, w, c, cell, out_h, out_w, &g);
+    if (rc) return rc;
+    if (m == 0) return VN_OK;
+    const int smem = 256 * 32 * 4 + ((h * w * c + 15) & ~15);
+    VN_REQUIRE(smem <= 220 * 1024, "aux_target: frame too large for shared memory");
+    static int configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(vn::vn_aux_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = smem;
+    }
+    const int grid = m < 148 * 8 ? m : 148 * 8;
+    vn::vn_aux_target_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, m, g, out);
+    return vn::check_launch("vn_aux_target_kernel");
+}
+
+int32_t vn_gather_plane_f32_chw(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, int32_t h,
+                                int32_t w, int32_t c, float *out, void *stream) {
+    int32_t rc = check_plane(store, plane, h, w, c, "gather_plane_f32_chw");
+    if (rc) return rc;
+    VN_REQUIRE(idx && out && n >= 0, "gather_plane_f32_chw: bad arguments");
+    if (n == 0) return VN_OK;
+    const int smem = (h * w * c + 15) & ~15;
+    VN_REQUIRE(smem <= 220 * 1024, "gather_plane_f32_chw: frame too large for shared memory");
+    static int configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(vn::vn_gather_f32_chw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = smem;
+    }
+    const int grid = n < 148 * 8 ? n : 148 * 8;
+    vn::vn_gather_f32_chw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, n, h, w,
+                                                                                        c, out);
+    return vn::check_launch("vn_gather_f32_chw_kernel");
+}
+
+int32_t vn_rp_labels(const float *reward, int32_t n, int8_t *labels, int32_t *zero_idx, int32_t *nonzero_idx,
+                     int32_t *counts, int32_t *scratch, void *stream) {
+    VN_REQUIRE(reward && scratch, "rp_labels: reward and scratch are required");
+    VN_REQUIRE(n >= 0 && n <= (1 << 24), "rp_labels: n=%d (max 2^24 per call)", n);
+    if (n == 0) return VN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (n + vn::kRpBlock - 1) / vn::kRpBlock;
+    vn::vn_rp_count_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, labels, scratch);
+    vn::vn_rp_scan_kernel<<<1, 1024, 0, st>>>(scratch, blocks, n, counts);
+    if (zero_idx || nonzero_idx)
+        vn::vn_rp_scatter_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, scratch, zero_idx, nonzero_idx);
+    return vn::check_launch("vn_rp_labels");
+}
+
+}  // extern "C"

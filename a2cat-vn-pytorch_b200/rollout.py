@@ -1,0 +1,182 @@
+"""Rollout buffer and return / auxiliary-target builders on the device.
+
+Host-side mirror of what the reference gets from deep_rl (un-vendored) and from
+experiments/ai2_auxiliary/trainer.py: every function takes / returns CUDA tensors and calls one
+C-ABI entry point of libvn_b200.so.  Batch-major ``[B, T, ...]`` like the reference tensors.
+
+The rollout buffer stores STATE INDICES, not frames: a 128-step rollout of 8,192 envs is 4 MB of
+int32 instead of 22 GB of uint8 frames, and the target builders re-gather the frames they need from
+the HBM store (which mostly sits in the 126 MB L2).
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from .store import DeviceWorld
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def nstep_returns(rewards, dones, last_values, gamma, time_major=False):
+    """A2C n-step returns (deep_rl RolloutStorage.batch).
+    rewards float32, dones uint8/bool: [B, T] (or [T, B] with time_major=True); last_values [B]."""
+    lib = L.load()
+    rewards = rewards.contiguous().float()
+    dones = dones.contiguous().to(torch.uint8)
+    last_values = last_values.contiguous().float()
+    if time_major:
+        t, n = rewards.shape
+        sn, st = 1, n
+    else:
+        n, t = rewards.shape
+        sn, st = t, 1
+    out = torch.empty_like(rewards)
+    with torch.cuda.device(rewards.device):
+        L.check(lib.vn_nstep_returns(rewards.data_ptr(), dones.data_ptr(), last_values.data_ptr(), float(gamma), n, t,
+                                     sn, st, out.data_ptr(), _stream(rewards)))
+    return out
+
+
+def discounted_backup(rewards, dones, bootstrap, gamma):
+    """rewards [B, T, ...]; dones [B, T]; bootstrap [B, ...] -> R_t = r_t + gamma (1 - done_t) R_{t+1}."""
+    lib = L.load()
+    b, t = rewards.shape[:2]
+    d = rewards[0, 0].numel()
+    rewards = rewards.contiguous().float()
+    dones = dones.contiguous().to(torch.uint8)
+    bootstrap = bootstrap.contiguous().float()
+    out = torch.empty_like(rewards)
+    with torch.cuda.device(rewards.device):
+        L.check(lib.vn_discounted_backup(rewards.data_ptr(), dones.data_ptr(), bootstrap.data_ptr(), float(gamma), b, t,
+                                         d, out.data_ptr(), _stream(rewards)))
+    return out
+
+
+def _geom(dw, plane, cell, output_size):
+    lay = dw.world.layout
+    pi = dw.plane_index(plane)
+    h, w = lay.frame_hw
+    c = lay.plane_bytes[pi] // (h * w)
+    if output_size is None:
+        output_size = (h // cell, w // cell)
+    return pi, h, w, c, int(output_size[0]), int(output_size[1])
+
+
+def pixel_control_reward(dw: DeviceWorld, states, cell_size=4, output_size=None, plane="rgb"):
+    """deep_rl.a2c_unreal.util.pixel_control_reward computed from state indices.
+    states: int32 [B, T+1] GLOBAL state of every observation of the sequence -> float32 [B, T, 1, h, w]."""
+    lib = L.load()
+    pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
+    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
+    b, t1 = states.shape
+    out = torch.empty((b, t1 - 1, 1, oh, ow), dtype=torch.float32, device=dw.device)
+    with torch.cuda.device(dw.device):
+        L.check(lib.vn_pixel_control(C.byref(dw.store), pi, states.data_ptr(), b, t1 - 1, h, w, c, cell_size, oh, ow,
+                                     out.data_ptr(), _stream(states)))
+    return out
+
+
+def auxiliary_target(dw: DeviceWorld, states, plane, cell_size=4, output_size=None):
+    """compute_auxiliary_target (experiments/ai2_auxiliary/trainer.py:9-15) from state indices.
+    states int32 [B, T] -> float32 [B, T, C, h, w]."""
+    lib = L.load()
+    pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
+    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
+    shape = tuple(states.shape)
+    out = torch.empty(shape + (c, oh, ow), dtype=torch.float32, device=dw.device)
+    with torch.cuda.device(dw.device):
+        L.check(lib.vn_aux_target(C.byref(dw.store), pi, states.data_ptr(), states.numel(), h, w, c, cell_size, oh, ow,
+                                  out.data_ptr(), _stream(states)))
+    return out
+
+
+def auxiliary_targets(dw, states, goal_states, cell_size=4, output_size=None):
+    """compute_auxiliary_targets (trainer.py:17-19): targets for observation leaves 2.. of the aux5
+    tuple = (depth, segmentation, goal_segmentation)."""
+    return (auxiliary_target(dw, states, "depth", cell_size, output_size),
+            auxiliary_target(dw, states, "segmentation", cell_size, output_size),
+            auxiliary_target(dw, goal_states, "segmentation", cell_size, output_size))
+
+
+def policy_input(dw: DeviceWorld, states, plane="rgb"):
+    """TransposeImage + ScaledFloatFrame fused with the gather: float32 [..., C, H, W] in [0, 1]."""
+    lib = L.load()
+    pi, h, w, c, _, _ = _geom(dw, plane, 1, None)
+    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
+    out = torch.empty(tuple(states.shape) + (c, h, w), dtype=torch.float32, device=dw.device)
+    with torch.cuda.device(dw.device):
+        L.check(lib.vn_gather_plane_f32_chw(C.byref(dw.store), pi, states.data_ptr(), states.numel(), h, w, c,
+                                            out.data_ptr(), _stream(states)))
+    return out
+
+
+def reward_prediction_labels(rewards, with_lists=True):
+    """UNREAL reward-prediction classes (0 zero / 1 positive / 2 negative) and the ascending lists of
+    zero / non-zero reward positions (flattened) that the 50/50 sampler draws from.
+    Returns (labels int8 like rewards, zero_idx int32, nonzero_idx int32); the lists are device tensors
+    trimmed to their lengths (one 8-byte D2H read for the two counts)."""
+    lib = L.load()
+    r = rewards.contiguous().float()
+    n = r.numel()
+    labels = torch.empty(r.shape, dtype=torch.int8, device=r.device)
+    scratch = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int32, device=r.device)
+    counts = torch.zeros(2, dtype=torch.int32, device=r.device)
+    zero = torch.empty(n, dtype=torch.int32, device=r.device) if with_lists else None
+    nonzero = torch.empty(n, dtype=torch.int32, device=r.device) if with_lists else None
+    with torch.cuda.device(r.device):
+        L.check(lib.vn_rp_labels(r.data_ptr(), n, labels.data_ptr(), L.ptr(zero), L.ptr(nonzero), counts.data_ptr(),
+                                 scratch.data_ptr(), _stream(r)))
+    if not with_lists:
+        return labels, None, None
+    cz, cn = counts.tolist()
+    return labels, zero[:cz], nonzero[:cn]
+
+
+class RolloutBuffer:
+    """Device-resident rollout of T steps x B envs: int32 states / goals, float32 rewards, uint8 dones,
+    int32 actions; time-major storage (each env step appends one contiguous row), batch-major views
+    handed to the builders."""
+
+    def __init__(self, dw: DeviceWorld, num_envs, num_steps):
+        self.dw, self.B, self.T = dw, num_envs, num_steps
+        dev = dw.device
+        self.states = torch.zeros((num_steps + 1, num_envs), dtype=torch.int32, device=dev)
+        self.goals = torch.zeros((num_steps + 1, num_envs), dtype=torch.int32, device=dev)
+        self.rewards = torch.zeros((num_steps, num_envs), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((num_steps, num_envs), dtype=torch.uint8, device=dev)
+        self.actions = torch.zeros((num_steps, num_envs), dtype=torch.int32, device=dev)
+        self.t = 0
+
+    def start(self, env):
+        """Records the observation the rollout starts from (after reset() or the previous rollout)."""
+        self.states[0].copy_(env.obs_state)
+        self.goals[0].copy_(env.goal)
+        self.t = 0
+
+    def insert(self, env, actions):
+        """Call after env.step(actions): appends (action, reward, done) and the NEXT observation's state."""
+        t = self.t
+        self.actions[t].copy_(actions.to(torch.int32) if torch.is_tensor(actions) else torch.as_tensor(actions))
+        self.rewards[t].copy_(env.reward)
+        self.dones[t].copy_(env.done)
+        self.states[t + 1].copy_(env.obs_state)
+        self.goals[t + 1].copy_(env.goal)
+        self.t = t + 1
+
+    def returns(self, last_values, gamma):
+        """[B, T] n-step returns."""
+        return nstep_returns(self.rewards, self.dones, last_values, gamma, time_major=True).t().contiguous()
+
+    def pixel_control(self, cell_size=4, output_size=None):
+        return pixel_control_reward(self.dw, self.states.t().contiguous(), cell_size, output_size)
+
+    def auxiliary_targets(self, cell_size=4, output_size=None):
+        s = self.states[:-1].t().contiguous()
+        g = self.goals[:-1].t().contiguous()
+        return auxiliary_targets(self.dw, s, g, cell_size, output_size)
+
+    def reward_prediction(self):
+        return reward_prediction_labels(self.rewards.t().contiguous())

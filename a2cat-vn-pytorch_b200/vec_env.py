@@ -1,0 +1,406 @@
+"""Drop-in vectorised environment: the reference's gym ``Env`` / baselines-style ``VecEnv`` surface
+over the CUDA hot path.
+
+Reference surface kept:
+  * ``reset() -> obs``; ``step(actions) -> (obs, rewards, dones, infos)``; ``step_async`` /
+    ``step_wait``; ``close()``; ``num_envs``; ``observation_space``; ``action_space.n == 4``
+    (deep_rl SubprocVecEnv as used at experiments/thor_cached_auxiliary.py:58-71);
+  * ``call_unwrapped('set_complexity', c)`` and ``set_hardness`` (thor_cached_auxiliary.py:68-70);
+  * observation layouts: ``((rgb, goal_rgb, depth, seg, goal_seg), last_action_reward)``
+    (gym_graph/graph.py:117-120 + UnrealEnvBaseWrapper), a bare frame (gym_graph/graph.py:56-58),
+    ``(obs, goal)`` (gym_ai2thor/envs/cached.py:53-57) or ``{'image','goal'}`` (gym_thor_cached.py:89-92);
+  * ``info`` keys ``state``, ``win`` (gym_graph/graph.py:72-79), ``episode`` (RewardCollector),
+    ``TimeLimit.truncated`` (gym TimeLimit).
+
+What changes: observations are ``uint8`` CUDA tensors (views of persistent batch buffers that the
+next ``step`` overwrites) instead of pickled float32 numpy arrays; the goal leaves are rewritten only
+for envs that reset; all envs advance in two kernel launches.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+from . import spaces
+from .store import DeviceWorld
+from .tables import World, Family
+
+#: named observation layouts -> leaves.  A leaf is a store plane ("rgb", "depth", "segmentation") or the
+#: same plane of the goal state ("goal_rgb", "goal_segmentation").
+OBS_LAYOUTS = {
+    # GoalGymGraphAuxiliaryEnv.observe, environments/gym_graph/graph.py:117-120
+    "aux5": ("rgb", "goal_rgb", "depth", "segmentation", "goal_segmentation"),
+    # OrientedGraphEnv.observe, environments/gym_graph/graph.py:56-58 (also graph/env.py envs)
+    "frame": "rgb",
+    # THORDiscreteCachedEnv, environments/gym_ai2thor/envs/cached.py:53-57
+    "pair": ("rgb", "goal_rgb"),
+    # THORCachedEnv.process, environments/gym_thor_cached.py:89-92
+    "dict": {"image": "rgb", "goal": "goal_rgb"},
+    # BASELINE.json configs[1]: "84x84 RGB+depth+goal"
+    "rgbd_goal": ("rgb", "goal_rgb", "depth"),
+}
+
+
+def resolve_layout(layout):
+    if isinstance(layout, str):
+        if layout not in OBS_LAYOUTS:
+            raise ValueError("obs_layout must be one of %s or a tuple / dict of leaves" % (sorted(OBS_LAYOUTS),))
+        return OBS_LAYOUTS[layout]
+    return layout
+
+
+def shard_range(num_envs_total, rank=0, world_size=1):
+    """Envs [lo, hi) owned by ``rank``: contiguous, sizes differ by at most one."""
+    base, rem = divmod(num_envs_total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class LazyInfos:
+    """``infos`` of one step.  Behaves like the tuple of dicts the reference VecEnv returns, built from
+    the packed per-env info arrays only when an element is read (host_outputs=False: the arrays are
+    fetched from the device on first access and are valid until the next step)."""
+
+    def __init__(self, env, arrays, noop):
+        self._env, self._a, self._noop = env, arrays, noop
+
+    def __len__(self):
+        return self._env.num_envs
+
+    def _host(self):
+        if callable(self._a):
+            self._a = self._a()
+        if torch.is_tensor(self._noop):
+            self._noop = self._noop.cpu().numpy()
+        return self._a
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        h = self._host()
+        env = self._env
+        info = {}
+        graph_family = env.family.name != "thor_cached"        # cached.py:99 returns an empty dict
+        if graph_family and not (env.family.noop_action and self._noop is not None and self._noop[i]):
+            info["state"] = env.world.state_tuple(int(h["info_state"][i]))     # gym_graph/graph.py:72-79
+        if graph_family and h["win"][i]:
+            info["win"] = True
+        if h["truncated"][i]:                                   # gym TimeLimit: key exists only at the limit
+            info["TimeLimit.truncated"] = bool(h["truncated"][i] == 1)
+        if h["done"][i]:                                        # RewardCollector
+            info["episode"] = dict(r=float(h["episode_return"][i]), l=int(h["episode_length"][i]))
+        return info
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class GraphVecEnv:
+    def __init__(self, world, num_envs, *, device="cuda", seed=0, max_episode_steps=900, rewards=(1.0, 0.0, 0.0),
+                 obs_layout="aux5", unreal_wrapper=True, env_tasks=None, auto_reset=True, rank=0, world_size=1,
+                 gather="auto", inject=None, host_outputs=True, device_world=None):
+        """
+        world            tables.World (compiled scenes) - or pass a ready ``device_world``
+        num_envs         TOTAL number of envs of the job; this process owns shard_range(num_envs, rank, world_size)
+        env_tasks        per GLOBAL env (lo, count) range into world.tasks (default: env i owns all tasks
+                         of scene i % n_scenes ... see _default_env_tasks)
+        inject           optional (task [n_local, R] int32, start [n_local, R] int32 GLOBAL states) reset stream
+        host_outputs     rewards / dones as numpy (reference behaviour) or as CUDA tensors
+        """
+        self.dw = device_world if device_world is not None else DeviceWorld(world, device)
+        self.world: World = self.dw.world
+        self.family: Family = self.world.family
+        self.lib = self.dw.lib
+        self.device = self.dw.device
+        self.rank, self.world_size = rank, world_size
+        self.num_envs_total = num_envs
+        lo, hi = shard_range(num_envs, rank, world_size)
+        self.env_lo, self.num_envs = lo, hi - lo
+        n = self.num_envs
+        self.max_episode_steps = int(max_episode_steps or 0)
+        self.obs_layout = obs_layout
+        self.unreal_wrapper = unreal_wrapper
+        self.host_outputs = host_outputs
+        self.n_actions = 4
+        self.gather = {"auto": L.GATHER_AUTO, "ldg": L.GATHER_LDG, "bulk": L.GATHER_BULK}[gather]
+        lay = self.world.layout
+        self.leaves = resolve_layout(obs_layout)
+        names = self.leaves.values() if isinstance(self.leaves, dict) else \
+            (self.leaves if isinstance(self.leaves, tuple) else (self.leaves,))
+        self.obs_planes = tuple(dict.fromkeys(x for x in names if not x.startswith("goal_")))
+        self.goal_planes = tuple(dict.fromkeys(x[5:] for x in names if x.startswith("goal_")))
+        for p in self.obs_planes + self.goal_planes:
+            if p not in lay.planes:
+                raise ValueError("obs_layout %r needs plane %r in the store (has %s)" % (obs_layout, p, lay.planes))
+
+        tasks = self._default_env_tasks(num_envs) if env_tasks is None else np.asarray(env_tasks, np.int32)
+        if tasks.shape != (num_envs, 2):
+            raise ValueError("env_tasks must be [num_envs, 2] (lo, count)")
+        if (tasks[:, 1] < 1).any() or (tasks[:, 0] < 0).any() or (tasks.sum(1) > len(self.world.tasks)).any():
+            raise ValueError("env_tasks ranges fall outside the task table")
+        tasks = tasks[lo:hi]
+
+        h, w = lay.frame_hw
+        with torch.cuda.device(self.device):
+            i32 = lambda: torch.zeros(n, dtype=torch.int32, device=self.device)
+            self.state, self.goal, self.task, self.elapsed, self.ep_length = i32(), i32(), i32(), i32(), i32()
+            self.epoch = i32()      # uint32 on the device side, same bits
+            self.ep_return = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.task_lo = torch.from_numpy(np.ascontiguousarray(tasks[:, 0])).to(self.device)
+            self.task_cnt = torch.from_numpy(np.ascontiguousarray(tasks[:, 1])).to(self.device)
+            # per-env scalars the host reads every step, packed so ONE D2H copy returns them:
+            # reward f32 | episode_return f32 | episode_length i32 | info_state i32 | done | truncated | win | did_reset
+            self._pack = torch.zeros(n * 20, dtype=torch.uint8, device=self.device)
+            self.reward = self._pack[:4 * n].view(torch.float32)
+            self.episode_return = self._pack[4 * n:8 * n].view(torch.float32)
+            self.episode_length = self._pack[8 * n:12 * n].view(torch.int32)
+            self.info_state = self._pack[12 * n:16 * n].view(torch.int32)
+            self.done = self._pack[16 * n:17 * n]
+            self.truncated = self._pack[17 * n:18 * n]
+            self.win = self._pack[18 * n:19 * n]
+            self.did_reset = self._pack[19 * n:20 * n]
+            self.lar = torch.zeros((n, self.n_actions + 1), dtype=torch.float32, device=self.device)
+            self.obs_state = i32()
+            self.stats = torch.zeros(L.VN_N_STATS, dtype=torch.int64, device=self.device)
+            self.actions_dev = i32()
+            self.obs_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
+                                           dtype=torch.uint8, device=self.device) for p in self.obs_planes}
+            self.goal_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
+                                            dtype=torch.uint8, device=self.device) for p in self.goal_planes}
+            self._pack_host = torch.zeros(n * 20, dtype=torch.uint8).pin_memory()
+            self._actions_host = torch.zeros(n, dtype=torch.int32).pin_memory()
+        self._inject_keep = None
+        self._c_inject = None
+        if inject is not None:
+            self.set_inject(*inject)
+
+        self._c_envs = L.Envs(n, lo, *(t.data_ptr() for t in (self.state, self.goal, self.task, self.elapsed,
+                                                              self.epoch, self.ep_return, self.ep_length,
+                                                              self.task_lo, self.task_cnt)))
+        fam = self.family
+        flags = 0
+        flags |= L.RULE_COLLISION_SKIPS_GOAL if fam.collision_skips_goal else 0
+        flags |= L.RULE_NEG_STEP_REWARD if fam.neg_step_reward else 0
+        flags |= L.RULE_COLLISION_OVERRIDES if fam.collision_overrides else 0
+        flags |= L.RULE_TERM_PREV_OBS if fam.term_prev_obs else 0
+        flags |= L.RULE_TWO_LEVEL if fam.two_level_sampling else 0
+        flags |= L.RULE_NOOP_ACTION if fam.noop_action else 0
+        flags |= L.RULE_AUTO_RESET if auto_reset else 0
+        self._c_rules = L.Rules(float(rewards[0]), float(rewards[1]), float(rewards[2]), self.max_episode_steps,
+                                fam.goal_compare, flags, self.n_actions, 0, C.c_uint64(seed & (2 ** 64 - 1)))
+        out = L.StepOut()
+        for i, p in enumerate(lay.planes):
+            out.obs[i] = self.obs_buf[p].data_ptr() if p in self.obs_buf else None
+            out.goal_obs[i] = self.goal_buf[p].data_ptr() if p in self.goal_buf else None
+        out.reward, out.done, out.truncated = self.reward.data_ptr(), self.done.data_ptr(), self.truncated.data_ptr()
+        out.win, out.did_reset = self.win.data_ptr(), self.did_reset.data_ptr()
+        out.last_action_reward = self.lar.data_ptr()
+        out.episode_return, out.episode_length = self.episode_return.data_ptr(), self.episode_length.data_ptr()
+        out.info_state, out.obs_state, out.stats = self.info_state.data_ptr(), self.obs_state.data_ptr(), self.stats.data_ptr()
+        self._c_out = out
+
+        def frame(leaf):
+            p = leaf[5:] if leaf.startswith("goal_") else leaf
+            return spaces.Box(0, 255, (h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)), np.uint8)
+
+        if isinstance(self.leaves, dict):
+            inner = spaces.Dict({k: frame(v) for k, v in self.leaves.items()})
+        elif isinstance(self.leaves, tuple):
+            inner = spaces.Tuple(tuple(frame(v) for v in self.leaves))
+        else:
+            inner = frame(self.leaves)
+        self.observation_space = spaces.Tuple((inner, spaces.Box(0.0, 1.0, (self.n_actions + 1,), np.float32))) \
+            if unreal_wrapper else inner
+        self.action_space = spaces.Discrete(self.n_actions)
+        self.set_hardness = self.set_complexity     # experiments/thor_cached_auxiliary.py:68
+        self._pending = False
+        self.closed = False
+        self.kernel_launches = 0
+
+    # ------------------------------------------------------------------ construction helpers
+    def _default_env_tasks(self, num_envs):
+        """Reference create_envs builds one env per (scene, goal) task (thor_cached_auxiliary.py:66);
+        with more envs than tasks the tasks are dealt round-robin, each env owning ONE task.  Families
+        whose env samples its task on reset (MultipleGraphEnv, THORCachedEnv task lists) should pass
+        ``env_tasks`` explicitly."""
+        t = len(self.world.tasks)
+        lo = np.arange(num_envs, dtype=np.int32) % t
+        return np.stack([lo, np.ones(num_envs, np.int32)], 1)
+
+    def set_inject(self, task, start):
+        """Injected reset stream for parity runs: [n_local, R] task offsets (relative to the env's task
+        range) and GLOBAL start states; reset k of env i consumes column k."""
+        task = torch.as_tensor(np.ascontiguousarray(task, dtype=np.int32)).to(self.device)
+        start = torch.as_tensor(np.ascontiguousarray(start, dtype=np.int32)).to(self.device)
+        assert task.shape == start.shape and task.shape[0] == self.num_envs
+        self._inject_keep = (task, start)
+        self._c_inject = L.Inject(task.data_ptr(), start.data_ptr(), task.shape[1], 0)
+
+    # ------------------------------------------------------------------ reference surface
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _leaf(self, name):
+        return self.goal_buf[name[5:]] if name.startswith("goal_") else self.obs_buf[name]
+
+    def _obs(self):
+        lv = self.leaves
+        if isinstance(lv, dict):
+            inner = {k: self._leaf(v) for k, v in lv.items()}
+        elif isinstance(lv, tuple):
+            inner = tuple(self._leaf(v) for v in lv)
+        else:
+            inner = self._leaf(lv)
+        return (inner, self.lar) if self.unreal_wrapper else inner
+
+    def reset(self, mask=None):
+        """(Re)starts every env (or the masked ones) and returns the stacked observation."""
+        self._check_open()
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.vn_env_reset(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
+                                          C.byref(self._c_rules),
+                                          C.byref(self._c_inject) if self._c_inject is not None else None,
+                                          L.ptr(m), C.byref(self._c_out), self.gather, self._stream()))
+        self.kernel_launches += 2
+        return self._obs()
+
+    def step_async(self, actions):
+        self._check_open()
+        if torch.is_tensor(actions) and actions.is_cuda:
+            a = actions if actions.dtype == torch.int32 else actions.to(torch.int32)
+            a = a.contiguous()
+        else:
+            src = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
+            # baselines passes None for "no action" only to single envs; -1 is the batched spelling
+            self._actions_host.copy_(src.reshape(-1).to(torch.int32))
+            self.actions_dev.copy_(self._actions_host, non_blocking=True)
+            a = self.actions_dev
+        if a.numel() != self.num_envs:
+            raise ValueError("expected %d actions, got %d" % (self.num_envs, a.numel()))
+        self._last_actions = a
+        with torch.cuda.device(self.device):
+            L.check(self.lib.vn_env_step(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
+                                         C.byref(self._c_rules),
+                                         C.byref(self._c_inject) if self._c_inject is not None else None,
+                                         a.data_ptr(), C.byref(self._c_out), self.gather, self._stream()))
+        self.kernel_launches += 2
+        self._pending = True
+
+    def _unpack(self, host):
+        n = self.num_envs
+        return dict(reward=host[:4 * n].view(np.float32), episode_return=host[4 * n:8 * n].view(np.float32),
+                    episode_length=host[8 * n:12 * n].view(np.int32), info_state=host[12 * n:16 * n].view(np.int32),
+                    done=host[16 * n:17 * n], truncated=host[17 * n:18 * n], win=host[18 * n:19 * n],
+                    did_reset=host[19 * n:20 * n])
+
+    def step_wait(self):
+        if not self._pending:
+            raise RuntimeError("step_wait() without step_async()")
+        self._pending = False
+        noop = (self._last_actions < 0) if self.family.noop_action else None
+        if self.host_outputs:
+            # reference behaviour: rewards / dones are host numpy arrays -> one packed D2H copy + sync
+            self._pack_host.copy_(self._pack, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            h = self._unpack(self._pack_host.numpy().copy())
+            return self._obs(), h["reward"], h["done"].astype(bool), LazyInfos(self, h, noop)
+        fetch = lambda: self._unpack(self._pack.cpu().numpy())
+        return self._obs(), self.reward, self.done.bool(), LazyInfos(self, fetch, noop)
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.closed = True
+
+    def _check_open(self):
+        if self.closed:
+            raise RuntimeError("environment is closed")
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def call_unwrapped(self, name, *args, **kwargs):
+        """deep_rl SubprocVecEnv.call_unwrapped: calls a method on every (unwrapped) env; here the
+        batch is one object, so the result list repeats the single return value."""
+        r = getattr(self, name)(*args, **kwargs)
+        return [r] * self.num_envs
+
+    def set_complexity(self, complexity=None):
+        self.dw.set_complexity(complexity)
+
+    # ------------------------------------------------------------------ extras
+    def states(self):
+        """Current states as reference tuples (x, y[, r]) - host copy."""
+        return [self.world.state_tuple(int(s)) for s in self.state.cpu().numpy()]
+
+    def episode_stats(self, reduce=False, reset=False):
+        """Running device-side episode statistics.  ``reduce=True`` sums them over all ranks with ONE
+        all-reduce of 8 numbers (NCCL) - the only collective anywhere near this path."""
+        v = self.stats.clone()
+        vals = v.cpu().numpy().copy()
+        out = np.zeros(L.VN_N_STATS, np.float64)
+        for i, name in enumerate(L.STAT_NAMES):
+            out[i] = vals[i:i + 1].view(np.float64)[0] if name == "return_sum" else float(vals[i])
+        if reduce and self.world_size > 1:
+            out = reduce_stats(out, self.device)
+        if reset:
+            self.stats.zero_()
+        return dict(zip(L.STAT_NAMES, out.tolist()))
+
+    def state_dict(self):
+        keys = ("state", "goal", "task", "elapsed", "epoch", "ep_return", "ep_length", "stats")
+        d = {k: getattr(self, k).cpu().clone() for k in keys}
+        d["complexity"] = self.dw.complexity
+        return d
+
+    def load_state_dict(self, d):
+        for k in ("state", "goal", "task", "elapsed", "epoch", "ep_return", "ep_length", "stats"):
+            getattr(self, k).copy_(d[k].to(self.device))
+        self.set_complexity(d.get("complexity"))
+        # refresh observation / goal batches for the restored states
+        self.gather_current()
+
+    def gather_current(self):
+        """Re-gathers observation and goal planes for the current states (after load_state_dict)."""
+        for p, buf in self.obs_buf.items():
+            gather_plane(self.dw, p, self.state, out=buf, variant=self.gather)
+        for p, buf in self.goal_buf.items():
+            gather_plane(self.dw, p, self.goal, out=buf, variant=self.gather)
+        return self._obs()
+
+
+def gather_plane(dw: DeviceWorld, plane, idx, out=None, variant=L.GATHER_AUTO):
+    """out[i] = frame ``plane`` of state idx[i]: the batched ``ThorGridWorld.render``
+    (graph/multi_graph_no_tp.py:12-25) for an arbitrary index list (replay sampling etc.)."""
+    pi = dw.plane_index(plane)
+    lay = dw.world.layout
+    h, w = lay.frame_hw
+    idx = idx.to(device=dw.device, dtype=torch.int32).contiguous()
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n, h, w, lay.plane_bytes[pi] // (h * w)), dtype=torch.uint8, device=dw.device)
+    with torch.cuda.device(dw.device):
+        L.check(dw.lib.vn_gather_plane(C.byref(dw.store), pi, idx.data_ptr(), n, out.data_ptr(), variant,
+                                       torch.cuda.current_stream(dw.device).cuda_stream))
+    return out
+
+
+def reduce_stats(vec, device=None, group=None):
+    """Sum of the 8-number statistics vector over all ranks.  NCCL when the process group is NCCL
+    (tensor on ``device``), gloo otherwise (CPU tensor)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return vec
+    backend = dist.get_backend(group)
+    t = torch.as_tensor(np.asarray(vec, np.float64))
+    if backend == "nccl":
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()

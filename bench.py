@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py - env-steps/s of the cached-graph navigation hot path (step + reset + frame gather).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, one process per GPU)
+  python bench.py --impl reference [--steps K] [--warmup W]       # reference arm: CPU port on all host cores
+  torchrun --nproc-per-node N ... bench.py --gpus N ...           # N > 1 (the driver launches this)
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one synthetic
+thor-cached scene, 1,500 positions x 4 rotations = 6,000 states, 84x84 RGB + depth + goal frame,
+4,096 envs per GPU (weak scaling: every GPU steps its own 4,096 envs, store replicated), uniform
+random actions, TimeLimit 900, curriculum hardness 0.01 (experiments/thor_cached_auxiliary.py:70).
+One "step" = one vectorised step of all envs.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ENVS_PER_GPU = 4096
+N_CELLS, GRID = 1500, (50, 60)
+MAX_EPISODE_STEPS = 900
+HARDNESS = 0.01
+SCENE_SEED = 0
+F_RGB, F_DEPTH = 84 * 84 * 3, 84 * 84
+WORKLOAD = "C2 synthetic thor-cached scene: 1,500 positions x 4 rotations, 84x84 RGB+depth+goal, 4,096 envs per GPU"
+
+
+def make_scene(vn):
+    return vn.scenes.make_thor_scene(N_CELLS, GRID, seed=SCENE_SEED, n_goals=4, planes=("rgb", "depth"))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic():
+    """DRAM bytes per gather launch from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("gather_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------ CPU port
+_CPU = {}
+
+
+def _cpu_world(n_envs, seed):
+    """Oracle envs of the bench workload with the reference's cost profile (frames in RAM, per-reset
+    candidate enumeration).  Built once per process (workers inherit it by fork)."""
+    from oracle import envs as oenvs, vec as ovec
+    vn = importlib.import_module("a2cat-vn-pytorch_b200")
+    if "scene" not in _CPU:
+        scene = make_scene(vn)
+        _CPU["scene"] = scene
+        _CPU["osc"] = oenvs.OracleScene(scene, with_all_pairs=True, cache_frames=True)
+    scene, osc = _CPU["scene"], _CPU["osc"]
+    envs = []
+    for i in range(n_envs):
+        goal = scene.goals[i % len(scene.goals)]          # one env per (scene, goal) task, dealt round-robin
+        e = oenvs.GymGraphRgbdGoalEnv(osc, goals=goal)
+        e.set_complexity(HARDNESS)
+        e.reset_source = ovec.ReferenceStyleResetSource(osc, [goal], lambda t, e=e: e.optimal_distance(), seed + i)
+        envs.append(ovec.RewardCollector(ovec.TimeLimit(e, MAX_EPISODE_STEPS)))
+    return ovec.VecEnv(envs)
+
+
+def _cpu_worker(conn, n_envs, seed):
+    """baselines SubprocVecEnv worker protocol: step -> auto-reset -> send obs over a pipe."""
+    ve = _cpu_world(n_envs, seed)
+    while True:
+        cmd, data = conn.recv()
+        if cmd == "step":
+            conn.send(ve.step(data)[:3])
+        elif cmd == "reset":
+            conn.send(ve.reset())
+        else:
+            conn.close()
+            return
+
+
+def cpu_run(n_envs, steps, warmup, workers, seed=0):
+    """Returns (env-steps/s, resets) of the CPU port on `workers` processes."""
+    import multiprocessing as mp
+    rng = np.random.RandomState(seed)
+    if workers <= 1:
+        ve = _cpu_world(n_envs, seed)
+        ve.reset()
+        for _ in range(warmup):
+            ve.step(rng.randint(0, 4, n_envs))
+        t0 = time.perf_counter()
+        nres = 0
+        for _ in range(steps):
+            _, _, d, _ = ve.step(rng.randint(0, 4, n_envs))
+            nres += int(d.sum())
+        dt = time.perf_counter() - t0
+        return n_envs * steps / dt, nres, dt
+    _cpu_world(0, seed)                                   # build the scene before forking
+    ctx = mp.get_context("fork")
+    per = [n_envs // workers + (1 if r < n_envs % workers else 0) for r in range(workers)]
+    pipes, procs = [], []
+    for r, n in enumerate(per):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_cpu_worker, args=(b, n, seed + 100000 * r), daemon=True)
+        p.start()
+        pipes.append(a)
+        procs.append(p)
+
+    def vec(cmd, acts=None):
+        off = 0
+        for n, c in zip(per, pipes):
+            c.send((cmd, None if acts is None else acts[off:off + n]))
+            off += n
+        outs = [c.recv() for c in pipes]
+        if cmd == "reset":
+            return None
+        obs = tuple(np.concatenate([o[0][0][k] for o in outs]) for k in range(3))      # parent-side stack
+        return obs, np.concatenate([o[1] for o in outs]), np.concatenate([o[2] for o in outs])
+
+    vec("reset")
+    for _ in range(warmup):
+        vec("step", rng.randint(0, 4, n_envs))
+    t0 = time.perf_counter()
+    nres = 0
+    for _ in range(steps):
+        _, _, d = vec("step", rng.randint(0, 4, n_envs))
+        nres += int(d.sum())
+    dt = time.perf_counter() - t0
+    for c in pipes:
+        c.send(("close", None))
+    for p in procs:
+        p.join(5)
+    return n_envs * steps / dt, nres, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    n_envs = 16 * workers                     # bounded sample of the workload: 16 envs per worker
+    steps = args.steps if args.steps else 300
+    warm = args.warmup if args.warmup is not None else 5
+    value, nres, dt = cpu_run(n_envs, steps, warm, workers)
+    line = {
+        "metric": "env-steps/s (obs gather+step+reset)", "value": value, "unit": "env-steps/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d envs x %d vector steps" % (n_envs, steps)},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": workers, "kind": "port",
+                         "sample": "%d envs x %d vector steps over %d worker processes (pipes), oracle port of "
+                                   "GoalGymGraphAuxiliaryEnv incl. per-reset candidate enumeration; p_reset=%.4f"
+                                   % (n_envs, steps, workers, nres / max(1, n_envs * steps))},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    vn = importlib.import_module("a2cat-vn-pytorch_b200")
+    L = vn.lib
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    K = args.steps if args.steps else 20000
+    W = args.warmup if args.warmup is not None else 200
+    W = max(W, 3)
+
+    scene = make_scene(vn)
+    world = vn.compile_world([scene], vn.GYM_GRAPH)
+    n_total = ENVS_PER_GPU * world_size
+    env = vn.GraphVecEnv(world, n_total, device=dev, seed=1, max_episode_steps=MAX_EPISODE_STEPS,
+                         obs_layout="rgbd_goal", unreal_wrapper=True, rank=rank, world_size=world_size,
+                         gather=args.gather, host_outputs=False)
+    env.set_complexity(HARDNESS)
+    N = env.num_envs
+    # action stream resident in HBM: cyclic buffer of uniform random actions (Philox via torch generator)
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    n_rows = min(K + W, 2048)
+    actions = torch.randint(0, 4, (n_rows, N), device=dev, generator=gen, dtype=torch.int32)
+    env.reset()
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def device_loop(k0, k):
+        for i in range(k0, k0 + k):
+            env.step_async(actions[i % n_rows])
+            env._pending = False
+
+    device_loop(0, W)
+    env.stats.zero_()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = env.kernel_launches
+    ev0.record()
+    device_loop(W, K)
+    if world_size > 1:
+        # the only collective near this path: episode statistics, once per logging interval
+        stats_vec = env.stats.to(torch.float64)
+        dist.all_reduce(stats_vec)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = env.kernel_launches - launches0
+    if world_size > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    stats = env.episode_stats(reduce=True)
+    value = n_total * K / (ms * 1e-3)
+    p_reset = stats["resets"] / max(1.0, stats["steps"])
+    coll = stats["collisions"] / max(1.0, stats["steps"])
+
+    # ---- roofline of the dominant kernel (the frame gather): instrumented pass, events around K2 only
+    Kr = min(K, 500)
+    es = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kr)]
+    import ctypes as C
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    env.stats.zero_()
+    torch.cuda.synchronize(dev)
+    for i in range(Kr):
+        a = actions[(W + K + i) % n_rows]
+        L.check(env.lib.vn_env_step_scalar(C.byref(env.dw.tables), C.byref(env._c_envs), C.byref(env._c_rules), None,
+                                           a.data_ptr(), C.byref(env._c_out), stream))
+        es[i][0].record()
+        L.check(env.lib.vn_env_gather(C.byref(env.dw.store), C.byref(env._c_envs), C.byref(env._c_out), env.gather,
+                                      stream))
+        es[i][1].record()
+    torch.cuda.synchronize(dev)
+    gather_ms = float(np.mean([a.elapsed_time(b) for a, b in es]))
+    rs = env.episode_stats()
+    p_reset_r = rs["resets"] / max(1.0, rs["steps"])
+    alg_bytes = N * (2 * (F_RGB + F_DEPTH) + p_reset_r * 2 * F_RGB)
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(), "kernel": "vn_gather_%s_kernel" % args.gather_name(env),
+                "kernel_ms": gather_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "step_frac": (N * (2 * (F_RGB + F_DEPTH) + p_reset * 2 * F_RGB + 40)) / (ms * 1e-3 / K) / 1e9 / peak
+                if world_size == 1 else None}
+
+    # ---- e2e through the public VecEnv API: host actions in, host rewards/dones out, every step
+    env_e = vn.GraphVecEnv(world, n_total, device=dev, seed=2, max_episode_steps=MAX_EPISODE_STEPS,
+                           obs_layout="rgbd_goal", unreal_wrapper=True, rank=rank, world_size=world_size,
+                           gather=args.gather, host_outputs=True, device_world=env.dw)
+    env_e.reset()
+    Ke = min(K, 3000)
+    host_actions = actions[:min(n_rows, 512)].cpu().numpy()
+    for i in range(20):
+        env_e.step(host_actions[i % len(host_actions)])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        obs, rew, done, infos = env_e.step(host_actions[i % len(host_actions)])
+    barrier()
+    dt = time.perf_counter() - t0
+    if world_size > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": n_total * Ke / dt, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 20 * N,
+           "steps": Ke, "note": "VecEnv.step(numpy actions) -> (CUDA uint8 obs, numpy rewards, numpy dones, infos); "
+                                "observations stay in HBM for the policy"}
+    # secondary: also bring the observation batch to pinned host memory every step (what a CPU policy would need)
+    pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (obs[0][0], obs[0][2])]
+    Kh = min(Ke, 200)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Kh):
+        obs, rew, done, infos = env_e.step(host_actions[i % len(host_actions)])
+        pin[0].copy_(obs[0][0], non_blocking=True)
+        pin[1].copy_(obs[0][2], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    dth = time.perf_counter() - t0
+    e2e["host_obs_value"] = n_total * Kh / dth if world_size == 1 else None
+    e2e["host_obs_d2h_bytes_per_step"] = N * (F_RGB + F_DEPTH) + 20 * N
+
+    cpu_baseline = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        v, nres, cdt = cpu_run(16, 400, 3, 1)
+        cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
+                        "sample": "16 envs x 400 vector steps, one process, sequential + np.stack (DummyVecEnv "
+                                  "equivalent), %.1f s, p_reset=%.4f" % (cdt, nres / (16 * 400.0))}
+
+    if rank == 0:
+        line = {
+            "metric": "env-steps/s (obs gather+step+reset)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world_size, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_total": n_total, "states": world.n_states,
+                       "store_bytes": env.dw.nbytes(), "batch_bytes_per_step": N * (2 * F_RGB + F_DEPTH),
+                       "l2": "inputs larger than L2: 169 MB store + 116 MB batch touched per step vs 126 MB L2",
+                       "gather": args.gather, "p_reset": p_reset, "collision_rate": coll,
+                       "max_episode_steps": MAX_EPISODE_STEPS, "hardness": HARDNESS,
+                       "parallelism": "env-sharded x%d, no data-path collective" % world_size},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.gather_name = lambda env: {0: "auto", 1: "ldg", 2: "bulk"}[env.gather]
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

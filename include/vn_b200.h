@@ -1,0 +1,227 @@
+/*
+ * vn_b200.h - C ABI of the B200-native cached-graph navigation hot path (libvn_b200.so).
+ *
+ * The reference (felipefelixarias/a2cat-vn-pytorch) is pure Python and has NO plugin / FFI surface
+ * for this path; its seam is the gym Env / baselines-style VecEnv duck type built in
+ * experiments/thor_cached_auxiliary.py:58-71.  This header is therefore the boundary a Python
+ * VecEnv (ours: a2cat-vn-pytorch_b200/vec_env.py, bound with ctypes) or any other host binds to.
+ * Each entry point names the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no exceptions cross the boundary.
+ *   - every function returns 0 on success or a negative VN_E* code; vn_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread.
+ *   - all data pointers are CALLER-OWNED DEVICE pointers (e.g. torch tensor.data_ptr()) unless
+ *     marked [host]; the descriptor structs themselves are read on the host during the call.
+ *   - no allocation, no implicit synchronisation: kernels are enqueued on the caller's
+ *     cudaStream_t (passed as void*; NULL = legacy default stream) and the call returns.
+ *   - re-entrant: there is no global state apart from the thread-local error string.
+ *
+ * State numbering: oriented scenes use state = free_cell_rank * 4 + rotation (the numbering of
+ * graph/util.py:208-210,229-237 save_graph_as_h5), un-oriented ones state = free_cell_rank; with
+ * several scenes resident the indices are global (scene_base + local).
+ */
+#ifndef VN_B200_H
+#define VN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VN_ABI_VERSION 1
+#define VN_MAX_PLANES 6 /* rgb, depth, segmentation (+ the 3 third-person planes of graph/thor_graph.py:25-31) */
+
+/* error codes */
+#define VN_OK 0
+#define VN_EINVAL (-1)    /* bad argument (null pointer, size, alignment) */
+#define VN_ECUDA (-2)     /* CUDA runtime error at launch */
+#define VN_EUNSUPPORTED (-3)
+
+/* vn_rules_t.flags */
+#define VN_RULE_COLLISION_SKIPS_GOAL 0x01 /* gym_graph/graph.py:69-72: collision returns before the goal test */
+#define VN_RULE_NEG_STEP_REWARD 0x02      /* gym_ai2thor/envs/cached.py:84: reward = -cfg[1] */
+#define VN_RULE_COLLISION_OVERRIDES 0x04  /* cached.py:87-88: collided reward overrides the terminal reward */
+#define VN_RULE_TERM_PREV_OBS 0x08        /* cached.py:90-97: terminal step returns the previous observation */
+#define VN_RULE_TWO_LEVEL 0x10            /* graph/util.py:103-116: 0.9 / 0.1 curriculum buckets */
+#define VN_RULE_NOOP_ACTION 0x20          /* graph/env.py:118-120: action -1 is a no-op with reward 0.0 */
+#define VN_RULE_AUTO_RESET 0x40           /* baselines VecEnv worker: if done: ob = env.reset() */
+
+/* vn_rules_t.goal_compare */
+#define VN_GOAL_FULL 0     /* gym_graph/graph.py:60-61 position and rotation; cached.py:83 index equality */
+#define VN_GOAL_POSITION 1 /* position only (state >> 2) */
+#define VN_GOAL_NEVER 2    /* graph/env.py:61 as written: never true */
+
+/* indices into the device statistics vector (vn_step_out_t.stats, uint64 each; [1] is a double) */
+#define VN_STAT_EPISODES 0
+#define VN_STAT_RETURN_SUM 1 /* double, bit pattern stored in the uint64 slot */
+#define VN_STAT_LENGTH_SUM 2
+#define VN_STAT_SUCCESSES 3
+#define VN_STAT_COLLISIONS 4
+#define VN_STAT_STEPS 5
+#define VN_STAT_TRUNCATIONS 6
+#define VN_STAT_RESETS 7
+#define VN_N_STATS 8
+
+/* The cached-observation store resident in HBM.  Replaces the numpy arrays
+ * ThorGridWorld._observations/_depths/_segmentations [X,Y,4,H,W,C] (graph/multi_graph_no_tp.py:6-25,
+ * 141-144) and the h5 'observation' dataset (graph/util.py:224): one record per state holding all
+ * planes, record pitch and plane offsets multiples of 128 B, plane sizes multiples of 16 B. */
+typedef struct vn_store {
+    const uint8_t *base;               /* [n_states][state_pitch] */
+    int64_t state_pitch;
+    int32_t n_states;
+    int32_t n_planes;
+    int32_t plane_off[VN_MAX_PLANES];
+    int32_t plane_bytes[VN_MAX_PLANES];
+} vn_store_t;
+
+/* Transition + reset tables.  adj replaces graph.util.step + is_valid_state (graph/util.py:15-37)
+ * and the h5 'graph' dataset (graph/util.py:212-233); the candidate lists replace the per-reset
+ * Python loops of sample_initial_state / sample_initial_position (graph/util.py:88-143). */
+typedef struct vn_tables {
+    const int32_t *adj;           /* [n_states][4] next state, -1 = collision */
+    const int32_t *task_goal;     /* [n_tasks] goal state */
+    const int32_t *task_cand_off; /* [n_tasks + 1] CSR offsets into cand_state */
+    const int32_t *task_prefix;   /* [n_tasks] number of leading candidates eligible under the curriculum */
+    const int32_t *cand_state;    /* candidates of each task sorted by curriculum distance */
+    int32_t n_states;
+    int32_t n_tasks;
+} vn_tables_t;
+
+/* Per-env mutable state (struct of arrays, n_envs each). */
+typedef struct vn_envs {
+    int32_t n_envs;
+    int32_t env_id_base;     /* global id of env 0 of this shard: keys the RNG so results do not depend on sharding */
+    int32_t *state;
+    int32_t *goal;           /* goal state of the current episode */
+    int32_t *task;           /* task of the current episode */
+    int32_t *elapsed;        /* steps since reset (gym TimeLimit) */
+    uint32_t *epoch;         /* resets so far = RNG counter = index into the injected stream */
+    float *ep_return;        /* RewardCollector accumulators */
+    int32_t *ep_length;
+    const int32_t *task_lo;  /* [n_envs] first task this env may draw (gym_graph/graph.py:47 goals list) */
+    const int32_t *task_cnt; /* [n_envs] number of tasks it draws from */
+} vn_envs_t;
+
+typedef struct vn_rules {
+    float reward_goal, reward_step, reward_collision; /* rewards = [1.0, 0.0, 0.0] gym_graph/graph.py:10 */
+    int32_t max_episode_steps;                        /* gym TimeLimit; <= 0 disables */
+    int32_t goal_compare;
+    int32_t flags;
+    int32_t n_actions;                                /* 4 */
+    int32_t reserved;
+    uint64_t seed;
+} vn_rules_t;
+
+/* Optional injected reset stream (parity runs): reset k of env i uses task_lo[i] + task[i*stride + k]
+ * and start state start[i*stride + k] instead of the Philox draw.  NULL pointers = Philox. */
+typedef struct vn_inject {
+    const int32_t *task;
+    const int32_t *start;
+    int32_t stride;
+    int32_t reserved;
+} vn_inject_t;
+
+/* Outputs of one vectorised step.  Any pointer may be NULL to skip that output. */
+typedef struct vn_step_out {
+    uint8_t *obs[VN_MAX_PLANES];      /* [n_envs][plane_bytes[p]] observation batch, contiguous */
+    uint8_t *goal_obs[VN_MAX_PLANES]; /* persistent goal batch: rows rewritten only for envs that reset */
+    float *reward;                    /* [n_envs] */
+    uint8_t *done;                    /* [n_envs] env done OR time-limit */
+    uint8_t *truncated;               /* [n_envs] gym TimeLimit: 0 limit not reached (no info key), 1 info['TimeLimit.truncated']
+                                         = True, 2 limit reached on a step that was terminal anyway (= False) */
+    uint8_t *win;                     /* [n_envs] info['win'] */
+    uint8_t *did_reset;               /* [n_envs] */
+    float *last_action_reward;        /* [n_envs][n_actions + 1] UnrealEnvBaseWrapper vector */
+    float *episode_return;            /* [n_envs] info['episode']['r'], valid where done */
+    int32_t *episode_length;          /* [n_envs] info['episode']['l'], valid where done */
+    int32_t *info_state;              /* [n_envs] info['state']: state after the move, before auto-reset */
+    int32_t *obs_state;               /* [n_envs] state whose frames were gathered (scratch, required) */
+    uint64_t *stats;                  /* [VN_N_STATS] running sums, see VN_STAT_* */
+} vn_step_out_t;
+
+/* gather kernel variants (all bit-identical) */
+#define VN_GATHER_AUTO 0
+#define VN_GATHER_LDG 1      /* 16-byte vector loads/stores through registers */
+#define VN_GATHER_BULK 2     /* cp.async.bulk (TMA engine) global->shared->global, mbarrier-tracked */
+
+int32_t vn_abi_version(void);
+const char *vn_last_error(void);
+
+/* Fills the store with the synthetic frame hash (a2cat-vn-pytorch_b200/scenes.py frame_bytes):
+ * record r of this call holds local state state0 + r of scene `scene`.  Stands in for loading
+ * the pickled scene (graph/util.py:69-79) when no AI2-THOR data exists. */
+int32_t vn_fill_store(const vn_store_t *store, int32_t record0, int32_t n_records, uint64_t seed, int32_t scene,
+                      int32_t state0, const int32_t *plane_ids /* [host][n_planes] */, void *stream);
+
+/* VecEnv.reset(): (re)starts every env (mask == NULL) or the masked ones, gathers observation and
+ * goal frames.  Replaces OrientedGraphEnv.reset (gym_graph/graph.py:46-54), sample_initial_state,
+ * THORDiscreteCachedEnv.reset (cached.py:47-57) for the whole batch. */
+int32_t vn_env_reset(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
+                     const vn_rules_t *rules, const vn_inject_t *inject, const uint8_t *mask,
+                     const vn_step_out_t *out, int32_t gather_variant, void *stream);
+
+/* VecEnv.step(actions): adjacency lookup, collision / goal test, reward, time limit, done,
+ * auto-reset, episode statistics, last_action_reward and the frame gather, for all envs.
+ * Replaces OrientedGraphEnv.step (gym_graph/graph.py:67-79), SimpleGraphEnv.step (graph/env.py:117-133),
+ * THORDiscreteCachedEnv.step (cached.py:74-99), ThorGridWorld.render (graph/multi_graph_no_tp.py:12-25),
+ * GoalGymGraphAuxiliaryEnv.observe (gym_graph/graph.py:110-120) and the SubprocVecEnv worker loop. */
+int32_t vn_env_step(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
+                    const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *actions,
+                    const vn_step_out_t *out, int32_t gather_variant, void *stream);
+
+/* The two halves of vn_env_step as separate launches (vn_env_step == scalar half then gather half on
+ * the same stream).  Exposed so a host can time the gather kernel on its own or overlap the scalar
+ * half of one batch with the gather of another. */
+int32_t vn_env_step_scalar(const vn_tables_t *tables, const vn_envs_t *envs, const vn_rules_t *rules,
+                           const vn_inject_t *inject, const int32_t *actions, const vn_step_out_t *out, void *stream);
+int32_t vn_env_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
+                      int32_t gather_variant, void *stream);
+
+/* out[i] = plane `plane` of store record idx[i] (replay / sample_sequence gathers,
+ * experiments/ai2_auxiliary/trainer.py:29). */
+int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, uint8_t *out,
+                        int32_t gather_variant, void *stream);
+
+/* TransposeImage + ScaledFloatFrame (deep_rl.common.env, used at thor_cached_auxiliary.py:61-62)
+ * fused with the gather: out[i] = float32 CHW of plane / 255. */
+int32_t vn_gather_plane_f32_chw(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, int32_t h,
+                                int32_t w, int32_t c, float *out, void *stream);
+
+/* A2C n-step returns (deep_rl RolloutStorage.batch):
+ *   R_T = (1 - done[T-1]) * last_value;  R_t = reward[t] + gamma * (1 - done[t]) * R_{t+1}.
+ * Element (n, t) of reward/done/out lives at n * stride_n + t * stride_t. */
+int32_t vn_nstep_returns(const float *reward, const uint8_t *done, const float *last_value, float gamma, int32_t n,
+                         int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream);
+
+/* Backward discounted scan with a trailing feature axis of width d (pixel-control returns):
+ *   R_T = bootstrap;  R_t = reward[t] + gamma * (1 - done[t]) * R_{t+1};  arrays are [n][t][d]. */
+int32_t vn_discounted_backup(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,
+                             int32_t n, int32_t t, int32_t d, float *out, void *stream);
+
+/* UNREAL pixel-control reward (deep_rl.a2c_unreal.util.pixel_control_reward) computed
+ * straight from the store: for states[n][0..t] (t+1 entries, row stride t+1)
+ *   out[n][k] = mean_c avg_pool_cell( | f(states[n][k+1]) - f(states[n][k]) | ),  f = plane / 255 in fp32,
+ * centred crop to (out_h*cell, out_w*cell).  out is [n][t][out_h][out_w] float32. */
+int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
+                         int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out,
+                         void *stream);
+
+/* compute_auxiliary_target (experiments/ai2_auxiliary/trainer.py:9-15) from the store:
+ * out[i] = avg_pool_cell(crop(plane(idx[i]) / 255)), [m][c][out_h][out_w] float32. */
+int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t m, int32_t h, int32_t w,
+                      int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out, void *stream);
+
+/* Reward-prediction classes (0 zero, 1 positive, 2 negative) and the ascending position lists of
+ * zero / non-zero rewards the 50/50 sampler draws from.  counts[0..1] receive the list
+ * lengths.  Ballot / warp-scan compaction in three small launches, order preserving, up to 2^24
+ * positions per call; scratch is int32 [(n + 1023) / 1024] caller-owned device memory. */
+int32_t vn_rp_labels(const float *reward, int32_t n, int8_t *labels, int32_t *zero_idx, int32_t *nonzero_idx,
+                     int32_t *counts, int32_t *scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VN_B200_H */

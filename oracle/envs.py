@@ -19,7 +19,7 @@ class OracleScene:
     """What the reference's pickled scene objects expose: ``maze``, ``graph`` (all-pairs distances),
     ``optimal_actions``, ``render``.  Built from a synthetic GridScene (input data only)."""
 
-    def __init__(self, grid_scene, with_all_pairs=True):
+    def __init__(self, grid_scene, with_all_pairs=True, cache_frames=False):
         self.src = grid_scene
         self.maze = grid_scene.maze
         self.goals = list(grid_scene.goals)
@@ -28,6 +28,14 @@ class OracleScene:
         self.dtype = np.uint8
         h, w = grid_scene.frame_hw
         self.observation_shape = (h, w, 3)
+        # the reference keeps every frame in RAM (multi_graph_no_tp.py:141-144); the CPU baseline
+        # does the same so that render() is an index, not a hash evaluation
+        self._cache = {p: grid_scene.plane_frames(p) for p in grid_scene.planes} if cache_frames else None
+
+    def _frame(self, plane, s):
+        if self._cache is not None:
+            return self._cache[plane][s]
+        return self.src.plane_frames(plane, [s])[0]
 
     # graph/multi_graph_no_tp.py:12-25 ThorGridWorld.render
     def render(self, position, direction, modes=("rgb",)):
@@ -35,12 +43,12 @@ class OracleScene:
         ret = tuple()
         for m in ("rgb", "depth", "segmentation"):
             if m in modes:
-                ret = ret + (self.src.plane_frames(m, [s])[0],)
+                ret = ret + (self._frame(m, s),)
         return ret[0] if len(ret) == 1 else ret
 
     # un-oriented scenes (graph/maze_graph.py:20-24 after the store-build-time hoist): frame by cell
     def render_cell(self, position):
-        return self.src.plane_frames("rgb", [self.src.state_index(tuple(position))])[0]
+        return self._frame("rgb", self.src.state_index(tuple(position)))
 
 
 class GymGraphEnv:
@@ -104,6 +112,23 @@ class GymGraphAuxiliaryEnv(GymGraphEnv):
         goal_rgb, goal_seg = self.render_goal()
         rgb, depth, seg = self.graph.render(state[:2], state[2], modes=["rgb", "depth", "segmentation"])
         return (rgb, goal_rgb, depth, seg, goal_seg)
+
+
+class GymGraphRgbdGoalEnv(GymGraphAuxiliaryEnv):
+    """BASELINE.json configs[1] observation "RGB + depth + goal": GoalGymGraphAuxiliaryEnv restricted to
+    the leaves (rgb, goal_rgb, depth) - same render calls with modes without 'segmentation'."""
+
+    def render_goal(self):
+        cached, value = self._cached_goal
+        if cached is None or cached != self.goal:
+            value = self.graph.render(self.goal[:2], self.goal[2], modes=["rgb"])
+            self._cached_goal = (self.goal, value)
+        return value
+
+    def observe(self, state):
+        goal_rgb = self.render_goal()
+        rgb, depth = self.graph.render(state[:2], state[2], modes=["rgb", "depth"])
+        return (rgb, goal_rgb, depth)
 
 
 class GraphEnvOriented(GymGraphEnv):

@@ -163,3 +163,22 @@ class PhiloxResetSource:
         else:
             idx = int(philox.mulhi(d[2], p))
         return t, pots[idx]
+
+
+class ReferenceStyleResetSource:
+    """Reset sampling with the reference's COST profile, for the CPU baseline only: like
+    sample_initial_state (graph/util.py:119-143) it re-enumerates every free cell, recomputes the
+    rotation steps and the weights on EVERY reset, then draws with numpy's ``choice(p=weights)`` from a
+    seeded RandomState (the reference uses the unseeded global stream)."""
+
+    def __init__(self, scene, goals, optimal_distance_fn, seed):
+        self.scene, self.goals, self.od = scene, goals, optimal_distance_fn
+        self.rng = np.random.RandomState(seed)
+
+    def __call__(self):
+        t = int(self.rng.randint(len(self.goals)))
+        goal = self.goals[t]
+        pots, dists = gu.initial_state_candidates(self.scene.maze, self.scene.graph, self.scene.optimal_actions, goal)
+        w = gu.initial_state_weights(dists, self.od(t))
+        x = self.rng.choice(np.arange(len(pots)), p=w)
+        return t, pots[x]

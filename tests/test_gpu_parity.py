@@ -1,0 +1,344 @@
+"""Parity of the CUDA path (through the C ABI of libvn_b200.so) with
+  (a) the golden trajectories recorded from the UNMODIFIED reference classes, and
+  (b) the oracle restatement driven with the same streams (incl. the Philox reset path).
+Bit-exact for states / rewards / dones / observation bytes."""
+import importlib
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import envs as oenvs
+from oracle import graph_util as gu
+from oracle import vec as ovec
+
+pytestmark = pytest.mark.gpu
+
+vn = importlib.import_module("a2cat-vn-pytorch_b200")
+T = vn.tables
+
+
+def f32bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def replay_device(g, world, env_kwargs, inject_task, inject_start, n_leaves, tuple_width, noop_ok=False):
+    """Drives GraphVecEnv with the golden's actions + injected resets; returns a record like drive()."""
+    import torch
+    actions = g["actions"]
+    Tn, N = actions.shape
+    sched = H.schedule_of(g) if "sched_t" in g else {}
+    env = vn.GraphVecEnv(world, N, max_episode_steps=int(g["max_episode_steps"]), unreal_wrapper=False,
+                         inject=(inject_task, inject_start), **env_kwargs)
+    if 0 in sched:
+        env.set_complexity(sched[0])
+
+    def leaf_crcs(obs):
+        leaves = obs if isinstance(obs, tuple) else (obs,)
+        host = [x.cpu().numpy() for x in leaves]
+        return [[H.crc(x[i]) for x in host] for i in range(N)]
+
+    rec = dict(rewards=np.zeros((Tn, N), np.float32), dones=np.zeros((Tn, N), bool), truncated=np.zeros((Tn, N), bool),
+               wins=np.zeros((Tn, N), bool), env_dones=np.zeros((Tn, N), bool),
+               obs_crc=np.zeros((Tn, N, n_leaves), np.uint32), states=np.zeros((Tn, N, tuple_width), np.int32),
+               post_states=np.zeros((Tn, N, tuple_width), np.int32))
+    obs = env.reset()
+    rec["reset_obs_crc"] = np.array(leaf_crcs(obs), np.uint32)
+    tup = (lambda s: np.atleast_1d(world.state_tuple(int(s)))) if tuple_width > 1 else (lambda s: np.array([int(s)]))
+    rec["reset_states"] = np.array([tup(s) for s in env.state.cpu().numpy()], np.int32)
+    for t in range(Tn):
+        if t in sched and t != 0:
+            env.set_complexity(sched[t])
+        obs, rew, done, infos = env.step(actions[t])
+        h = infos._host()
+        rec["rewards"][t] = rew
+        rec["dones"][t] = done
+        rec["truncated"][t] = h["truncated"] == 1
+        rec["wins"][t] = h["win"].astype(bool)
+        rec["env_dones"][t] = done & ~(h["truncated"] == 1)
+        rec["states"][t] = np.array([tup(s) for s in h["info_state"]], np.int32)
+        rec["post_states"][t] = np.array([tup(s) for s in env.state.cpu().numpy()], np.int32)
+        rec["obs_crc"][t] = leaf_crcs(obs)
+        # infos dictionaries carry the reference keys
+        if t % 97 == 0:
+            for i in range(N):
+                info = infos[i]
+                if done[i]:
+                    assert "episode" in info
+    return rec, env
+
+
+def assert_equal(rec, g, obs=True, wins=True):
+    for k in ("states", "post_states", "dones", "env_dones", "truncated", "reset_states") + (("wins",) if wins else ()):
+        a, b = np.asarray(rec[k]), np.asarray(g[k])
+        assert np.array_equal(a.reshape(b.shape), b), k
+    assert np.array_equal(f32bits(rec["rewards"]), f32bits(g["rewards"])), "rewards (bitwise, incl. -0.0)"
+    if obs:
+        assert np.array_equal(rec["obs_crc"], g["obs_crc"]), "observation bytes"
+        assert np.array_equal(rec["reset_obs_crc"], g["reset_obs_crc"]), "reset observation bytes"
+
+
+def starts_to_index(scene, starts, counts):
+    out = np.zeros(starts.shape[:2], np.int32)
+    for i in range(starts.shape[0]):
+        for k in range(int(counts[i])):
+            out[i, k] = scene.state_index(tuple(int(v) for v in starts[i, k]))
+    return out
+
+
+@pytest.mark.parametrize("gather", ["ldg", "bulk"])
+def test_golden_gym_graph_auxiliary(gather):
+    g = H.load("gym_graph_aux")
+    scene = H.scene_from_golden(g, True, ("rgb", "depth", "segmentation"))
+    goals = [tuple(int(v) for v in x) for x in g["goals"]]
+    world = T.compile_world([scene], T.GYM_GRAPH, tasks=[(0, gl) for gl in goals])
+    N = g["actions"].shape[1]
+    env_tasks = np.tile(np.array([[0, len(goals)]], np.int32), (N, 1))
+    rec, env = replay_device(g, world, dict(obs_layout="aux5", rewards=tuple(g["rewards_cfg"]), env_tasks=env_tasks,
+                                            gather=gather),
+                             g["reset_choice"], starts_to_index(scene, g["reset_start"], g["reset_count"]), 5, 3)
+    assert_equal(rec, g)
+    st = env.episode_stats()
+    assert st["episodes"] == g["dones"].sum() and st["successes"] == g["wins"].sum()
+    assert st["steps"] == g["actions"].size and st["truncations"] == g["truncated"].sum()
+
+
+def test_golden_gym_graph_oriented():
+    g = H.load("gym_graph_oriented")
+    scene = H.scene_from_golden(g, True, ("rgb", "depth", "segmentation"))
+    goal = tuple(int(v) for v in g["goals"][0])
+    world = T.compile_world([scene], T.GYM_GRAPH, tasks=[(0, goal)])
+    rec, _ = replay_device(g, world, dict(obs_layout="frame", rewards=tuple(g["rewards_cfg"])),
+                           g["reset_choice"], starts_to_index(scene, g["reset_start"], g["reset_count"]), 1, 3)
+    assert_equal(rec, g)
+
+
+def test_golden_graph_env_simple():
+    g = H.load("graph_env_simple")
+    scene = H.scene_from_golden(g, False, ("rgb",))
+    world = T.compile_world([scene], T.SIMPLE_GRAPH)
+    rec, _ = replay_device(g, world, dict(obs_layout="frame", rewards=tuple(g["rewards_cfg"])),
+                           g["reset_choice"], starts_to_index(scene, g["reset_start"], g["reset_count"]), 1, 2)
+    # the reference env returns float32 frame / 255 (graph/env.py:110-115): compare those bytes
+    assert_equal(rec, g, obs=False)
+    import torch
+    env = vn.GraphVecEnv(world, 1, unreal_wrapper=False, obs_layout="frame",
+                         inject=(g["reset_choice"][:1], starts_to_index(scene, g["reset_start"][:1], g["reset_count"][:1])))
+    ob = env.reset()
+    f = (ob[0].cpu().numpy().astype(np.float32) / 255.0)
+    assert H.crc(f) == int(g["reset_obs_crc"][0, 0])
+    f2 = vn.rollout.policy_input(env.dw, env.state)[0].cpu().numpy()       # fused gather + /255 + CHW
+    assert np.array_equal(np.transpose(f2, (1, 2, 0)), f)
+
+
+def test_golden_graph_env_multiple():
+    g = H.load("graph_env_multiple")
+    K = int(g["n_graphs"])
+    scs = [H.scenes.GridScene(g["maze%d" % k], [tuple(int(v) for v in g["goal%d" % k])], False, (84, 84), ("rgb",),
+                              frame_seed=int(g["frame_seed%d" % k]), scene_id=k) for k in range(K)]
+    world = T.compile_world(scs, T.SIMPLE_GRAPH)
+    N = g["actions"].shape[1]
+    starts = np.zeros(g["reset_start"].shape[:2], np.int32)
+    for i in range(N):
+        for k in range(int(g["reset_count"][i])):
+            gi = int(g["reset_choice"][i, k])
+            starts[i, k] = world.scene_base[gi] + scs[gi].state_index(tuple(int(v) for v in g["reset_start"][i, k]))
+    env_tasks = np.tile(np.array([[0, K]], np.int32), (N, 1))
+    rec, _ = replay_device(g, world, dict(obs_layout="frame", rewards=tuple(g["rewards_cfg"]), env_tasks=env_tasks),
+                           g["reset_choice"], starts, 1, 2)
+    assert_equal(rec, g, obs=False)
+
+
+def test_golden_graph_env_oriented_never_terminates():
+    g = H.load("graph_env_oriented")
+    scene = H.scene_from_golden(g, True, ("rgb", "depth", "segmentation"))
+    goal = tuple(int(v) for v in g["goals"][0])
+    world = T.compile_world([scene], T.GRAPH_ENV_ORIENTED, tasks=[(0, goal)])
+    rec, _ = replay_device(g, world, dict(obs_layout="frame"), g["reset_choice"],
+                           starts_to_index(scene, g["reset_start"], g["reset_count"]), 1, 3)
+    assert_equal(rec, g, obs=False)
+
+
+def test_golden_thor_cached():
+    g = H.load("thor_cached")
+    scene = H.scene_from_golden(g, True, ("rgb",))
+    # the reference draws the goal from all states (cached.py:39): one task per distinct recorded goal
+    goals = sorted(set(int(v) for i in range(g["reset_goal"].shape[0]) for v in g["reset_goal"][i, :g["reset_count"][i]]))
+    world = T.compile_world([scene], T.THOR_CACHED, tasks=[(0, gl) for gl in goals])
+    assert np.array_equal(world.adj, g["graph"])          # the h5 'graph' dataset, action order fwd/back/rot+/rot-
+    lut = {gl: k for k, gl in enumerate(goals)}
+    N = g["actions"].shape[1]
+    task = np.zeros_like(g["reset_goal"])
+    for i in range(N):
+        for k in range(int(g["reset_count"][i])):
+            task[i, k] = lut[int(g["reset_goal"][i, k])]
+    env_tasks = np.tile(np.array([[0, len(goals)]], np.int32), (N, 1))
+    rec, _ = replay_device(g, world, dict(obs_layout="pair", env_tasks=env_tasks), task, g["reset_start"], 2, 1)
+    assert_equal(rec, g, obs=False, wins=False)
+    assert np.signbit(rec["rewards"][rec["rewards"] == 0]).any()        # -0.0 of cached.py:84 reproduced
+
+
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("family,oriented", [("gym_graph", True), ("simple_graph", False)])
+def test_philox_reset_path_matches_oracle(family, oriented):
+    """No injection: the device's Philox sampling + curriculum prefix vs the oracle restatement that
+    is built from the oracle's own candidate lists."""
+    import torch
+    fam = T.FAMILIES[family]
+    planes = ("rgb", "depth", "segmentation") if oriented else ("rgb",)
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 3, n_goals=3, oriented=oriented, planes=planes)
+    osc = oenvs.OracleScene(scene)
+    world = T.compile_world([scene], fam)
+    N, Tn, seed, max_steps = 12, 300, 1234, 25
+    env_tasks = np.tile(np.array([[0, 3]], np.int32), (N, 1)) if oriented else None
+    env = vn.GraphVecEnv(world, N, seed=seed, max_episode_steps=max_steps, unreal_wrapper=True,
+                         obs_layout="aux5" if oriented else "frame", env_tasks=env_tasks)
+    oes = []
+    for i in range(N):
+        if oriented:
+            e = oenvs.GymGraphAuxiliaryEnv(osc, goals=list(scene.goals))
+            cands = [gu.initial_state_candidates(scene.maze, osc.graph, osc.optimal_actions, gl) for gl in scene.goals]
+            e.reset_source = ovec.PhiloxResetSource(seed, i, cands, lambda t, e=e: e.optimal_distance(), False)
+        else:
+            # default env_tasks deal tasks round-robin: env i owns task i % 3
+            gl = scene.goals[i % 3]
+            e = oenvs.SimpleGraphEnv(osc, goal=gl)
+            cands = [gu.initial_position_candidates(scene.maze, osc.graph, gl)]
+            e.reset_source = ovec.PhiloxResetSource(seed, i, cands, lambda t, e=e: e.optimal_distance(), True)
+        oes.append(ovec.RewardCollector(ovec.TimeLimit(e, max_steps)))
+    ov = ovec.VecEnv(oes)
+    rng = np.random.RandomState(5)
+    for c in (0.25, None):
+        env.set_complexity(c)
+        for e in oes:
+            e.set_complexity(c)
+        (obs, lar) = env.reset()
+        oobs, olar = ov.reset()
+        for t in range(Tn):
+            a = rng.randint(-1 if not oriented else 0, 4, size=N)
+            (obs, lar), rew, done, infos = env.step(a)
+            (oobs, olar), orew, odone, oinfos = ov.step(a)
+            assert np.array_equal(done, odone), t
+            assert np.array_equal(f32bits(rew), f32bits(orew)), t
+            assert np.array_equal(f32bits(lar.cpu().numpy()), f32bits(olar)), t
+            assert [oe.state for oe in oes] == env.states(), t
+            leaves = obs if isinstance(obs, tuple) else (obs,)
+            oleaves = oobs if isinstance(oobs, tuple) else (oobs,)
+            for x, y in zip(leaves, oleaves):
+                y = y if y.dtype == np.uint8 else np.rint(y * 255).astype(np.uint8)
+                assert np.array_equal(x.cpu().numpy(), y), t
+            for i in range(N):
+                info, oinfo = infos[i], oinfos[i]
+                assert info.get("episode") == oinfo.get("episode"), (t, i)
+                assert info.get("TimeLimit.truncated") == oinfo.get("TimeLimit.truncated"), (t, i)
+                assert info.get("state") == oinfo.get("state") and info.get("win") == oinfo.get("win"), (t, i)
+        assert done.sum() >= 0
+
+
+def test_store_fill_matches_host_hash():
+    import torch
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 9, n_goals=1, planes=("rgb", "depth", "segmentation"), scene_id=4)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    dw = vn.DeviceWorld(world)
+    for p in ("rgb", "depth", "segmentation"):
+        dev = dw.plane_view(p).cpu().numpy()
+        assert np.array_equal(dev, scene.plane_frames(p)), p
+    lay = world.layout
+    pad = np.ones(lay.state_pitch, bool)
+    for o, b in zip(lay.plane_off, lay.plane_bytes):
+        pad[o:o + b] = False
+    assert not dw.frames.cpu().numpy()[:, pad].any()
+
+
+def test_full_size_properties_c2():
+    """BASELINE.json configs[1] at full size (1,500 cells x 4 rotations, 4,096 envs): size-independent
+    properties instead of a slow scalar oracle."""
+    import torch
+    scene = H.scenes.make_thor_scene(1500, (50, 60), seed=0, n_goals=4, planes=("rgb", "depth"))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    assert world.n_states == 6000
+    N = 4096
+    envs = {v: vn.GraphVecEnv(world, N, seed=7, max_episode_steps=50, obs_layout="rgbd_goal", gather=v,
+                              host_outputs=False) for v in ("ldg", "bulk")}
+    dw = envs["ldg"].dw
+    adj = dw.adj.view(-1, 4)
+    rgb, depth = dw.plane_view("rgb"), dw.plane_view("depth")
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for e in envs.values():
+        e.set_complexity(0.1)
+        e.reset()
+    e0, e1 = envs["ldg"], envs["bulk"]
+    for t in range(120):
+        a = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        prev = e0.state.clone()
+        ((o_rgb, o_goal, o_depth), lar), rew, done, _ = e0.step(a)
+        ((b_rgb, b_goal, b_depth), blar), brew, bdone, _ = e1.step(a)
+        # the two gather variants are bit-identical
+        assert torch.equal(o_rgb, b_rgb) and torch.equal(o_depth, b_depth) and torch.equal(o_goal, b_goal)
+        assert torch.equal(rew, brew) and torch.equal(done, bdone) and torch.equal(e0.state, e1.state)
+        # transition table property: next = adj[prev, a], unchanged on collision
+        nxt = adj[prev.long(), a.long()]
+        moved = torch.where(nxt >= 0, nxt, prev)
+        assert torch.equal(e0.info_state, moved)
+        # gather property: every observation row equals the store frame of the env's current state
+        s = e0.state.long()
+        assert torch.equal(o_rgb, rgb[s]) and torch.equal(o_depth, depth[s])
+        assert torch.equal(o_goal, rgb[e0.goal.long()])
+        # resets land on curriculum-eligible candidates and zero the wrapper vector
+        r = e0.did_reset.bool()
+        assert torch.equal(r, done)
+        assert (lar[r] == 0).all()
+    st = e0.episode_stats()
+    assert st["steps"] == 120 * N and st["episodes"] == st["resets"] - N > 0
+
+
+def test_checkpoint_roundtrip():
+    import torch
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    a = vn.GraphVecEnv(world, 32, seed=3, max_episode_steps=20)
+    a.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(30):
+        a.step(rng.randint(0, 4, 32))
+    sd = a.state_dict()
+    b = vn.GraphVecEnv(world, 32, seed=3, max_episode_steps=20, device_world=a.dw)
+    b.load_state_dict(sd)
+    for _ in range(40):
+        act = rng.randint(0, 4, 32)
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act)
+        assert np.array_equal(ra, rb) and np.array_equal(da, db) and torch.equal(a.state, b.state)
+        assert all(torch.equal(x, y) for x, y in zip(oa[0], ob[0]))
+
+
+def test_sharding_is_invisible():
+    """RNG keyed by GLOBAL env id: 2 shards of 24 envs == one process with 48 envs."""
+    import torch
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    whole = vn.GraphVecEnv(world, 48, seed=11, max_episode_steps=15)
+    parts = [vn.GraphVecEnv(world, 48, seed=11, max_episode_steps=15, rank=r, world_size=2, device_world=whole.dw)
+             for r in range(2)]
+    whole.reset()
+    [p.reset() for p in parts]
+    rng = np.random.RandomState(1)
+    for _ in range(60):
+        a = rng.randint(0, 4, 48)
+        _, r, d, _ = whole.step(a)
+        outs = [p.step(a[p.env_lo:p.env_lo + p.num_envs]) for p in parts]
+        assert np.array_equal(r, np.concatenate([o[1] for o in outs]))
+        assert np.array_equal(d, np.concatenate([o[2] for o in outs]))
+        assert torch.equal(whole.state, torch.cat([p.state for p in parts]))
+
+
+def test_c_abi_rejects_bad_arguments():
+    import ctypes as C
+    L = vn.lib
+    lib = L.load()
+    st = L.Store()
+    rc = lib.vn_gather_plane(C.byref(st), 0, None, 0, None, 0, None)
+    assert rc == -1 and b"store" in lib.vn_last_error()
+    with pytest.raises(ValueError):
+        scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=1, planes=("rgb",))
+        vn.GraphVecEnv(T.compile_world([scene], T.GYM_GRAPH), 4, obs_layout="aux5")

@@ -1,0 +1,154 @@
+"""Rollout / target builders on the device vs the oracle (oracle/rollout.py).
+Tolerance from BASELINE.json north_star: 1e-5 relative in fp32 (plus 1e-7 absolute for exact zeros)."""
+import importlib
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import rollout as orl
+
+pytestmark = pytest.mark.gpu
+
+vn = importlib.import_module("a2cat-vn-pytorch_b200")
+T = vn.tables
+RTOL, ATOL = 1e-5, 1e-7
+
+
+@pytest.fixture(scope="module")
+def dw():
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2, planes=("rgb", "depth", "segmentation"))
+    return vn.DeviceWorld(T.compile_world([scene], T.GYM_GRAPH))
+
+
+@pytest.mark.parametrize("time_major", [False, True])
+def test_nstep_returns(time_major):
+    import torch
+    rng = np.random.RandomState(0)
+    B, Tn = 37, 20
+    r = rng.randn(B, Tn).astype(np.float32)
+    d = rng.rand(B, Tn) < 0.15
+    v = rng.randn(B).astype(np.float32)
+    want = orl.nstep_returns(r, d, v, 0.99)
+    rt, dt = torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda()
+    if time_major:
+        got = vn.rollout.nstep_returns(rt.t().contiguous(), dt.t().contiguous(), torch.from_numpy(v).cuda(), 0.99,
+                                       time_major=True).t()
+    else:
+        got = vn.rollout.nstep_returns(rt, dt, torch.from_numpy(v).cuda(), 0.99)
+    # same operation order as the oracle -> bit-exact, which is stronger than the 1e-5 bar
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_nstep_returns_c5_size():
+    """BASELINE.json configs[4]: T = 128, N x T = 2^20."""
+    import torch
+    rng = np.random.RandomState(1)
+    B, Tn = 8192, 128
+    r = (rng.rand(B, Tn) < 0.02).astype(np.float32)
+    d = r > 0
+    v = rng.randn(B).astype(np.float32)
+    want = orl.nstep_returns(r, d, v, 0.99)
+    got = vn.rollout.nstep_returns(torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(v).cuda(), 0.99)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+
+
+def test_discounted_backup():
+    import torch
+    rng = np.random.RandomState(2)
+    B, Tn, D = 5, 7, 400
+    r = rng.rand(B, Tn, 20, 20).astype(np.float32)
+    d = rng.rand(B, Tn) < 0.2
+    b = rng.rand(B, 20, 20).astype(np.float32)
+    want = orl.discounted_backup(r.reshape(B, Tn, D), d, b.reshape(B, D), 0.9).reshape(r.shape)
+    got = vn.rollout.discounted_backup(torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(b).cuda(), 0.9)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+
+
+def test_pixel_control_reward(dw):
+    import torch
+    rng = np.random.RandomState(3)
+    B, Tn = 6, 21
+    S = dw.world.n_states
+    states = rng.randint(0, S, size=(B, Tn + 1)).astype(np.int32)
+    states[:, 5] = states[:, 4]            # identical consecutive frames -> exact zeros
+    scene = dw.world.scenes[0]
+    frames = scene.plane_frames("rgb", states.reshape(-1)).reshape(B, Tn + 1, 84, 84, 3)
+    x = orl.u8_to_policy_input(frames)                     # TransposeImage + ScaledFloatFrame
+    for out_size in ((20, 20), None):
+        want = orl.pixel_control_reward(x, 4, out_size)
+        got = vn.rollout.pixel_control_reward(dw, torch.from_numpy(states), 4, out_size).cpu().numpy()
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+        assert (got[:, 4] == 0).all()
+
+
+def test_auxiliary_targets(dw):
+    import torch
+    rng = np.random.RandomState(4)
+    B, Tn = 4, 9
+    S = dw.world.n_states
+    states = rng.randint(0, S, size=(B, Tn)).astype(np.int32)
+    goals = rng.randint(0, S, size=(B, Tn)).astype(np.int32)
+    scene = dw.world.scenes[0]
+    got = vn.rollout.auxiliary_targets(dw, torch.from_numpy(states), torch.from_numpy(goals), 4, (20, 20))
+    for g, (plane, idx) in zip(got, (("depth", states), ("segmentation", states), ("segmentation", goals))):
+        c = 1 if plane == "depth" else 3
+        fr = scene.plane_frames(plane, idx.reshape(-1)).reshape(B, Tn, 84, 84, c)
+        want = orl.aux_target(orl.u8_to_policy_input(fr), 4, (20, 20))
+        np.testing.assert_allclose(g.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+
+
+def test_aux_target_against_reference_golden():
+    """tests/golden/aux_target.npz was produced by the reference's own compute_auxiliary_target."""
+    import torch
+    g = H.load("aux_target")
+    rng = np.random.RandomState(int(g["x_seed"]))
+    u8 = rng.randint(0, 256, size=(2, 3, 3, 84, 84)).astype(np.uint8)            # [B, T, C, H, W]
+    frames = np.moveaxis(u8, 2, -1).reshape(6, 84, 84, 3)
+    scene = H.scenes.GridScene(np.ones((1, 6), bool), [(0, 0)], False, (84, 84), ("rgb",), explicit={"rgb": frames})
+    dwx = vn.DeviceWorld(T.compile_world([scene], T.SIMPLE_GRAPH, tasks=[(0, (0, 0))]))
+    idx = torch.arange(6, dtype=torch.int32).view(2, 3)
+    np.testing.assert_allclose(vn.rollout.auxiliary_target(dwx, idx, "rgb", 4, (20, 20)).cpu().numpy(), g["y20"],
+                               rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(vn.rollout.auxiliary_target(dwx, idx, "rgb", 4, None).cpu().numpy(), g["y21"],
+                               rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n", [1, 31, 1024, 1025, 70001, 1 << 20])
+def test_reward_prediction_labels_and_compaction(n):
+    import torch
+    rng = np.random.RandomState(n)
+    r = np.where(rng.rand(n) < 0.03, rng.choice([-1.0, 1.0, 0.5], size=n), 0.0).astype(np.float32)
+    labels, zero, nonzero = vn.rollout.reward_prediction_labels(torch.from_numpy(r).cuda())
+    z, nz = orl.rp_index_lists(r)
+    assert np.array_equal(labels.cpu().numpy(), orl.rp_labels(r))
+    assert np.array_equal(zero.cpu().numpy(), z) and np.array_equal(nonzero.cpu().numpy(), nz)
+
+
+def test_rollout_buffer_end_to_end(dw):
+    """Env steps -> rollout buffer (state indices only) -> returns / PC / aux / RP, vs the oracle."""
+    import torch
+    N, Tn = 16, 12
+    env = vn.GraphVecEnv(dw.world, N, seed=5, max_episode_steps=10, device_world=dw, host_outputs=False)
+    env.set_complexity(0.2)
+    env.reset()
+    buf = vn.rollout.RolloutBuffer(dw, N, Tn)
+    buf.start(env)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(Tn):
+        a = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        env.step(a)
+        buf.insert(env, a)
+    v = torch.randn(N, device="cuda")
+    R = buf.returns(v, 0.99).cpu().numpy()
+    want = orl.nstep_returns(buf.rewards.t().cpu().numpy(), buf.dones.t().cpu().numpy(), v.cpu().numpy(), 0.99)
+    np.testing.assert_allclose(R, want, rtol=RTOL, atol=ATOL)
+    scene = dw.world.scenes[0]
+    st = buf.states.t().cpu().numpy()
+    fr = scene.plane_frames("rgb", st.reshape(-1)).reshape(N, Tn + 1, 84, 84, 3)
+    np.testing.assert_allclose(buf.pixel_control(4, (20, 20)).cpu().numpy(),
+                               orl.pixel_control_reward(orl.u8_to_policy_input(fr), 4, (20, 20)), rtol=RTOL, atol=ATOL)
+    labels, zero, nonzero = buf.reward_prediction()
+    assert np.array_equal(labels.cpu().numpy(), orl.rp_labels(buf.rewards.t().cpu().numpy()))
+    assert buf.dones.sum() > 0

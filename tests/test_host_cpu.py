@@ -1,0 +1,205 @@
+"""CPU tests of the host-side logic: the flat-table compiler against the oracle (which follows the
+reference's tuple arithmetic), the C-ABI library's exported symbols, sharding and the gloo
+statistics reduction (world_size 2)."""
+import ctypes
+import importlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import graph_util as gu
+from oracle import philox
+
+vn = importlib.import_module("a2cat-vn-pytorch_b200")
+T = vn.tables
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("seed,shape", [(0, (10, 10)), (3, (9, 7)), (5, (6, 12))])
+def test_adjacency_matches_reference_step(seed, shape):
+    scene = H.scenes.make_maze_scene(shape, 0.25, seed, n_goals=1)
+    adj = T.build_adjacency(scene, "graph")
+    adj_h5 = T.build_adjacency(scene, "h5")
+    for s in range(scene.n_states):
+        st = scene.state_tuple(s)
+        for a in range(4):
+            n = gu.step(st, a)                                   # graph/util.py:15-25
+            want = scene.state_index(n) if gu.is_valid_state(scene.maze, n) else -1
+            assert adj[s, a] == want
+        assert list(adj_h5[s]) == [adj[s, 0], adj[s, 2], adj[s, 1], adj[s, 3]]
+    dist, _ = gu.compute_shortest_path_data(scene.maze)
+    _, graph, _ = gu.h5_tables(scene.maze, dist)                 # graph/util.py:212-233
+    assert np.array_equal(adj_h5, graph)
+    un = H.scenes.GridScene(scene.maze, [tuple(scene.cells[0])], False, (84, 84), ("rgb",))
+    adj_c = T.build_adjacency(un, "compass")
+    for s in range(un.n_states):
+        x, y = un.state_tuple(s)
+        for a in range(4):
+            c = gu.direction_to_change(a)
+            n = (x + c[0], y + c[1])
+            assert adj_c[s, a] == (un.state_index(n) if gu.is_valid_state(un.maze, n) else -1)
+
+
+def test_bfs_tables_match_reference_golden():
+    g = H.load("graph_util")
+    for k in range(int(g["n_mazes"])):
+        d, a = T.all_pairs(g["maze%d" % k])
+        assert np.array_equal(d, g["dist%d" % k]) and np.array_equal(a, g["act%d" % k])
+
+
+@pytest.mark.parametrize("family", ["gym_graph", "simple_graph"])
+def test_candidate_tables_equal_reference_eligible_sets(family):
+    """For every golden (maze, goal, complexity): the device's curriculum prefix == the set of
+    candidates the reference gives positive weight (graph/util.py:135-142 / :103-116)."""
+    g = H.load("graph_util")
+    fam = T.FAMILIES[family]
+    for k in range(int(g["n_mazes"])):
+        maze = g["maze%d" % k]
+        dist, act = gu.compute_shortest_path_data(maze)
+        for gi, goal in enumerate(g["goals%d" % k]):
+            goal = tuple(int(v) for v in goal)
+            goal = goal if fam.oriented else goal[:2]
+            scene = H.scenes.GridScene(maze, [goal], fam.oriented, (84, 84), ("rgb",))
+            task = T.build_task(scene, 0, goal, fam)
+            assert task.max_dist == int(dist.max())
+            if fam.oriented:
+                pots, d = gu.initial_state_candidates(maze, dist, act, goal)
+            else:
+                pots, d = gu.initial_position_candidates(maze, dist, goal)
+            by_state = {scene.state_index(p): dd for p, dd in zip(pots, d)}
+            assert sorted(by_state) == sorted(task.cand_state.tolist())
+            assert [by_state[s] for s in task.cand_state.tolist()] == task.cand_dist.tolist()
+            assert (np.diff(task.cand_dist) >= 0).all()
+            for ci, c in enumerate(g["complexities"]):
+                c = None if c < 0 else float(c)
+                w = g["w_%s_%d_%d_%d" % ("state" if fam.oriented else "position", k, gi, ci)]
+                pre = T.curriculum_prefix(task, fam, c)
+                levels = np.unique(w[w > 0])
+                hi = {scene.state_index(p) for p, ww in zip(pots, w) if ww == levels.max()}
+                if c is None or len(levels) == 1:
+                    want = {scene.state_index(p) for p, ww in zip(pots, w) if ww > 0}
+                else:     # two-level rule: the prefix is the 0.9 bucket
+                    mass = {lv: w[w == lv].sum() for lv in levels}
+                    big = max(mass, key=mass.get)
+                    want = {scene.state_index(p) for p, ww in zip(pots, w) if ww == big}
+                assert set(task.cand_state[:pre].tolist()) == want, (k, gi, c)
+
+
+def test_thor_cached_candidates_follow_h5_distance():
+    scene = H.scenes.make_maze_scene((9, 8), 0.2, 31, n_goals=1, planes=("rgb",))
+    dist, _ = gu.compute_shortest_path_data(scene.maze)
+    _, _, spd = gu.h5_tables(scene.maze, dist)
+    for goal in (0, 17, scene.n_states - 1):
+        task = T.build_task(scene, 0, goal, T.THOR_CACHED)
+        assert sorted(task.cand_state.tolist()) == np.nonzero(spd[:, goal] > 0)[0].tolist()   # cached.py:41-44
+
+
+def test_world_concatenation_and_layout():
+    scs = [H.scenes.make_maze_scene((8, 9), 0.2, 20 + k, n_goals=2, scene_id=k) for k in range(3)]
+    w = T.compile_world(scs, T.GYM_GRAPH)
+    assert w.n_states == sum(s.n_states for s in scs) and len(w.tasks) == 6
+    for si, s in enumerate(scs):
+        b = int(w.scene_base[si])
+        local = T.build_adjacency(s, "graph")
+        blk = w.adj[b:b + s.n_states]
+        assert np.array_equal(np.where(blk >= 0, blk - b, -1), local)
+        assert w.state_tuple(b + 5) == s.state_tuple(5)
+    lay = w.layout
+    assert lay.plane_bytes == (21168, 7056, 21168) and lay.state_pitch % 128 == 0
+    assert all(o % 128 == 0 for o in lay.plane_off)
+    with pytest.raises(ValueError):
+        T.StoreLayout.make(("rgb",), (10, 10))        # 300 bytes is not a multiple of 16
+
+
+def test_frame_hash_is_stable():
+    # known-answer bytes: guards the host hash that the device fill kernel must reproduce
+    b = H.scenes.frame_bytes(0, 0, 0, 0, 16)
+    assert b.dtype == np.uint8 and b.shape == (16,)
+    b2 = H.scenes.frame_bytes(0, 0, np.array([0, 1]), 0, 16)
+    assert np.array_equal(b2[0], b) and not np.array_equal(b2[1], b)
+    assert H.crc(H.scenes.frame_bytes(7, 3, 11, 2, 21168)) == H.crc(H.scenes.frame_bytes(7, 3, 11, 2, 21168))
+
+
+def test_generators():
+    m = H.scenes.grown_scene_maze(1500, (50, 60), 0)
+    assert m.sum() == 1500
+    assert H.scenes._component_of(m, tuple(np.argwhere(m)[0])).sum() == 1500
+    d = H.scenes.dungeon_maze((64, 64), 0)
+    assert d.shape == (64, 64) and 0.1 < d.mean() < 0.7
+    assert H.scenes._component_of(d, tuple(np.argwhere(d)[0])).sum() == d.sum()
+    sc = H.scenes.make_dungeon_scene((64, 64), 0)
+    assert sc.goals[0] == tuple(int(v) for v in np.argwhere(sc.maze)[0])      # dungeon_graph.py:20
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports exactly what include/vn_b200.h declares."""
+    L = vn.lib
+    lib = L.load()
+    header = open(os.path.join(ROOT, "include", "vn_b200.h")).read()
+    declared = set(re.findall(r"^(?:int32_t|const char \*)\s*\*?(vn_[a-z0-9_]+)\(", header, re.M))
+    assert declared == set(L.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.vn_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", L.library_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (vn_[a-z0-9_]+)", out))
+    assert declared <= exported
+    # struct sizes agree with the header (guards the ctypes mirrors)
+    assert ctypes.sizeof(L.Store) == 8 + 8 + 4 + 4 + 24 + 24
+    assert ctypes.sizeof(L.Rules) == 40 and ctypes.sizeof(L.Inject) == 24
+    assert ctypes.sizeof(L.StepOut) == 8 * (6 + 6 + 11)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "a2cat-vn-pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_shard_range_partitions():
+    from importlib import import_module
+    shard_range = import_module("a2cat-vn-pytorch_b200.vec_env").shard_range
+    for n, w in ((262144, 8), (10, 3), (7, 8), (0, 2)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ve = importlib.import_module("a2cat-vn-pytorch_b200.vec_env")
+    lo, hi = ve.shard_range(101, rank, world)
+    # each rank contributes statistics of its own env shard; the reduced vector is the job total
+    local = np.array([hi - lo, 0.5 * (hi - lo), 3 * (hi - lo), rank, 0, 10 * (hi - lo), 0, 1], np.float64)
+    total = ve.reduce_stats(local)
+    # per-env Philox draws depend on the GLOBAL env id only
+    draws = philox.reset_draws(9, np.arange(lo, hi), 0)
+    q.put((rank, total.tolist(), lo, hi, draws[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_multi_rank_stats_reduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    (r0, t0, lo0, hi0, d0), (r1, t1, lo1, hi1, d1) = res
+    assert t0 == t1 and t0[0] == 101 and t0[5] == 1010 and t0[3] == 1 and t0[7] == 2
+    assert (lo0, hi1) == (0, 101) and hi0 == lo1
+    assert d0 + d1 == philox.reset_draws(9, np.arange(101), 0)[:, 0].tolist()
