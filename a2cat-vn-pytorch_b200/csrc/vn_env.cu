@@ -7,6 +7,7 @@
 //   K2 vn_gather_*      one CTA per env: copies the env's observation planes (and, only if the env just
 //                       reset, its goal planes) from the HBM store into the contiguous policy batch.
 //                       >99.9 % of the bytes; HBM-bound; two variants (LDG.128 registers / bulk async copy).
+#include <cstdlib>
 #include <string>
 
 #include "vn_common.cuh"
@@ -44,12 +45,22 @@ struct StepParams {
     vn_step_out_t out;
     const int32_t *actions;  // NULL in reset mode
     const uint8_t *mask;     // reset mode only
+    int32_t *actions_copy;   // optional device copy of the actions (host-actions path)
 };
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 
+// Programmatic dependent launch: every kernel of the step path lets its successor be scheduled early
+// (launch latency overlaps this kernel's execution) and waits for its predecessor's memory to be visible
+// before touching any env data.  Both are no-ops when the launch was not programmatic.
+__device__ __forceinline__ void pdl_wait_then_release() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 template <bool kReset>
 __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
+    pdl_wait_then_release();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int flags = p.rules.flags;
     uint32_t st_episodes = 0, st_len = 0, st_succ = 0, st_coll = 0, st_steps = 0, st_trunc = 0, st_resets = 0;
@@ -67,7 +78,8 @@ __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
         if (kReset) {
             do_reset = p.mask ? (p.mask[i] != 0) : true;
         } else {
-            const int a = p.actions[i];
+            const int a = p.actions[i];  // may live in mapped pinned host memory (vn_env_step_host)
+            if (p.actions_copy) p.actions_copy[i] = a;
             const int s_old = s;
             bool terminal = false, collided = false;
             float r;
@@ -103,11 +115,29 @@ __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
             do_reset = done && (flags & VN_RULE_AUTO_RESET);
             obs_s = (terminal && (flags & VN_RULE_TERM_PREV_OBS) && !do_reset) ? s_old : s;
 
+            const uint8_t trunc_code = at_limit ? (trunc ? 1 : 2) : 0;
             if (p.out.reward) p.out.reward[i] = r;
             if (p.out.done) p.out.done[i] = done;
-            if (p.out.truncated) p.out.truncated[i] = at_limit ? (trunc ? 1 : 2) : 0;
+            if (p.out.truncated) p.out.truncated[i] = trunc_code;
             if (p.out.win) p.out.win[i] = terminal;
             if (p.out.info_state) p.out.info_state[i] = s;
+            if (p.out.host_pack) {
+                // mirror of the per-env scalars written straight into mapped pinned host memory
+                // (layout: vn_b200.h "host pack"): the host reads them after the event that follows
+                // this kernel, with no copy-engine operation on the critical path
+                uint8_t *hp = p.out.host_pack;
+                const size_t n = (size_t)p.env.n_envs;
+                reinterpret_cast<float *>(hp)[i] = r;
+                reinterpret_cast<int32_t *>(hp + 12 * n)[i] = s;
+                hp[16 * n + i] = done;
+                hp[17 * n + i] = trunc_code;
+                hp[18 * n + i] = terminal;
+                hp[19 * n + i] = do_reset;
+                if (done) {
+                    reinterpret_cast<float *>(hp + 4 * n)[i] = ep_ret;
+                    reinterpret_cast<int32_t *>(hp + 8 * n)[i] = ep_len;
+                }
+            }
             if (done) {
                 if (p.out.episode_return) p.out.episode_return[i] = ep_ret;
                 if (p.out.episode_length) p.out.episode_length[i] = ep_len;
@@ -236,6 +266,8 @@ __device__ __forceinline__ void copy_segment16(const uint8_t *__restrict__ src, 
 
 template <int kThreads, int kUnroll>
 __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherParams p) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int env = blockIdx.x; env < p.n; env += gridDim.x) {
         const int rec = __ldg(p.obs_state + env);
         const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
@@ -263,47 +295,84 @@ __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherPar
 // One warp per CTA; lane 0 issues one cp.async.bulk per plane into shared memory (completion counted in
 // bytes on an mbarrier), then one cp.async.bulk per plane from shared memory to the batch rows.  No data
 // passes through registers; several CTAs per SM keep ~200 KB of copies in flight.
-__device__ __forceinline__ void bulk_copy_record(const vn_store_t &st, const uint8_t *src, uint8_t *const *dst,
-                                                 int env, uint8_t *smem, uint64_t *bar, uint32_t &parity) {
+//
+// Work unit = (env, slice): each plane is cut into `split` slices of whole 16-byte units, so that
+// split > 1 gives more, smaller CTAs per SM.  Units are handed out by an atomic ticket counter
+// (persistent CTAs, dynamic scheduling): no CTA idles while another still has a queue of records.
+__device__ unsigned int g_sched[64][2];  // [slot][0] next ticket, [slot][1] CTAs finished; self-resetting
+
+__device__ __forceinline__ void bulk_copy_slice(const vn_store_t &st, const uint8_t *src, uint8_t *const *dst,
+                                                int env, int slice, int split, uint8_t *smem, uint64_t *bar,
+                                                uint32_t &parity) {
     // the previous shared->global reads of this buffer must have drained before it is refilled
     bulk_wait_read<0>();
     uint32_t total = 0;
     for (int pl = 0; pl < st.n_planes; ++pl)
-        if (dst[pl]) total += st.plane_bytes[pl];
+        if (dst[pl]) {
+            const int n16 = st.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
+            const int lo = min(slice * per, n16), hi = min(lo + per, n16);
+            total += (uint32_t)(hi - lo) << 4;
+        }
+    if (total == 0) return;
     mbar_expect_tx(bar, total);
     uint32_t off = 0;
     for (int pl = 0; pl < st.n_planes; ++pl)
         if (dst[pl]) {
-            bulk_g2s(smem + off, src + st.plane_off[pl], st.plane_bytes[pl], bar);
-            off += st.plane_bytes[pl];
+            const int n16 = st.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
+            const int lo = min(slice * per, n16), hi = min(lo + per, n16);
+            if (hi > lo) {
+                bulk_g2s(smem + off, src + st.plane_off[pl] + ((size_t)lo << 4), (uint32_t)(hi - lo) << 4, bar);
+                off += (uint32_t)(hi - lo) << 4;
+            }
         }
     mbar_wait(bar, parity);
     parity ^= 1;
     off = 0;
     for (int pl = 0; pl < st.n_planes; ++pl)
         if (dst[pl]) {
-            bulk_s2g(dst[pl] + (size_t)env * st.plane_bytes[pl], smem + off, st.plane_bytes[pl]);
-            off += st.plane_bytes[pl];
+            const int n16 = st.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
+            const int lo = min(slice * per, n16), hi = min(lo + per, n16);
+            if (hi > lo) {
+                bulk_s2g(dst[pl] + (size_t)env * st.plane_bytes[pl] + ((size_t)lo << 4), smem + off,
+                         (uint32_t)(hi - lo) << 4);
+                off += (uint32_t)(hi - lo) << 4;
+            }
         }
     bulk_commit();
 }
 
-__global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p) {
+__global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p, int split, int slot, int dynamic) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     if (threadIdx.x != 0) return;
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the prologue above overlapped the scalar kernel; its results are needed from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     uint32_t parity = 0;
-    for (int env = blockIdx.x; env < p.n; env += gridDim.x) {
+    const int units = p.n * split;
+    int u = dynamic ? (int)atomicAdd(&g_sched[slot][0], 1u) : (int)blockIdx.x;
+    while (u < units) {
+        const int env = u / split, slice = u - env * split;
         const uint8_t *src = p.store.base + (size_t)p.obs_state[env] * p.store.state_pitch;
-        bulk_copy_record(p.store, src, p.obs, env, smem, &bar, parity);
+        bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, &bar, parity);
         if (p.goal && (!p.did_reset || p.did_reset[env])) {
             const uint8_t *gsrc = p.store.base + (size_t)p.goal[env] * p.store.state_pitch;
-            bulk_copy_record(p.store, gsrc, p.goal_obs, env, smem, &bar, parity);
+            bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity);
         }
+        u = dynamic ? (int)atomicAdd(&g_sched[slot][0], 1u) : u + (int)gridDim.x;
     }
     bulk_wait_read<0>();
+    if (dynamic) {
+        // last CTA out re-arms the slot for the launch that will reuse it
+        __threadfence();
+        if (atomicAdd(&g_sched[slot][1], 1u) == gridDim.x - 1) {
+            g_sched[slot][0] = 0;
+            g_sched[slot][1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // =====================================================================================================
@@ -353,6 +422,25 @@ static int32_t validate_store(const vn_store_t *s) {
     return VN_OK;
 }
 
+// Launch with programmatic stream serialisation allowed (PDL): the kernel may be scheduled while its
+// predecessor in the stream is still running; it synchronises itself with griddepcontrol.wait.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !(getenv("VN_NO_PDL") && atoi(getenv("VN_NO_PDL")));
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int g_sm_count = 0;
 static int sm_count() {
     if (!g_sm_count) {
@@ -372,17 +460,29 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         VN_REQUIRE(!gp.goal_obs[pl] || (reinterpret_cast<uintptr_t>(gp.goal_obs[pl]) & 15) == 0,
                    "gather: goal_obs[%d] must be 16-byte aligned", pl);
     }
-    if (variant == VN_GATHER_AUTO) variant = VN_GATHER_LDG;
+    if (variant == VN_GATHER_AUTO) {
+        // measured on B200 (profiles/): the bulk-copy variant reaches 94 % of the copy peak, LDG.128 86 %
+        int per_env = 0;
+        for (int pl = 0; pl < gp.store.n_planes; ++pl)
+            if (gp.obs[pl]) per_env += gp.store.plane_bytes[pl];
+        variant = per_env <= 100 * 1024 ? VN_GATHER_BULK : VN_GATHER_LDG;
+    }
     if (variant == VN_GATHER_LDG) {
         constexpr int kThreads = 256;
-        vn_gather_ldg_kernel<kThreads, 4><<<gp.n, kThreads, 0, stream>>>(gp);
+        launch_pdl(vn_gather_ldg_kernel<kThreads, 4>, dim3(gp.n), dim3(kThreads), 0, stream, gp);
         return check_launch("vn_gather_ldg_kernel");
     }
     if (variant == VN_GATHER_BULK) {
+        // tunables (development overrides through the environment; defaults chosen from profiles/)
+        static const int env_split = getenv("VN_BULK_SPLIT") ? atoi(getenv("VN_BULK_SPLIT")) : 0;
+        static const int env_per_sm = getenv("VN_BULK_PER_SM") ? atoi(getenv("VN_BULK_PER_SM")) : 0;
+        static const int env_dynamic = getenv("VN_BULK_DYNAMIC") ? atoi(getenv("VN_BULK_DYNAMIC")) : 1;
+        const int split = env_split > 0 ? env_split : 1;
         int smem_obs = 0, smem_goal = 0;
         for (int pl = 0; pl < gp.store.n_planes; ++pl) {
-            if (gp.obs[pl]) smem_obs += gp.store.plane_bytes[pl];
-            if (gp.goal && gp.goal_obs[pl]) smem_goal += gp.store.plane_bytes[pl];
+            const int n16 = gp.store.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
+            if (gp.obs[pl]) smem_obs += per << 4;
+            if (gp.goal && gp.goal_obs[pl]) smem_goal += per << 4;
         }
         const int smem = max(smem_obs, smem_goal);
         VN_REQUIRE(smem <= 200 * 1024, "gather(bulk): %d bytes of planes per env exceed shared memory", smem);
@@ -391,9 +491,12 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
             cudaFuncSetAttribute(vn_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             configured = smem;
         }
-        const int per_sm = max(1, min(32, (220 * 1024) / (smem + 1024)));
-        const int grid = min(gp.n, sm_count() * per_sm);
-        vn_gather_bulk_kernel<<<grid, 32, smem, stream>>>(gp);
+        int per_sm = max(1, min(32, (220 * 1024) / (smem + 1024)));
+        if (env_per_sm > 0) per_sm = min(per_sm, env_per_sm);
+        const int grid = (int)min((int64_t)gp.n * split, (int64_t)sm_count() * per_sm);
+        static unsigned launch_seq = 0;
+        const int slot = (int)(launch_seq++ & 63u);
+        launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, split, slot, env_dynamic);
         return check_launch("vn_gather_bulk_kernel");
     }
     set_error("gather: unknown variant %d", variant);
@@ -402,7 +505,7 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
 
 static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
                           const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask,
-                          const vn_step_out_t *out, void *stream, bool reset) {
+                          const vn_step_out_t *out, void *stream, bool reset, int32_t *actions_copy = nullptr) {
     VN_REQUIRE(tab && tab->adj && tab->task_goal && tab->task_cand_off && tab->task_prefix && tab->cand_state,
                "tables: null pointer");
     VN_REQUIRE(tab->n_tasks > 0, "tables: n_tasks=%d", tab->n_tasks);
@@ -427,13 +530,14 @@ static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const v
     sp.out = *out;
     sp.actions = actions;
     sp.mask = mask;
+    sp.actions_copy = actions_copy;
     const int threads = 128;
     const int blocks = (envs->n_envs + threads - 1) / threads;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (reset)
-        vn_step_kernel<true><<<blocks, threads, 0, st>>>(sp);
+        launch_pdl(vn_step_kernel<true>, dim3(blocks), dim3(threads), 0, st, sp);
     else
-        vn_step_kernel<false><<<blocks, threads, 0, st>>>(sp);
+        launch_pdl(vn_step_kernel<false>, dim3(blocks), dim3(threads), 0, st, sp);
     return check_launch("vn_step_kernel");
 }
 
@@ -524,6 +628,62 @@ int32_t vn_env_step_scalar(const vn_tables_t *tables, const vn_envs_t *envs, con
 int32_t vn_env_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
                       int32_t gather_variant, void *stream) {
     return vn::run_gather(store, envs, out, gather_variant, stream);
+}
+
+int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
+                         const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
+                         int32_t *dev_actions_copy, const vn_step_out_t *out, void *ready_event,
+                         int32_t gather_variant, void *stream) {
+    int32_t rc = vn::validate_store(store);
+    if (rc) return rc;
+    VN_REQUIRE(host_actions, "step_host: host_actions is null");
+    cudaPointerAttributes pa;
+    VN_REQUIRE(cudaPointerGetAttributes(&pa, host_actions) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                   pa.devicePointer != nullptr,
+               "step_host: host_actions must be pinned (page-locked, device-mapped) host memory");
+    if (out && out->host_pack) {
+        VN_REQUIRE(cudaPointerGetAttributes(&pa, out->host_pack) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
+                       pa.devicePointer != nullptr,
+                   "step_host: out->host_pack must be pinned (page-locked, device-mapped) host memory");
+    }
+    // the scalar kernel reads the actions from, and mirrors its per-env results to, mapped host memory
+    rc = vn::run_scalar(tables, envs, rules, inject, host_actions, nullptr, out, stream, false, dev_actions_copy);
+    if (rc) return rc;
+    if (ready_event) {
+        cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(ready_event), static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) {
+            vn::set_error("step_host: event record: %s", cudaGetErrorString(e));
+            return VN_ECUDA;
+        }
+    }
+    return vn::run_gather(store, envs, out, gather_variant, stream);
+}
+
+int32_t vn_event_create(void **event) {
+    VN_REQUIRE(event, "event_create: null");
+    cudaEvent_t ev;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        vn::set_error("event_create: %s", cudaGetErrorString(e));
+        return VN_ECUDA;
+    }
+    *event = ev;
+    return VN_OK;
+}
+
+int32_t vn_event_destroy(void *event) {
+    if (event) cudaEventDestroy(static_cast<cudaEvent_t>(event));
+    return VN_OK;
+}
+
+int32_t vn_event_wait(void *event) {
+    VN_REQUIRE(event, "event_wait: null");
+    cudaError_t e = cudaEventSynchronize(static_cast<cudaEvent_t>(event));
+    if (e != cudaSuccess) {
+        vn::set_error("event_wait: %s", cudaGetErrorString(e));
+        return VN_ECUDA;
+    }
+    return VN_OK;
 }
 
 int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, uint8_t *out,

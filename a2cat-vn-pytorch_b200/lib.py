@@ -54,7 +54,8 @@ class Inject(C.Structure):
 class StepOut(C.Structure):
     _fields_ = [("obs", _P * VN_MAX_PLANES), ("goal_obs", _P * VN_MAX_PLANES), ("reward", _P), ("done", _P),
                 ("truncated", _P), ("win", _P), ("did_reset", _P), ("last_action_reward", _P),
-                ("episode_return", _P), ("episode_length", _P), ("info_state", _P), ("obs_state", _P), ("stats", _P)]
+                ("episode_return", _P), ("episode_length", _P), ("info_state", _P), ("obs_state", _P), ("stats", _P),
+                ("host_pack", _P)]
 
 
 class VnError(RuntimeError):
@@ -65,7 +66,7 @@ _lib = None
 
 #: every symbol include/vn_b200.h declares
 EXPORTS = ("vn_abi_version", "vn_last_error", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
-           "vn_env_gather", "vn_gather_plane",
+           "vn_env_gather", "vn_env_step_host", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_nstep_returns", "vn_discounted_backup", "vn_pixel_control",
            "vn_aux_target", "vn_rp_labels")
 
@@ -99,6 +100,10 @@ def load(build_if_missing=True):
         "vn_env_step": (i32, [S, T, E, R, I, _P, O, i32, _P]),
         "vn_env_step_scalar": (i32, [T, E, R, I, _P, O, _P]),
         "vn_env_gather": (i32, [S, E, O, i32, _P]),
+        "vn_env_step_host": (i32, [S, T, E, R, I, _P, _P, O, _P, i32, _P]),
+        "vn_event_create": (i32, [C.POINTER(_P)]),
+        "vn_event_destroy": (i32, [_P]),
+        "vn_event_wait": (i32, [_P]),
         "vn_gather_plane": (i32, [S, i32, _P, i32, _P, i32, _P]),
         "vn_gather_plane_f32_chw": (i32, [S, i32, _P, i32, i32, i32, i32, _P, _P]),
         "vn_nstep_returns": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, _P]),

@@ -199,6 +199,11 @@ class GraphVecEnv:
         out.episode_return, out.episode_length = self.episode_return.data_ptr(), self.episode_length.data_ptr()
         out.info_state, out.obs_state, out.stats = self.info_state.data_ptr(), self.obs_state.data_ptr(), self.stats.data_ptr()
         self._c_out = out
+        # same outputs + the mapped pinned host mirror of the per-env scalars (host-actions path)
+        out_h = L.StepOut()
+        C.memmove(C.byref(out_h), C.byref(out), C.sizeof(L.StepOut))
+        out_h.host_pack = self._pack_host.data_ptr()
+        self._c_out_host = out_h
 
         def frame(leaf):
             p = leaf[5:] if leaf.startswith("goal_") else leaf
@@ -217,6 +222,13 @@ class GraphVecEnv:
         self._pending = False
         self.closed = False
         self.kernel_launches = 0
+        # host path: pinned staging seen as numpy views + an event recorded after the scalar results
+        # have landed on the host (the gather is still running when step() returns)
+        self._actions_np = self._actions_host.numpy()
+        self._pack_np = self._pack_host.numpy()
+        self._ready = C.c_void_p()
+        L.check(self.lib.vn_event_create(C.byref(self._ready)))
+        self._p_inject = C.byref(self._c_inject) if self._c_inject is not None else None
 
     # ------------------------------------------------------------------ construction helpers
     def _default_env_tasks(self, num_envs):
@@ -270,12 +282,28 @@ class GraphVecEnv:
 
     def step_async(self, actions):
         self._check_open()
+        inj = C.byref(self._c_inject) if self._c_inject is not None else None
+        if self.host_outputs and not (torch.is_tensor(actions) and actions.is_cuda):
+            # reference-facing path: host actions in, host scalars out - ONE C call enqueues
+            # H2D, scalar kernel, D2H, event, gather kernel
+            a = np.asarray(actions.cpu() if torch.is_tensor(actions) else actions).reshape(-1)
+            if a.size != self.num_envs:
+                raise ValueError("expected %d actions, got %d" % (self.num_envs, a.size))
+            self._actions_np[:] = a
+            self._last_actions = self._actions_np
+            with torch.cuda.device(self.device):
+                L.check(self.lib.vn_env_step_host(
+                    C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs), C.byref(self._c_rules),
+                    inj, self._actions_host.data_ptr(), self.actions_dev.data_ptr(), C.byref(self._c_out_host),
+                    self._ready, self.gather, self._stream()))
+            self._pending = "host"
+            self.kernel_launches += 2
+            return
         if torch.is_tensor(actions) and actions.is_cuda:
             a = actions if actions.dtype == torch.int32 else actions.to(torch.int32)
             a = a.contiguous()
         else:
             src = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
-            # baselines passes None for "no action" only to single envs; -1 is the batched spelling
             self._actions_host.copy_(src.reshape(-1).to(torch.int32))
             self.actions_dev.copy_(self._actions_host, non_blocking=True)
             a = self.actions_dev
@@ -284,11 +312,10 @@ class GraphVecEnv:
         self._last_actions = a
         with torch.cuda.device(self.device):
             L.check(self.lib.vn_env_step(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
-                                         C.byref(self._c_rules),
-                                         C.byref(self._c_inject) if self._c_inject is not None else None,
-                                         a.data_ptr(), C.byref(self._c_out), self.gather, self._stream()))
+                                         C.byref(self._c_rules), inj, a.data_ptr(), C.byref(self._c_out), self.gather,
+                                         self._stream()))
         self.kernel_launches += 2
-        self._pending = True
+        self._pending = "device"
 
     def _unpack(self, host):
         n = self.num_envs
@@ -300,14 +327,18 @@ class GraphVecEnv:
     def step_wait(self):
         if not self._pending:
             raise RuntimeError("step_wait() without step_async()")
-        self._pending = False
+        mode, self._pending = self._pending, False
         noop = (self._last_actions < 0) if self.family.noop_action else None
+        if mode == "host":
+            # wait for the scalars only; the gather of this step is still in flight on the stream
+            L.check(self.lib.vn_event_wait(self._ready))
+            h = self._unpack(self._pack_np.copy())
+            return self._obs(), h["reward"], h["done"].view(np.bool_), LazyInfos(self, h, noop)
         if self.host_outputs:
-            # reference behaviour: rewards / dones are host numpy arrays -> one packed D2H copy + sync
             self._pack_host.copy_(self._pack, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            h = self._unpack(self._pack_host.numpy().copy())
-            return self._obs(), h["reward"], h["done"].astype(bool), LazyInfos(self, h, noop)
+            h = self._unpack(self._pack_np.copy())
+            return self._obs(), h["reward"], h["done"].view(np.bool_), LazyInfos(self, h, noop)
         fetch = lambda: self._unpack(self._pack.cpu().numpy())
         return self._obs(), self.reward, self.done.bool(), LazyInfos(self, fetch, noop)
 
@@ -316,6 +347,9 @@ class GraphVecEnv:
         return self.step_wait()
 
     def close(self):
+        if not self.closed and self._ready:
+            self.lib.vn_event_destroy(self._ready)
+            self._ready = C.c_void_p()
         self.closed = True
 
     def _check_open(self):

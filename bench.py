@@ -8,7 +8,9 @@
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): one synthetic
 thor-cached scene, 1,500 positions x 4 rotations = 6,000 states, 84x84 RGB + depth + goal frame,
 4,096 envs per GPU (weak scaling: every GPU steps its own 4,096 envs, store replicated), uniform
-random actions, TimeLimit 900, curriculum hardness 0.01 (experiments/thor_cached_auxiliary.py:70).
+random actions, TimeLimit 900, no curriculum by default (start states uniform over the scene, so the
+4,096 envs read ~4,096 different frames per step and the gather is HBM-bound; with the reference's
+initial hardness 0.01 - `--hardness 0.01` - the envs cluster around the goals and most reads hit L2).
 One "step" = one vectorised step of all envs.  Rank 0 prints ONE JSON line.
 """
 import argparse
@@ -28,7 +30,7 @@ import numpy as np  # noqa: E402
 ENVS_PER_GPU = 4096
 N_CELLS, GRID = 1500, (50, 60)
 MAX_EPISODE_STEPS = 900
-HARDNESS = 0.01
+HARDNESS = None
 SCENE_SEED = 0
 F_RGB, F_DEPTH = 84 * 84 * 3, 84 * 84
 WORKLOAD = "C2 synthetic thor-cached scene: 1,500 positions x 4 rotations, 84x84 RGB+depth+goal, 4,096 envs per GPU"
@@ -46,7 +48,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -64,7 +66,7 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake": 0x80, "sync_boost": 0x10}
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -79,7 +81,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -124,7 +126,7 @@ def _cpu_world(n_envs, seed):
     for i in range(n_envs):
         goal = scene.goals[i % len(scene.goals)]          # one env per (scene, goal) task, dealt round-robin
         e = oenvs.GymGraphRgbdGoalEnv(osc, goals=goal)
-        e.set_complexity(HARDNESS)
+        e.set_complexity(_CPU.get("hardness", HARDNESS))
         e.reset_source = ovec.ReferenceStyleResetSource(osc, [goal], lambda t, e=e: e.optimal_distance(), seed + i)
         envs.append(ovec.RewardCollector(ovec.TimeLimit(e, MAX_EPISODE_STEPS)))
     return ovec.VecEnv(envs)
@@ -202,10 +204,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _CPU["hardness"] = None if args.hardness in (None, "none") else float(args.hardness)
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
-    n_envs = 16 * workers                     # bounded sample of the workload: 16 envs per worker
     steps = args.steps if args.steps else 300
+    # bounded sample of the workload: 16 envs per worker, fewer when K is large (<= ~1.5 M env-steps in all)
+    n_envs = max(workers, min(16 * workers, int(1.5e6 / max(1, steps))))
     warm = args.warmup if args.warmup is not None else 5
     value, nres, dt = cpu_run(n_envs, steps, warm, workers)
     line = {
@@ -248,7 +252,9 @@ def run_cuda(args):
     env = vn.GraphVecEnv(world, n_total, device=dev, seed=1, max_episode_steps=MAX_EPISODE_STEPS,
                          obs_layout="rgbd_goal", unreal_wrapper=True, rank=rank, world_size=world_size,
                          gather=args.gather, host_outputs=False)
-    env.set_complexity(HARDNESS)
+    hardness = None if args.hardness in (None, "none") else float(args.hardness)
+    _CPU["hardness"] = hardness
+    env.set_complexity(hardness)
     N = env.num_envs
     # action stream resident in HBM: cyclic buffer of uniform random actions (Philox via torch generator)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -266,6 +272,7 @@ def run_cuda(args):
             env.step_async(actions[i % n_rows])
             env._pending = False
 
+    device_loop(0, args.mix)      # un-timed: lets the state distribution settle (random-walk mixing)
     device_loop(0, W)
     env.stats.zero_()
     barrier()
@@ -315,11 +322,37 @@ def run_cuda(args):
     alg_bytes = N * (2 * (F_RGB + F_DEPTH) + p_reset_r * 2 * F_RGB)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
+    # calibration: a plain contiguous device copy of the SAME number of bytes (torch copy_, the operation the
+    # measured peak was taken with, but at this kernel's size instead of 2 GiB) - what a ~40 us transfer can reach
+    nb = N * (F_RGB + F_DEPTH)
+    src_c = torch.empty(nb, dtype=torch.uint8, device=dev).random_(0, 255)
+    dst_c = torch.empty_like(src_c)
+    big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cal = []
+    for i in range(30):
+        big.zero_()                                  # flush L2 between calibration copies
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        dst_c.copy_(src_c)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        cal.append(c0.elapsed_time(c1))
+    copy_ms = float(np.median(cal[5:]))
+    del src_c, dst_c, big
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": profiled_traffic(), "kernel": "vn_gather_%s_kernel" % args.gather_name(env),
                 "kernel_ms": gather_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "same_size_copy_ms": copy_ms, "same_size_copy_gbs": 2 * nb / (copy_ms * 1e-3) / 1e9,
                 "step_frac": (N * (2 * (F_RGB + F_DEPTH) + p_reset * 2 * F_RGB + 40)) / (ms * 1e-3 / K) / 1e9 / peak
                 if world_size == 1 else None}
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / K, "kernel_ms": gather_ms, "frac": roofline["frac"],
+                              "step_frac": roofline["step_frac"], "p_reset": p_reset}))
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- e2e through the public VecEnv API: host actions in, host rewards/dones out, every step
     env_e = vn.GraphVecEnv(world, n_total, device=dev, seed=2, max_episode_steps=MAX_EPISODE_STEPS,
@@ -373,7 +406,7 @@ def run_cuda(args):
                        "store_bytes": env.dw.nbytes(), "batch_bytes_per_step": N * (2 * F_RGB + F_DEPTH),
                        "l2": "inputs larger than L2: 169 MB store + 116 MB batch touched per step vs 126 MB L2",
                        "gather": args.gather, "p_reset": p_reset, "collision_rate": coll,
-                       "max_episode_steps": MAX_EPISODE_STEPS, "hardness": HARDNESS,
+                       "max_episode_steps": MAX_EPISODE_STEPS, "hardness": hardness, "mix_steps": args.mix,
                        "parallelism": "env-sharded x%d, no data-path collective" % world_size},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -391,6 +424,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="development: device-resident number + roofline only")
+    ap.add_argument("--hardness", default="none", help="curriculum hardness (set_complexity); 'none' = uniform starts")
+    ap.add_argument("--mix", type=int, default=1000, help="un-timed steps before warm-up")
     args = ap.parse_args()
     args.gather_name = lambda env: {0: "auto", 1: "ldg", 2: "bulk"}[env.gather]
     if args.impl == "reference":

@@ -140,6 +140,11 @@ typedef struct vn_step_out {
     int32_t *info_state;              /* [n_envs] info['state']: state after the move, before auto-reset */
     int32_t *obs_state;               /* [n_envs] state whose frames were gathered (scratch, required) */
     uint64_t *stats;                  /* [VN_N_STATS] running sums, see VN_STAT_* */
+    uint8_t *host_pack;               /* optional MAPPED PINNED HOST block of 20 * n_envs bytes ("host pack") that the
+                                         scalar kernel also writes, n = n_envs:
+                                           [0, 4n) reward f32 | [4n, 8n) episode_return f32 | [8n, 12n) episode_length i32
+                                           | [12n, 16n) info_state i32 | [16n, 17n) done | [17n, 18n) truncated
+                                           | [18n, 19n) win | [19n, 20n) did_reset */
 } vn_step_out_t;
 
 /* gather kernel variants (all bit-identical) */
@@ -179,6 +184,23 @@ int32_t vn_env_step_scalar(const vn_tables_t *tables, const vn_envs_t *envs, con
                            const vn_inject_t *inject, const int32_t *actions, const vn_step_out_t *out, void *stream);
 int32_t vn_env_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
                       int32_t gather_variant, void *stream);
+
+/* The reference-facing call with HOST buffers: VecEnv.step(actions) as deep_rl's trainer makes it
+ * (numpy actions in, numpy rewards / dones / infos out; experiments/thor_cached_auxiliary.py:67 +
+ * SubprocVecEnv.step).  host_actions and out->host_pack are PINNED host memory (device-mapped under
+ * UVA).  Enqueues, in stream order: the scalar half - which reads the actions straight from
+ * host_actions and mirrors the per-env scalars into out->host_pack over PCIe, so no copy-engine
+ * operation sits on the critical path -; a record of ready_event; the gather half.  The host waits on
+ * ready_event (vn_event_wait), i.e. for the scalars only, while the gather keeps running; the
+ * observations stay in HBM, ordered before any later work on the same stream.  dev_actions_copy
+ * (optional) receives a device copy of the actions for device-side consumers (rollout buffer). */
+int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
+                         const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
+                         int32_t *dev_actions_copy, const vn_step_out_t *out, void *ready_event,
+                         int32_t gather_variant, void *stream);
+int32_t vn_event_create(void **event);   /* cudaEventDisableTiming */
+int32_t vn_event_destroy(void *event);
+int32_t vn_event_wait(void *event);      /* cudaEventSynchronize; releases the GIL under ctypes */
 
 /* out[i] = plane `plane` of store record idx[i] (replay / sample_sequence gathers,
  * experiments/ai2_auxiliary/trainer.py:29). */
