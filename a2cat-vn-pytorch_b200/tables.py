@@ -184,13 +184,20 @@ def scene_max_dist(scene: GridScene) -> int:
 
 def build_task(scene: GridScene, scene_idx: int, goal, family: Family, max_dist: Optional[int] = None) -> Task:
     if max_dist is None:
-        max_dist = scene_max_dist(scene)
+        max_dist = 0 if family.name == "thor_cached" else scene_max_dist(scene)   # cached.py has no curriculum
     rank = scene.cell_rank
     if family.name == "thor_cached":
         # goal is a flat state index (cached.py:39); candidates = {s : dist[s][goal] > 0} with
         # dist = grid_dist + rot_diff, rot_diff 3 -> 1 (graph/util.py:240-247).  Literal, including
         # the quirk that an unreachable cell (-1) at rot_diff 2 has "distance" 1 > 0.
         g = int(goal)
+        spd = getattr(scene, "h5_spd", None)
+        if spd is not None:     # the file's own 'shortest_path_distance' dataset (loaders.scene_from_h5_arrays)
+            col = np.asarray(spd)[:, g]
+            states = np.nonzero(col > 0)[0].astype(np.int32)
+            dist = col[states].astype(np.int32)
+            order = np.argsort(dist, kind="stable")
+            return Task(scene_idx, g, g, states[order], dist[order], max_dist)
         gx, gy = scene.cells[g >> 2]
         gr = g & 3
         d = bfs_distances(scene.maze, (gx, gy))[scene.cells[:, 0], scene.cells[:, 1]]   # [C]
@@ -299,7 +306,10 @@ def compile_world(scenes: Sequence[GridScene], family: Family, tasks: Optional[S
     base = np.zeros(len(scenes) + 1, np.int64)
     adjs = []
     for i, s in enumerate(scenes):
-        a = build_adjacency(s, family.action_order).astype(np.int64)
+        if getattr(s, "h5_graph", None) is not None and family.action_order == "h5":
+            a = np.asarray(s.h5_graph, np.int64)      # the file's own 'graph' dataset (loaders.scene_from_h5_arrays)
+        else:
+            a = build_adjacency(s, family.action_order).astype(np.int64)
         a = np.where(a >= 0, a + base[i], -1)
         adjs.append(a.astype(np.int32))
         base[i + 1] = base[i] + s.n_states
@@ -309,7 +319,7 @@ def compile_world(scenes: Sequence[GridScene], family: Family, tasks: Optional[S
     built = []
     for si, goal in tasks:
         if si not in maxd:
-            maxd[si] = scene_max_dist(scenes[si])
+            maxd[si] = 0 if family.name == "thor_cached" else scene_max_dist(scenes[si])
         built.append(build_task(scenes[si], si, goal, family, maxd[si]))
     off = np.zeros(len(built) + 1, np.int64)
     for i, t in enumerate(built):

@@ -28,6 +28,7 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 ENVS_PER_GPU = 4096
+_OVERRIDE = {}
 N_CELLS, GRID = 1500, (50, 60)
 MAX_EPISODE_STEPS = 900
 HARDNESS = None
@@ -248,7 +249,7 @@ def run_cuda(args):
 
     scene = make_scene(vn)
     world = vn.compile_world([scene], vn.GYM_GRAPH)
-    n_total = ENVS_PER_GPU * world_size
+    n_total = (args.envs_per_gpu or ENVS_PER_GPU) * world_size
     env = vn.GraphVecEnv(world, n_total, device=dev, seed=1, max_episode_steps=MAX_EPISODE_STEPS,
                          obs_layout="rgbd_goal", unreal_wrapper=True, rank=rank, world_size=world_size,
                          gather=args.gather, host_outputs=False)
@@ -322,23 +323,25 @@ def run_cuda(args):
     alg_bytes = N * (2 * (F_RGB + F_DEPTH) + p_reset_r * 2 * F_RGB)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
-    # calibration: a plain contiguous device copy of the SAME number of bytes (torch copy_, the operation the
-    # measured peak was taken with, but at this kernel's size instead of 2 GiB) - what a ~40 us transfer can reach
+    # calibration: plain contiguous device copies of the SAME number of bytes (torch copy_, the operation the
+    # measured peak was taken with, but at this kernel's size instead of 2 GiB), back to back over 4 distinct
+    # (src, dst) pairs so that, like the gather in steady state, every copy starts with L2 full of the previous
+    # copy's dirty lines - what a ~40 us transfer can sustain on this GPU
     nb = N * (F_RGB + F_DEPTH)
-    src_c = torch.empty(nb, dtype=torch.uint8, device=dev).random_(0, 255)
-    dst_c = torch.empty_like(src_c)
-    big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    cal = []
-    for i in range(30):
-        big.zero_()                                  # flush L2 between calibration copies
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        dst_c.copy_(src_c)
-        c1.record()
-        torch.cuda.synchronize(dev)
-        cal.append(c0.elapsed_time(c1))
-    copy_ms = float(np.median(cal[5:]))
-    del src_c, dst_c, big
+    pairs = [(torch.empty(nb, dtype=torch.uint8, device=dev).random_(0, 255),
+              torch.empty(nb, dtype=torch.uint8, device=dev)) for _ in range(4)]
+    for i in range(8):
+        pairs[i % 4][1].copy_(pairs[i % 4][0])
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    c0.record()
+    for i in range(200):
+        pairs[i % 4][1].copy_(pairs[i % 4][0])
+    c1.record()
+    torch.cuda.synchronize(dev)
+    copy_ms = c0.elapsed_time(c1) / 200
+    del pairs
+
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": profiled_traffic(), "kernel": "vn_gather_%s_kernel" % args.gather_name(env),
                 "kernel_ms": gather_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
@@ -427,6 +430,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="development: device-resident number + roofline only")
     ap.add_argument("--hardness", default="none", help="curriculum hardness (set_complexity); 'none' = uniform starts")
     ap.add_argument("--mix", type=int, default=1000, help="un-timed steps before warm-up")
+    ap.add_argument("--envs-per-gpu", type=int, default=None, help="development: override the 4,096 envs per GPU")
     args = ap.parse_args()
     args.gather_name = lambda env: {0: "auto", 1: "ldg", 2: "bulk"}[env.gather]
     if args.impl == "reference":

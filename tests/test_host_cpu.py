@@ -203,3 +203,36 @@ def test_multi_rank_stats_reduce_gloo_world2():
     assert t0 == t1 and t0[0] == 101 and t0[5] == 1010 and t0[3] == 1 and t0[7] == 2
     assert (lo0, hi1) == (0, 101) and hi0 == lo1
     assert d0 + d1 == philox.reset_draws(9, np.arange(101), 0)[:, 0].tolist()
+
+
+def test_loaders_thor_grid_world_and_h5():
+    """Reference on-disk formats -> compiled world (loaders.py): dense ThorGridWorld arrays and the flat
+    h5 schema reproduce the tables / frames of the scene they were exported from."""
+    L = vn.loaders
+    scene = H.scenes.make_maze_scene((9, 8), 0.2, 31, n_goals=2, planes=("rgb", "depth", "segmentation"))
+    X, Y = scene.maze.shape
+
+    class TGW:      # duck-typed graph/multi_graph_no_tp.py:6-11
+        pass
+    g = TGW()
+    g._maze = scene.maze
+    for attr, plane, c in (("_observations", "rgb", 3), ("_depths", "depth", 1), ("_segmentations", "segmentation", 3)):
+        a = np.zeros((X, Y, 4, 84, 84, c), np.uint8)
+        a[scene.cells[:, 0], scene.cells[:, 1]] = scene.plane_frames(plane).reshape(scene.n_cells, 4, 84, 84, c)
+        setattr(g, attr, a)
+    loaded = L.scene_from_thor_grid_world(g, scene.goals)
+    for p in ("rgb", "depth", "segmentation"):
+        assert np.array_equal(loaded.plane_frames(p), scene.plane_frames(p))
+    w0, w1 = T.compile_world([scene], T.GYM_GRAPH), T.compile_world([loaded], T.GYM_GRAPH)
+    assert np.array_equal(w0.adj, w1.adj) and np.array_equal(w0.cand_state, w1.cand_state)
+    small = L.scene_from_thor_grid_world(g, scene.goals, screen_size=(44, 44), planes=("rgb",))
+    assert small.plane_frames("rgb").shape == (scene.n_states, 44, 44, 3)       # resize hoisted to load time
+
+    dist, _ = gu.compute_shortest_path_data(scene.maze)
+    _, graph, spd = gu.h5_tables(scene.maze, dist)
+    h5 = L.scene_from_h5_arrays(graph, scene.plane_frames("rgb"), spd)
+    wa = T.compile_world([H.scenes.GridScene(scene.maze, [], True, (84, 84), ("rgb",), frame_seed=scene.frame_seed)],
+                         T.THOR_CACHED, tasks=[(0, 5), (0, 40)])
+    wb = T.compile_world([h5], T.THOR_CACHED, tasks=[(0, 5), (0, 40)])
+    assert np.array_equal(wa.adj, wb.adj) and np.array_equal(wa.cand_state, wb.cand_state)
+    assert np.array_equal(wa.task_cand_off, wb.task_cand_off)
