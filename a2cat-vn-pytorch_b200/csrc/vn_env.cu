@@ -477,7 +477,10 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         static const int env_split = getenv("VN_BULK_SPLIT") ? atoi(getenv("VN_BULK_SPLIT")) : 0;
         static const int env_per_sm = getenv("VN_BULK_PER_SM") ? atoi(getenv("VN_BULK_PER_SM")) : 0;
         static const int env_dynamic = getenv("VN_BULK_DYNAMIC") ? atoi(getenv("VN_BULK_DYNAMIC")) : 1;
-        const int split = env_split > 0 ? env_split : 1;
+        // small batches (C1: 16 envs) cannot fill 148 SMs with one record per CTA: cut each record into
+        // slices until there are ~2 units per SM (latency-bound regime; one slice >= 2 KB)
+        int split = env_split > 0 ? env_split : 1;
+        if (env_split <= 0 && gp.n < 2 * sm_count()) split = min(16, (2 * sm_count() + gp.n - 1) / gp.n);
         int smem_obs = 0, smem_goal = 0;
         for (int pl = 0; pl < gp.store.n_planes; ++pl) {
             const int n16 = gp.store.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;

@@ -65,6 +65,31 @@ struct PoolGeom {
     int h, w, c, cell, out_h, out_w, top, left;
 };
 
+// out[cell] = mean_c avg_pool_cell(|nxt/255 - cur/255|) for one transition; frames and LUT in shared memory
+__device__ __forceinline__ void pc_cells(const uint8_t *cur, const uint8_t *nxt, const float *lut, const PoolGeom &g,
+                                         float *__restrict__ out_row) {
+    const int lane = threadIdx.x & 31;
+    const int cells = g.out_h * g.out_w;
+    const int row_bytes = g.w * g.c;
+    for (int cidx = threadIdx.x; cidx < cells; cidx += blockDim.x) {
+        const int oi = cidx / g.out_w, oj = cidx - oi * g.out_w;
+        float chan_sum = 0.f;
+        for (int ch = 0; ch < g.c; ++ch) {
+            float acc = 0.f;  // F.avg_pool2d: window sum in row-major order, then / cell^2
+            for (int dy = 0; dy < g.cell; ++dy) {
+                const int rowoff = (g.top + oi * g.cell + dy) * row_bytes + (g.left + oj * g.cell) * g.c + ch;
+                for (int dx = 0; dx < g.cell; ++dx) {
+                    const float a = lut[(int)nxt[rowoff + dx * g.c] * 32 + lane];
+                    const float b = lut[(int)cur[rowoff + dx * g.c] * 32 + lane];
+                    acc = __fadd_rn(acc, fabsf(__fsub_rn(a, b)));
+                }
+            }
+            chan_sum = __fadd_rn(chan_sum, __fdiv_rn(acc, (float)(g.cell * g.cell)));
+        }
+        out_row[cidx] = __fdiv_rn(chan_sum, (float)g.c);  // mean over channels
+    }
+}
+
 // CTA per (env n, chunk of time steps).  Frames of consecutive steps are kept in a 2-slot shared ring so
 // each frame is read from HBM/L2 once per chunk: (chunk + 1) / chunk reads per output.
 template <int kChunk>
@@ -80,7 +105,6 @@ __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t 
     const int env = blockIdx.x / chunks;
     const int k0 = (blockIdx.x - env * chunks) * kChunk;
     const int k1 = min(t, k0 + kChunk);
-    const int lane = threadIdx.x & 31;
     const int32_t *srow = states + (int64_t)env * (t + 1);
     const uint8_t *pbase = store.base + store.plane_off[plane];
 
@@ -88,31 +112,114 @@ __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t 
     load_frame(frame0, pbase + (size_t)srow[k0] * store.state_pitch, fbytes);
     uint8_t *cur = frame0, *nxt = frame1;
     const int cells = g.out_h * g.out_w;
-    const int row_bytes = g.w * g.c;
     for (int k = k0; k < k1; ++k) {
         load_frame(nxt, pbase + (size_t)srow[k + 1] * store.state_pitch, fbytes);
         __syncthreads();
-        for (int cidx = threadIdx.x; cidx < cells; cidx += blockDim.x) {
-            const int oi = cidx / g.out_w, oj = cidx - oi * g.out_w;
-            float chan_sum = 0.f;
-            for (int ch = 0; ch < g.c; ++ch) {
-                float acc = 0.f;  // F.avg_pool2d: window sum in row-major order, then / cell^2
-                for (int dy = 0; dy < g.cell; ++dy) {
-                    const int rowoff = (g.top + oi * g.cell + dy) * row_bytes + (g.left + oj * g.cell) * g.c + ch;
-                    for (int dx = 0; dx < g.cell; ++dx) {
-                        const float a = lut[(int)nxt[rowoff + dx * g.c] * 32 + lane];
-                        const float b = lut[(int)cur[rowoff + dx * g.c] * 32 + lane];
-                        acc = __fadd_rn(acc, fabsf(__fsub_rn(a, b)));
-                    }
-                }
-                chan_sum = __fadd_rn(chan_sum, __fdiv_rn(acc, (float)(g.cell * g.cell)));
-            }
-            out[((int64_t)env * t + k) * cells + cidx] = __fdiv_rn(chan_sum, (float)g.c);  // mean over channels
-        }
+        pc_cells(cur, nxt, lut, g, out + ((int64_t)env * t + k) * cells);
         __syncthreads();
         uint8_t *tmp = cur;
         cur = nxt;
         nxt = tmp;
+    }
+}
+
+// Direct pixel-control reward for a device-resident LIST of transitions (the reset transitions that the
+// per-scene transition table cannot serve).  Persistent CTAs loop over the list; its length is read from
+// device memory, so no host synchronisation is needed between the lookup pass and this one.
+__global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_store_t store, int plane,
+                                                                    const int32_t *__restrict__ states, int t,
+                                                                    PoolGeom g, const int32_t *__restrict__ pos,
+                                                                    const int32_t *__restrict__ count, int max_count,
+                                                                    float *__restrict__ out) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int fbytes = g.h * g.w * g.c;
+    float *lut = reinterpret_cast<float *>(smem_raw);
+    uint8_t *frame0 = smem_raw + 256 * 32 * sizeof(float);
+    uint8_t *frame1 = frame0 + ((fbytes + 15) & ~15);
+    const int m_total = min(*count, max_count);
+    if ((int)blockIdx.x >= m_total) return;
+    build_lut(lut);
+    const uint8_t *pbase = store.base + store.plane_off[plane];
+    const int cells = g.out_h * g.out_w;
+    for (int m = blockIdx.x; m < m_total; m += gridDim.x) {
+        const int p = pos[m];
+        const int env = p / t, k = p - env * t;
+        const int32_t *srow = states + (int64_t)env * (t + 1);
+        __syncthreads();
+        load_frame(frame0, pbase + (size_t)srow[k] * store.state_pitch, fbytes);
+        load_frame(frame1, pbase + (size_t)srow[k + 1] * store.state_pitch, fbytes);
+        __syncthreads();
+        pc_cells(frame0, frame1, lut, g, out + (int64_t)p * cells);
+    }
+}
+
+// rows[n][k] = pixel-control table row of transition states[n][k] -> states[n][k+1]
+constexpr int kRowZero = -1, kRowMiss = -2;
+__global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *__restrict__ adj,
+                                                                 const int32_t *__restrict__ states, int n, int t,
+                                                                 int32_t *__restrict__ rows,
+                                                                 int32_t *__restrict__ miss_pos,
+                                                                 int32_t *__restrict__ miss_count) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool miss = false;
+    if (p < (int64_t)n * t) {
+        const int env = (int)(p / t), k = (int)(p - (int64_t)env * t);
+        const int s = states[(int64_t)env * (t + 1) + k], s2 = states[(int64_t)env * (t + 1) + k + 1];
+        int row = kRowMiss;
+        if (s2 == s) {
+            row = kRowZero;  // collision / no-op: identical frames, |x - x| = 0 exactly
+        } else {
+            const int4 nb = __ldg(reinterpret_cast<const int4 *>(adj) + s);
+            if (nb.x == s2)
+                row = s * 4;
+            else if (nb.y == s2)
+                row = s * 4 + 1;
+            else if (nb.z == s2)
+                row = s * 4 + 2;
+            else if (nb.w == s2)
+                row = s * 4 + 3;
+        }
+        rows[p] = row;
+        miss = row == kRowMiss;
+    }
+    // warp-aggregated append of the misses (ballot + one atomic per warp)
+    const unsigned b = __ballot_sync(0xffffffffu, miss);
+    if (b) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == __ffs(b) - 1) base = atomicAdd(miss_count, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+        if (miss) miss_pos[base + __popc(b & ((1u << lane) - 1u))] = (int32_t)p;
+    }
+}
+
+// out[i] = table[idx[i]] (rows of row16 16-byte units); idx < 0 writes zeros (kRowZero) or leaves the row
+// untouched (kRowMiss: the list kernel fills it).  One warp per row, grid-stride.
+__global__ void __launch_bounds__(256) vn_gather_rows_kernel(const int4 *__restrict__ table, int row16,
+                                                             const int32_t *__restrict__ idx, int64_t n,
+                                                             int4 *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp0; i < n; i += nwarps) {
+        const int r = __ldg(idx + i);
+        if (r == kRowMiss) continue;
+        int4 *dst = out + i * row16;
+        if (r < 0) {
+            for (int k = lane; k < row16; k += 32) st_stream16(dst + k, make_int4(0, 0, 0, 0));
+        } else {
+            const int4 *src = table + (int64_t)r * row16;
+            int k = lane;
+            for (; k + 96 < row16; k += 128) {  // 4 independent 16-byte loads in flight per lane
+                const int4 v0 = __ldg(src + k), v1 = __ldg(src + k + 32), v2 = __ldg(src + k + 64),
+                           v3 = __ldg(src + k + 96);
+                st_stream16(dst + k, v0);
+                st_stream16(dst + k + 32, v1);
+                st_stream16(dst + k + 64, v2);
+                st_stream16(dst + k + 96, v3);
+            }
+            for (; k < row16; k += 32) st_stream16(dst + k, __ldg(src + k));
+        }
     }
 }
 
@@ -326,6 +433,57 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
     vn::vn_pixel_control_kernel<kChunk><<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         *store, plane, states, n, t, g, out);
     return vn::check_launch("vn_pixel_control_kernel");
+}
+
+int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int32_t *rows,
+                           int32_t *miss_pos, int32_t *miss_count, void *stream) {
+    VN_REQUIRE(adj && states && rows && miss_pos && miss_count, "transition_rows: null pointer");
+    VN_REQUIRE(n >= 0 && t >= 1, "transition_rows: n=%d t=%d", n, t);
+    VN_REQUIRE((reinterpret_cast<uintptr_t>(adj) & 15) == 0, "transition_rows: adj must be 16-byte aligned");
+    if (n == 0) return VN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(miss_count, 0, sizeof(int32_t), st);
+    const int64_t total = (int64_t)n * t;
+    vn::vn_transition_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(adj, states, n, t, rows, miss_pos,
+                                                                                  miss_count);
+    return vn::check_launch("vn_transition_rows_kernel");
+}
+
+int32_t vn_gather_rows(const void *table, int64_t row_bytes, const int32_t *idx, int64_t n, void *out, void *stream) {
+    VN_REQUIRE(table && idx && out, "gather_rows: null pointer");
+    VN_REQUIRE(row_bytes > 0 && (row_bytes & 15) == 0, "gather_rows: row_bytes=%lld must be a multiple of 16",
+               (long long)row_bytes);
+    VN_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+               "gather_rows: table and out must be 16-byte aligned");
+    if (n <= 0) return VN_OK;
+    const int64_t warps = n < 148 * 64 ? n : 148 * 64;
+    vn::vn_gather_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const int4 *>(table), (int)(row_bytes >> 4), idx, n, static_cast<int4 *>(out));
+    return vn::check_launch("vn_gather_rows_kernel");
+}
+
+int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
+                              int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w,
+                              const int32_t *pos, const int32_t *count, int32_t max_count, float *out, void *stream) {
+    int32_t rc = check_plane(store, plane, h, w, c, "pixel_control_list");
+    if (rc) return rc;
+    VN_REQUIRE(states && pos && count && out && n >= 0 && t >= 1 && max_count >= 0, "pixel_control_list: bad arguments");
+    vn::PoolGeom g;
+    rc = vn::pool_geom(h, w, c, cell, out_h, out_w, &g);
+    if (rc) return rc;
+    if (n == 0 || max_count == 0) return VN_OK;
+    const int fb = (h * w * c + 15) & ~15;
+    const int smem = 256 * 32 * 4 + 2 * fb;
+    VN_REQUIRE(smem <= 220 * 1024, "pixel_control_list: frame too large for shared memory");
+    static int configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(vn::vn_pixel_control_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = smem;
+    }
+    const int grid = max_count < 148 * 3 ? max_count : 148 * 3;
+    vn::vn_pixel_control_list_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        *store, plane, states, t, g, pos, count, max_count, out);
+    return vn::check_launch("vn_pixel_control_list_kernel");
 }
 
 int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t m, int32_t h, int32_t w,

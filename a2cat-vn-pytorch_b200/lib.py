@@ -68,6 +68,7 @@ _lib = None
 EXPORTS = ("vn_abi_version", "vn_last_error", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
            "vn_env_gather", "vn_env_step_host", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_nstep_returns", "vn_discounted_backup", "vn_pixel_control",
+           "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list",
            "vn_aux_target", "vn_rp_labels")
 
 
@@ -109,6 +110,9 @@ def load(build_if_missing=True):
         "vn_nstep_returns": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, _P]),
         "vn_discounted_backup": (i32, [_P, _P, _P, f32, i32, i32, i32, _P, _P]),
         "vn_pixel_control": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, i32, _P, _P]),
+        "vn_transition_rows": (i32, [_P, _P, i32, i32, _P, _P, _P, _P]),
+        "vn_gather_rows": (i32, [_P, i64, _P, i64, _P, _P]),
+        "vn_pixel_control_list": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, i32, _P, _P, i32, _P, _P]),
         "vn_aux_target": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, _P, _P]),
         "vn_rp_labels": (i32, [_P, i32, _P, _P, _P, _P, _P, _P]),
     }

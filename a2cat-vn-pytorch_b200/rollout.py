@@ -65,12 +65,9 @@ def _geom(dw, plane, cell, output_size):
     return pi, h, w, c, int(output_size[0]), int(output_size[1])
 
 
-def pixel_control_reward(dw: DeviceWorld, states, cell_size=4, output_size=None, plane="rgb"):
-    """deep_rl.a2c_unreal.util.pixel_control_reward (SURVEY.md D5) computed from state indices.
-    states: int32 [B, T+1] GLOBAL state of every observation of the sequence -> float32 [B, T, 1, h, w]."""
+def _pixel_control_direct(dw, states, cell_size, output_size, plane):
     lib = L.load()
     pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
-    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
     b, t1 = states.shape
     out = torch.empty((b, t1 - 1, 1, oh, ow), dtype=torch.float32, device=dw.device)
     with torch.cuda.device(dw.device):
@@ -79,26 +76,115 @@ def pixel_control_reward(dw: DeviceWorld, states, cell_size=4, output_size=None,
     return out
 
 
-def auxiliary_target(dw: DeviceWorld, states, plane, cell_size=4, output_size=None):
-    """compute_auxiliary_target (experiments/ai2_auxiliary/trainer.py:9-15) from state indices.
-    states int32 [B, T] -> float32 [B, T, C, h, w]."""
+def _aux_direct(dw, states, plane, cell_size, output_size):
     lib = L.load()
     pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
-    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
-    shape = tuple(states.shape)
-    out = torch.empty(shape + (c, oh, ow), dtype=torch.float32, device=dw.device)
+    out = torch.empty(tuple(states.shape) + (c, oh, ow), dtype=torch.float32, device=dw.device)
     with torch.cuda.device(dw.device):
         L.check(lib.vn_aux_target(C.byref(dw.store), pi, states.data_ptr(), states.numel(), h, w, c, cell_size, oh, ow,
                                   out.data_ptr(), _stream(states)))
     return out
 
 
-def auxiliary_targets(dw, states, goal_states, cell_size=4, output_size=None):
+class TargetTables:
+    """Per-world tables that turn the target builders into row gathers.  On a cached graph both targets
+    are pure functions of state indices, so they are evaluated once (with the direct kernels) and kept
+    resident in HBM - the same move as caching the frames themselves:
+
+      pc[s * 4 + a]  = pixel-control reward of the transition s -> adj[s][a]     [4 S, oh * ow] f32
+      aux[plane][s]  = avg_pool(crop(plane(s) / 255))                             [S, C, oh, ow] f32
+
+    C2 (6,000 states, 20x20): 38 MB + 10 MB (depth) + 29 MB (segmentation).
+    """
+
+    def __init__(self, dw: DeviceWorld, cell_size=4, output_size=None, plane="rgb"):
+        self.dw, self.cell, self.plane = dw, cell_size, plane
+        _, h, w, _, oh, ow = _geom(dw, plane, cell_size, output_size)
+        self.out_hw = (oh, ow)
+        S = dw.world.n_states
+        adj = dw.adj.view(S, 4)
+        me = torch.arange(S, dtype=torch.int32, device=dw.device)
+        nxt = torch.where(adj >= 0, adj, me[:, None])                       # collisions: s -> s (never looked up)
+        self.pc = torch.empty((4 * S, oh * ow), dtype=torch.float32, device=dw.device)
+        step = 1 << 16                                                       # bounded scratch while building
+        pairs = torch.stack([me.repeat_interleave(4), nxt.reshape(-1)], 1).contiguous()
+        for lo in range(0, 4 * S, step):
+            self.pc[lo:lo + step] = _pixel_control_direct(dw, pairs[lo:lo + step], cell_size, (oh, ow), plane).view(-1, oh * ow)
+        self._aux = {}
+
+    def aux(self, plane):
+        if plane not in self._aux:
+            S = self.dw.world.n_states
+            me = torch.arange(S, dtype=torch.int32, device=self.dw.device)
+            self._aux[plane] = _aux_direct(self.dw, me, plane, self.cell, self.out_hw).contiguous()
+        return self._aux[plane]
+
+    def nbytes(self):
+        return self.pc.numel() * 4 + sum(t.numel() * 4 for t in self._aux.values())
+
+
+def target_tables(dw: DeviceWorld, cell_size=4, output_size=None, plane="rgb") -> TargetTables:
+    """Cached per (world, plane, cell, output size)."""
+    _, _, _, _, oh, ow = _geom(dw, plane, cell_size, output_size)
+    cache = dw.__dict__.setdefault("_target_tables", {})
+    key = (plane, cell_size, oh, ow)
+    if key not in cache:
+        cache[key] = TargetTables(dw, cell_size, (oh, ow), plane)
+    return cache[key]
+
+
+def pixel_control_reward(dw: DeviceWorld, states, cell_size=4, output_size=None, plane="rgb", method="table"):
+    """deep_rl.a2c_unreal.util.pixel_control_reward (SURVEY.md D5) computed from state indices.
+    states: int32 [B, T+1] GLOBAL state of every observation of the sequence -> float32 [B, T, 1, h, w].
+
+    method="table" (default): rows of the per-world transition table (TargetTables) are gathered; the few
+    transitions the table cannot serve (resets) are computed directly by a list kernel in the same pass.
+    method="direct": every transition is computed from the two frames.  Both give identical bits."""
+    lib = L.load()
+    pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
+    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
+    if method == "direct" or (oh * ow) % 4:
+        return _pixel_control_direct(dw, states, cell_size, (oh, ow), plane)
+    tab = target_tables(dw, cell_size, (oh, ow), plane)
+    b, t1 = states.shape
+    t = t1 - 1
+    out = torch.empty((b, t, 1, oh, ow), dtype=torch.float32, device=dw.device)
+    rows = torch.empty(b * t, dtype=torch.int32, device=dw.device)
+    miss_pos = torch.empty(b * t, dtype=torch.int32, device=dw.device)
+    miss_count = torch.empty(1, dtype=torch.int32, device=dw.device)
+    with torch.cuda.device(dw.device):
+        st = _stream(states)
+        L.check(lib.vn_transition_rows(dw.adj.data_ptr(), states.data_ptr(), b, t, rows.data_ptr(), miss_pos.data_ptr(),
+                                       miss_count.data_ptr(), st))
+        L.check(lib.vn_gather_rows(tab.pc.data_ptr(), oh * ow * 4, rows.data_ptr(), b * t, out.data_ptr(), st))
+        L.check(lib.vn_pixel_control_list(C.byref(dw.store), pi, states.data_ptr(), b, t, h, w, c, cell_size, oh, ow,
+                                          miss_pos.data_ptr(), miss_count.data_ptr(), b * t, out.data_ptr(), st))
+    return out
+
+
+def auxiliary_target(dw: DeviceWorld, states, plane, cell_size=4, output_size=None, method="table"):
+    """compute_auxiliary_target (experiments/ai2_auxiliary/trainer.py:9-15) from state indices.
+    states int32 [B, T] -> float32 [B, T, C, h, w].  method="table": one row gather from the per-world
+    pooled-plane table; method="direct": pooled from the frame."""
+    lib = L.load()
+    pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
+    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
+    if method == "direct" or (c * oh * ow) % 4:
+        return _aux_direct(dw, states, plane, cell_size, (oh, ow))
+    tab = target_tables(dw, cell_size, (oh, ow)).aux(plane)
+    out = torch.empty(tuple(states.shape) + (c, oh, ow), dtype=torch.float32, device=dw.device)
+    with torch.cuda.device(dw.device):
+        L.check(lib.vn_gather_rows(tab.data_ptr(), c * oh * ow * 4, states.data_ptr(), states.numel(), out.data_ptr(),
+                                   _stream(states)))
+    return out
+
+
+def auxiliary_targets(dw, states, goal_states, cell_size=4, output_size=None, method="table"):
     """compute_auxiliary_targets (trainer.py:17-19): targets for observation leaves 2.. of the aux5
     tuple = (depth, segmentation, goal_segmentation)."""
-    return (auxiliary_target(dw, states, "depth", cell_size, output_size),
-            auxiliary_target(dw, states, "segmentation", cell_size, output_size),
-            auxiliary_target(dw, goal_states, "segmentation", cell_size, output_size))
+    return (auxiliary_target(dw, states, "depth", cell_size, output_size, method),
+            auxiliary_target(dw, states, "segmentation", cell_size, output_size, method),
+            auxiliary_target(dw, goal_states, "segmentation", cell_size, output_size, method))
 
 
 def policy_input(dw: DeviceWorld, states, plane="rgb"):

@@ -175,10 +175,33 @@ class Task:
 
 def scene_max_dist(scene: GridScene) -> int:
     """``np.max(self.graph.graph)`` (gym_graph/graph.py:35, graph/env.py:26): the largest grid
-    distance over all pairs.  Distances are symmetric, so BFS from every free cell."""
+    distance over all pairs of free cells.  All-pairs BFS on the cell graph (scipy's C implementation
+    when available, else one numpy BFS per cell)."""
+    try:
+        from scipy.sparse import csr_matrix
+        from scipy.sparse.csgraph import shortest_path
+    except Exception:
+        m = 0
+        for x, y in scene.cells:
+            m = max(m, int(bfs_distances(scene.maze, (x, y)).max()))
+        return m
+    rank = scene.cell_rank
+    X, Y = rank.shape
+    rows, cols = [], []
+    for dx, dy in ((1, 0), (0, 1)):
+        a = rank[:X - dx, :Y - dy]
+        b = rank[dx:, dy:]
+        ok = (a >= 0) & (b >= 0)
+        rows.append(a[ok])
+        cols.append(b[ok])
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    n = scene.n_cells
+    g = csr_matrix((np.ones(len(r) * 2, np.int8), (np.concatenate([r, c]), np.concatenate([c, r]))), shape=(n, n))
     m = 0
-    for x, y in scene.cells:
-        m = max(m, int(bfs_distances(scene.maze, (x, y)).max()))
+    for lo in range(0, n, 512):      # bounded memory: 512 sources at a time
+        d = shortest_path(g, method="D", unweighted=True, indices=np.arange(lo, min(n, lo + 512)))
+        d = d[np.isfinite(d)]
+        m = max(m, int(d.max()) if d.size else 0)
     return m
 
 

@@ -41,6 +41,43 @@ def make_scene(vn):
     return vn.scenes.make_thor_scene(N_CELLS, GRID, seed=SCENE_SEED, n_goals=4, planes=("rgb", "depth"))
 
 
+F_SEG = F_RGB = 84 * 84 * 3
+PLANE_BYTES = {"rgb": 84 * 84 * 3, "depth": 84 * 84, "segmentation": 84 * 84 * 3}
+
+
+def make_workload(vn, name):
+    """BASELINE.json configs -> (description, world, envs per GPU, obs_layout).  configs[1] (c2) is the one
+    the headline metric is quoted on; the others are secondary lines (`--workload`)."""
+    S, T = vn.scenes, vn.tables
+    if name == "c2":
+        return WORKLOAD, vn.compile_world([make_scene(vn)], vn.GYM_GRAPH), ENVS_PER_GPU, "rgbd_goal"
+    if name == "c1":
+        sc = S.make_maze_scene((10, 10), 0.25, 0, n_goals=1)
+        return ("C1 10x10 grid maze, 16 envs, 84x84 aux observation (rgb, goal, depth, seg, goal seg)",
+                vn.compile_world([sc], vn.GYM_GRAPH), 16, "aux5")
+    if name == "c3":
+        sc = S.make_dungeon_scene((64, 64), 0, oriented=True, planes=("rgb",))
+        return ("C3 dungeon 64x64 multi-room (oriented), 65,536 envs per GPU, RGB + goal image, auto-reset",
+                vn.compile_world([sc], vn.GYM_GRAPH), 65536, "pair")
+    if name == "c4":
+        scs = [S.make_thor_scene(N_CELLS, GRID, seed=k, n_goals=4, planes=("rgb", "depth"), scene_id=k) for k in range(30)]
+        return ("C4 30 synthetic thor-cached scenes resident (180,000 states, 5.1 GB), 32,768 envs per GPU, RGB+depth+goal",
+                vn.compile_world(scs, vn.GYM_GRAPH), 32768, "rgbd_goal")
+    if name == "rgb":
+        return ("84x84 RGB-only cached-graph nav (north_star target line), C2 scene, 4,096 envs per GPU",
+                vn.compile_world([make_scene(vn)], vn.GYM_GRAPH), ENVS_PER_GPU, "frame")
+    raise ValueError(name)
+
+
+def layout_bytes(vn, layout):
+    """(observation bytes per env-step, goal bytes per reset) of an obs layout."""
+    leaves = importlib.import_module("a2cat-vn-pytorch_b200.vec_env").resolve_layout(layout)
+    names = list(leaves.values()) if isinstance(leaves, dict) else (list(leaves) if isinstance(leaves, tuple) else [leaves])
+    obs = sum(PLANE_BYTES[x] for x in dict.fromkeys(n for n in names if not n.startswith("goal_")))
+    goal = sum(PLANE_BYTES[x[5:]] for x in dict.fromkeys(n for n in names if n.startswith("goal_")))
+    return obs, goal
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
@@ -247,11 +284,11 @@ def run_cuda(args):
     W = args.warmup if args.warmup is not None else 200
     W = max(W, 3)
 
-    scene = make_scene(vn)
-    world = vn.compile_world([scene], vn.GYM_GRAPH)
-    n_total = (args.envs_per_gpu or ENVS_PER_GPU) * world_size
+    workload, world, envs_per_gpu, layout = make_workload(vn, args.workload)
+    F_OBS, F_GOAL = layout_bytes(vn, layout)
+    n_total = (args.envs_per_gpu or envs_per_gpu) * world_size
     env = vn.GraphVecEnv(world, n_total, device=dev, seed=1, max_episode_steps=MAX_EPISODE_STEPS,
-                         obs_layout="rgbd_goal", unreal_wrapper=True, rank=rank, world_size=world_size,
+                         obs_layout=layout, unreal_wrapper=True, rank=rank, world_size=world_size,
                          gather=args.gather, host_outputs=False)
     hardness = None if args.hardness in (None, "none") else float(args.hardness)
     _CPU["hardness"] = hardness
@@ -320,14 +357,14 @@ def run_cuda(args):
     gather_ms = float(np.mean([a.elapsed_time(b) for a, b in es]))
     rs = env.episode_stats()
     p_reset_r = rs["resets"] / max(1.0, rs["steps"])
-    alg_bytes = N * (2 * (F_RGB + F_DEPTH) + p_reset_r * 2 * F_RGB)
+    alg_bytes = N * (2 * F_OBS + p_reset_r * 2 * F_GOAL)
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
     # calibration: plain contiguous device copies of the SAME number of bytes (torch copy_, the operation the
     # measured peak was taken with, but at this kernel's size instead of 2 GiB), back to back over 4 distinct
     # (src, dst) pairs so that, like the gather in steady state, every copy starts with L2 full of the previous
     # copy's dirty lines - what a ~40 us transfer can sustain on this GPU
-    nb = N * (F_RGB + F_DEPTH)
+    nb = N * F_OBS
     pairs = [(torch.empty(nb, dtype=torch.uint8, device=dev).random_(0, 255),
               torch.empty(nb, dtype=torch.uint8, device=dev)) for _ in range(4)]
     for i in range(8):
@@ -346,7 +383,7 @@ def run_cuda(args):
                 "traffic": profiled_traffic(), "kernel": "vn_gather_%s_kernel" % args.gather_name(env),
                 "kernel_ms": gather_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "same_size_copy_ms": copy_ms, "same_size_copy_gbs": 2 * nb / (copy_ms * 1e-3) / 1e9,
-                "step_frac": (N * (2 * (F_RGB + F_DEPTH) + p_reset * 2 * F_RGB + 40)) / (ms * 1e-3 / K) / 1e9 / peak
+                "step_frac": (N * (2 * F_OBS + p_reset * 2 * F_GOAL + 40)) / (ms * 1e-3 / K) / 1e9 / peak
                 if world_size == 1 else None}
 
     if args.quick:
@@ -359,7 +396,7 @@ def run_cuda(args):
 
     # ---- e2e through the public VecEnv API: host actions in, host rewards/dones out, every step
     env_e = vn.GraphVecEnv(world, n_total, device=dev, seed=2, max_episode_steps=MAX_EPISODE_STEPS,
-                           obs_layout="rgbd_goal", unreal_wrapper=True, rank=rank, world_size=world_size,
+                           obs_layout=layout, unreal_wrapper=True, rank=rank, world_size=world_size,
                            gather=args.gather, host_outputs=True, device_world=env.dw)
     env_e.reset()
     Ke = min(K, 3000)
@@ -380,21 +417,22 @@ def run_cuda(args):
            "steps": Ke, "note": "VecEnv.step(numpy actions) -> (CUDA uint8 obs, numpy rewards, numpy dones, infos); "
                                 "observations stay in HBM for the policy"}
     # secondary: also bring the observation batch to pinned host memory every step (what a CPU policy would need)
-    pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (obs[0][0], obs[0][2])]
+    obs_leaves = list(env_e.obs_buf.values())
+    pin = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in obs_leaves]
     Kh = min(Ke, 200)
     barrier()
     t0 = time.perf_counter()
     for i in range(Kh):
         obs, rew, done, infos = env_e.step(host_actions[i % len(host_actions)])
-        pin[0].copy_(obs[0][0], non_blocking=True)
-        pin[1].copy_(obs[0][2], non_blocking=True)
+        for dst, src in zip(pin, obs_leaves):
+            dst.copy_(src, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
     dth = time.perf_counter() - t0
     e2e["host_obs_value"] = n_total * Kh / dth if world_size == 1 else None
-    e2e["host_obs_d2h_bytes_per_step"] = N * (F_RGB + F_DEPTH) + 20 * N
+    e2e["host_obs_d2h_bytes_per_step"] = N * F_OBS + 20 * N
 
     cpu_baseline = None
-    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline and args.workload == "c2":
         v, nres, cdt = cpu_run(16, 400, 3, 1)
         cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
                         "sample": "16 envs x 400 vector steps, one process, sequential + np.stack (DummyVecEnv "
@@ -405,9 +443,10 @@ def run_cuda(args):
             "metric": "env-steps/s (obs gather+step+reset)", "value": value, "unit": "env-steps/s",
             "n_gpus": world_size, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_total": n_total, "states": world.n_states,
-                       "store_bytes": env.dw.nbytes(), "batch_bytes_per_step": N * (2 * F_RGB + F_DEPTH),
-                       "l2": "inputs larger than L2: 169 MB store + 116 MB batch touched per step vs 126 MB L2",
+            "config": {"workload": workload, "envs_total": n_total, "states": world.n_states,
+                       "store_bytes": env.dw.nbytes(), "batch_bytes_per_step": N * F_OBS,
+                       "l2": "inputs larger than L2: %.0f MB store + %.0f MB batch written per step vs 126 MB L2"
+                             % (env.dw.nbytes() / 1e6, N * F_OBS / 1e6),
                        "gather": args.gather, "p_reset": p_reset, "collision_rate": coll,
                        "max_episode_steps": MAX_EPISODE_STEPS, "hardness": hardness, "mix_steps": args.mix,
                        "parallelism": "env-sharded x%d, no data-path collective" % world_size},
@@ -419,6 +458,83 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+def run_rollout(args):
+    """BASELINE.json configs[4]: the A2C rollout builder - 128-step n-step returns + pixel-control rewards
+    and their discounted back-up + reward-prediction labels / index lists (+ the 3 auxiliary targets), on a
+    2^20 (env x step) batch, straight from state indices and the HBM store."""
+    import torch
+    vn = importlib.import_module("a2cat-vn-pytorch_b200")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    N, T = 8192, 128
+    K = args.steps if args.steps else 20
+    W = max(args.warmup if args.warmup is not None else 3, 3)
+    scene = vn.scenes.make_thor_scene(N_CELLS, GRID, seed=SCENE_SEED, n_goals=4, planes=("rgb", "depth", "segmentation"))
+    world = vn.compile_world([scene], vn.GYM_GRAPH)
+    env = vn.GraphVecEnv(world, N, device=dev, seed=1, max_episode_steps=50, obs_layout="frame", host_outputs=False)
+    env.set_complexity(0.05)
+    env.reset()
+    buf = vn.rollout.RolloutBuffer(env.dw, N, T)
+    buf.start(env)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    for _ in range(T):
+        a = torch.randint(0, 4, (N,), device=dev, generator=gen, dtype=torch.int32)
+        env.step_async(a)
+        env._pending = False
+        buf.insert(env, a)
+    states = buf.states.t().contiguous()          # [N, T+1]
+    goals = buf.goals[:-1].t().contiguous()
+    v_last = torch.randn(N, device=dev)
+    q_last = torch.rand(N, 20, 20, device=dev)
+    done_bt = buf.dones.t().contiguous()
+    R = vn.rollout
+
+    def builder(with_aux):
+        ret = R.nstep_returns(buf.rewards, buf.dones, v_last, 0.99, time_major=True)
+        pc = R.pixel_control_reward(env.dw, states, 4, (20, 20))
+        pcr = R.discounted_backup(pc.view(N, T, 400), done_bt, q_last.view(N, 400), 0.9)
+        lab = R.reward_prediction_labels(buf.rewards, with_lists=True)
+        aux = R.auxiliary_targets(env.dw, states[:, :-1], goals, 4, (20, 20)) if with_aux else None
+        return ret, pc, pcr, lab, aux
+
+    def timed(fn, k):
+        for _ in range(W):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / k
+
+    ms_core = timed(lambda: builder(False), K)
+    ms_all = timed(lambda: builder(True), max(2, K // 4))
+    ms_pc = timed(lambda: R.pixel_control_reward(env.dw, states, 4, (20, 20)), K)
+    ms_ret = timed(lambda: R.nstep_returns(buf.rewards, buf.dones, v_last, 0.99, time_major=True), K)
+    ms_rp = timed(lambda: R.reward_prediction_labels(buf.rewards, with_lists=True), K)
+    peak, peak_src = measured_peak()
+    # table path: every transition reads one 1,600-byte table row and writes one 1,600-byte output row; the
+    # ~2 % reset transitions read two 21,168-byte frames instead of the table row
+    miss = float(buf.dones.float().mean())
+    pc_bytes = N * T * (1600 + (1 - miss) * 1600 + miss * 2 * F_RGB)
+    line = {
+        "metric": "rollout-builder env-steps/s (n-step returns + pixel-control + back-up + RP)", "value": N * T / (ms_core * 1e-3),
+        "unit": "env-steps/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_core, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5 A2C rollout builder: T=128, N=8,192 (2^20 env-steps), gamma .99, PC cell 4 -> 20x20, gamma_pc .9",
+                   "ms": {"returns": ms_ret, "pixel_control": ms_pc, "rp_labels_and_lists": ms_rp, "core_total": ms_core,
+                          "with_aux_targets_total": ms_all}, "done_rate": float(buf.dones.float().mean())},
+        "roofline": {"bound": "hbm", "achieved": pc_bytes / (ms_pc * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": pc_bytes / (ms_pc * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel": "vn_transition_rows + vn_gather_rows + vn_pixel_control_list (table-driven pixel control)",
+                     "kernel_ms": ms_pc, "algorithmic_bytes_per_launch": pc_bytes, "peak_source": peak_src},
+        "gpu_launches": 7,
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,6 +544,8 @@ def main():
     ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="development: device-resident number + roofline only")
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "rgb"],
+                    help="BASELINE.json config; c2 is the headline, the others are secondary lines")
     ap.add_argument("--hardness", default="none", help="curriculum hardness (set_complexity); 'none' = uniform starts")
     ap.add_argument("--mix", type=int, default=1000, help="un-timed steps before warm-up")
     ap.add_argument("--envs-per-gpu", type=int, default=None, help="development: override the 4,096 envs per GPU")
@@ -435,6 +553,8 @@ def main():
     args.gather_name = lambda env: {0: "auto", 1: "ldg", 2: "bulk"}[env.gather]
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_rollout(args)
     else:
         run_cuda(args)
 

@@ -231,6 +231,24 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
                          int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out,
                          void *stream);
 
+/* Table-driven pixel control.  On a cached graph the pixel-control reward of a transition is a pure
+ * function of the state pair, so it is computed ONCE per (state, action) into a table
+ * pc_table[n_states * 4][out_h * out_w] (vn_pixel_control over the pairs (s, adj[s][a])) and a rollout's
+ * rewards become row gathers:
+ *   vn_transition_rows   rows[n][k] = s*4 + a with adj[s][a] == s' ; -1 (zeros) when s' == s (collision /
+ *                        no-op: identical frames); -2 for transitions the table cannot serve (resets):
+ *                        their positions n*t + k are appended to miss_pos and counted in miss_count[0]
+ *   vn_gather_rows       out[i] = table[idx[i]] (rows of row_bytes, multiple of 16); idx -1 writes zeros,
+ *                        idx -2 leaves the row untouched.  Also serves the auxiliary-target tables.
+ *   vn_pixel_control_list direct computation for the listed positions (count read from device memory,
+ *                        at most max_count), written into the same [n][t][out_h][out_w] output. */
+int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int32_t *rows,
+                           int32_t *miss_pos, int32_t *miss_count, void *stream);
+int32_t vn_gather_rows(const void *table, int64_t row_bytes, const int32_t *idx, int64_t n, void *out, void *stream);
+int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
+                              int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w,
+                              const int32_t *pos, const int32_t *count, int32_t max_count, float *out, void *stream);
+
 /* compute_auxiliary_target (experiments/ai2_auxiliary/trainer.py:9-15) from the store:
  * out[i] = avg_pool_cell(crop(plane(idx[i]) / 255)), [m][c][out_h][out_w] float32. */
 int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t m, int32_t h, int32_t w,

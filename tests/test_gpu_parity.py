@@ -342,3 +342,64 @@ def test_c_abi_rejects_bad_arguments():
     with pytest.raises(ValueError):
         scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=1, planes=("rgb",))
         vn.GraphVecEnv(T.compile_world([scene], T.GYM_GRAPH), 4, obs_layout="aux5")
+
+
+def _property_run(env, world, steps, obs_names):
+    """Size-independent properties of a vectorised run (used for the full-size C3 / C4 configurations)."""
+    import torch
+    dw = env.dw
+    adj = dw.adj.view(-1, 4)
+    planes = {p: dw.plane_view(p) for p in obs_names}
+    base = torch.from_numpy(world.scene_base).to(dw.device)
+    task_scene = torch.tensor([t.scene for t in world.tasks], device=dw.device)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    env.reset()
+    N = env.num_envs
+    for t in range(steps):
+        a = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        prev = env.state.clone()
+        obs, rew, done, _ = env.step(a)
+        nxt = adj[prev.long(), a.long()]
+        assert torch.equal(env.info_state, torch.where(nxt >= 0, nxt, prev))
+        s = env.state.long()
+        for name, buf in env.obs_buf.items():
+            assert torch.equal(buf, planes[name][s]), name
+        for name, buf in env.goal_buf.items():
+            assert torch.equal(buf, planes[name][env.goal.long()]), name
+        # an env never leaves the scene of its current task, and its goal is that task's goal
+        sc = torch.bucketize(s, base, right=True) - 1
+        assert torch.equal(sc, task_scene[env.task.long()])
+        assert torch.equal(env.goal, dw.task_goal[env.task.long()])
+        assert torch.equal(env.did_reset.bool(), done)
+        assert torch.equal(rew == 1.0, env.win.bool())
+    st = env.episode_stats()
+    assert st["steps"] == steps * N and st["episodes"] == st["resets"] - N
+
+
+def test_full_size_properties_c3_dungeon():
+    """BASELINE.json configs[2]: dungeon 64x64 multi-room, 65,536 envs, goal-image conditioning, auto-reset."""
+    sc = H.scenes.make_dungeon_scene((64, 64), 0, oriented=True, planes=("rgb",))
+    world = T.compile_world([sc], T.GYM_GRAPH)
+    env = vn.GraphVecEnv(world, 65536, seed=3, max_episode_steps=40, obs_layout="pair", host_outputs=False)
+    env.set_complexity(0.1)
+    _property_run(env, world, 25, ("rgb",))
+
+
+def test_full_size_properties_c4_multi_scene():
+    """BASELINE.json configs[3] on one GPU's shard: 30 scenes resident (180,000 states, 5.1 GB store),
+    32,768 envs (= 262,144 / 8), 120 (scene, goal) tasks dealt round-robin."""
+    scs = [H.scenes.make_thor_scene(1500, (50, 60), seed=k, n_goals=4, planes=("rgb", "depth"), scene_id=k)
+           for k in range(30)]
+    world = T.compile_world(scs, T.GYM_GRAPH)
+    assert world.n_states == 180000 and len(world.tasks) == 120
+    env = vn.GraphVecEnv(world, 262144, seed=5, max_episode_steps=30, obs_layout="rgbd_goal", host_outputs=False,
+                         rank=3, world_size=8)
+    assert env.num_envs == 32768 and env.env_lo == 3 * 32768
+    env.set_complexity(0.05)
+    _property_run(env, world, 12, ("rgb", "depth"))
+    # the hash-filled store matches the host hash for a sample of (scene, state) pairs
+    import torch
+    rgb = env.dw.plane_view("rgb")
+    for si, ls in ((0, 0), (7, 123), (29, 5999)):
+        g = int(world.scene_base[si]) + ls
+        assert np.array_equal(rgb[g].cpu().numpy(), scs[si].plane_frames("rgb", [ls])[0])

@@ -77,10 +77,39 @@ def test_pixel_control_reward(dw):
     x = orl.u8_to_policy_input(frames)                     # TransposeImage + ScaledFloatFrame
     for out_size in ((20, 20), None):
         want = orl.pixel_control_reward(x, 4, out_size)
-        got = vn.rollout.pixel_control_reward(dw, torch.from_numpy(states), 4, out_size).cpu().numpy()
-        assert got.shape == want.shape
-        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
-        assert (got[:, 4] == 0).all()
+        for method in ("direct", "table"):      # random state pairs are almost all table misses -> list kernel
+            got = vn.rollout.pixel_control_reward(dw, torch.from_numpy(states), 4, out_size, method=method).cpu().numpy()
+            assert got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+            assert (got[:, 4] == 0).all()
+
+
+def test_pixel_control_table_equals_direct_on_real_trajectories(dw):
+    """Trajectories from the env (moves, rotations, collisions, resets): the transition-table path must
+    give the same BITS as the direct kernel, and both must match the oracle."""
+    import torch
+    N, Tn = 64, 40
+    env = vn.GraphVecEnv(dw.world, N, seed=9, max_episode_steps=12, device_world=dw, host_outputs=False, obs_layout="frame")
+    env.set_complexity(0.3)
+    env.reset()
+    buf = vn.rollout.RolloutBuffer(dw, N, Tn)
+    buf.start(env)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(Tn):
+        a = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        env.step(a)
+        buf.insert(env, a)
+    st = buf.states.t().contiguous()
+    d = vn.rollout.pixel_control_reward(dw, st, 4, (20, 20), method="direct")
+    t = vn.rollout.pixel_control_reward(dw, st, 4, (20, 20), method="table")
+    assert torch.equal(d, t)
+    assert buf.dones.sum() > 20                      # resets (table misses) were exercised
+    same = (st[:, 1:] == st[:, :-1])
+    assert same.any() and (t[same] == 0).all()      # collisions -> exact zeros
+    scene = dw.world.scenes[0]
+    fr = scene.plane_frames("rgb", st.cpu().numpy().reshape(-1)).reshape(N, Tn + 1, 84, 84, 3)
+    np.testing.assert_allclose(t.cpu().numpy(), orl.pixel_control_reward(orl.u8_to_policy_input(fr), 4, (20, 20)),
+                               rtol=RTOL, atol=ATOL)
 
 
 def test_auxiliary_targets(dw):
@@ -91,12 +120,13 @@ def test_auxiliary_targets(dw):
     states = rng.randint(0, S, size=(B, Tn)).astype(np.int32)
     goals = rng.randint(0, S, size=(B, Tn)).astype(np.int32)
     scene = dw.world.scenes[0]
-    got = vn.rollout.auxiliary_targets(dw, torch.from_numpy(states), torch.from_numpy(goals), 4, (20, 20))
-    for g, (plane, idx) in zip(got, (("depth", states), ("segmentation", states), ("segmentation", goals))):
-        c = 1 if plane == "depth" else 3
-        fr = scene.plane_frames(plane, idx.reshape(-1)).reshape(B, Tn, 84, 84, c)
-        want = orl.aux_target(orl.u8_to_policy_input(fr), 4, (20, 20))
-        np.testing.assert_allclose(g.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+    for method in ("direct", "table"):
+        got = vn.rollout.auxiliary_targets(dw, torch.from_numpy(states), torch.from_numpy(goals), 4, (20, 20), method=method)
+        for g, (plane, idx) in zip(got, (("depth", states), ("segmentation", states), ("segmentation", goals))):
+            c = 1 if plane == "depth" else 3
+            fr = scene.plane_frames(plane, idx.reshape(-1)).reshape(B, Tn, 84, 84, c)
+            want = orl.aux_target(orl.u8_to_policy_input(fr), 4, (20, 20))
+            np.testing.assert_allclose(g.cpu().numpy(), want, rtol=RTOL, atol=ATOL)
 
 
 def test_aux_target_against_reference_golden():
