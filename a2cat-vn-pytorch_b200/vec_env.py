@@ -88,7 +88,7 @@ class LazyInfos:
             info["win"] = True
         if h["truncated"][i]:                                   # gym TimeLimit: key exists only at the limit
             info["TimeLimit.truncated"] = bool(h["truncated"][i] == 1)
-        if h["done"][i]:                                        # RewardCollector
+        if env.episode_info and h["done"][i]:                   # RewardCollector
             info["episode"] = dict(r=float(h["episode_return"][i]), l=int(h["episode_length"][i]))
         return info
 
@@ -99,7 +99,8 @@ class LazyInfos:
 class GraphVecEnv:
     def __init__(self, world, num_envs, *, device="cuda", seed=0, max_episode_steps=900, rewards=(1.0, 0.0, 0.0),
                  obs_layout="aux5", unreal_wrapper=True, env_tasks=None, auto_reset=True, rank=0, world_size=1,
-                 gather="auto", inject=None, host_outputs=True, device_world=None):
+                 gather="auto", inject=None, host_outputs=True, device_world=None, scaled_float=False,
+                 episode_info=True):
         """
         world            tables.World (compiled scenes) - or pass a ready ``device_world``
         num_envs         TOTAL number of envs of the job; this process owns shard_range(num_envs, rank, world_size)
@@ -107,6 +108,9 @@ class GraphVecEnv:
                          of scene i % n_scenes ... see _default_env_tasks)
         inject           optional (task [n_local, R] int32, start [n_local, R] int32 GLOBAL states) reset stream
         host_outputs     rewards / dones as numpy (reference behaviour) or as CUDA tensors
+        scaled_float     observation leaves as float32 CHW in [0, 1] - what TransposeImage + ScaledFloatFrame
+                         (experiments/thor_cached_auxiliary.py:61-62) hand to the model - produced by one fused
+                         gather/convert kernel per leaf instead of the uint8 HWC batch
         """
         self.dw = device_world if device_world is not None else DeviceWorld(world, device)
         self.world: World = self.dw.world
@@ -122,6 +126,8 @@ class GraphVecEnv:
         self.obs_layout = obs_layout
         self.unreal_wrapper = unreal_wrapper
         self.host_outputs = host_outputs
+        self.scaled_float = scaled_float
+        self.episode_info = episode_info     # RewardCollector's info['episode'] (create_envs wraps with it, :60)
         self.n_actions = 4
         self.gather = {"auto": L.GATHER_AUTO, "ldg": L.GATHER_LDG, "bulk": L.GATHER_BULK}[gather]
         lay = self.world.layout
@@ -207,7 +213,10 @@ class GraphVecEnv:
 
         def frame(leaf):
             p = leaf[5:] if leaf.startswith("goal_") else leaf
-            return spaces.Box(0, 255, (h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)), np.uint8)
+            c = lay.plane_bytes[lay.planes.index(p)] // (h * w)
+            if scaled_float:
+                return spaces.Box(0.0, 1.0, (c, h, w), np.float32)
+            return spaces.Box(0, 255, (h, w, c), np.uint8)
 
         if isinstance(self.leaves, dict):
             inner = spaces.Dict({k: frame(v) for k, v in self.leaves.items()})
@@ -254,6 +263,11 @@ class GraphVecEnv:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _leaf(self, name):
+        if self.scaled_float:
+            from . import rollout
+            if name.startswith("goal_"):
+                return rollout.policy_input(self.dw, self.goal, name[5:])
+            return rollout.policy_input(self.dw, self.obs_state, name)
         return self.goal_buf[name[5:]] if name.startswith("goal_") else self.obs_buf[name]
 
     def _obs(self):

@@ -403,3 +403,77 @@ def test_full_size_properties_c4_multi_scene():
     for si, ls in ((0, 0), (7, 123), (29, 5999)):
         g = int(world.scene_base[si]) + ls
         assert np.array_equal(rgb[g].cpu().numpy(), scs[si].plane_frames("rgb", [ls])[0])
+
+
+def test_single_env_surface_without_auto_reset():
+    """GraphEnv = the bare reference class: no auto-reset, no TimeLimit; compared with the oracle env
+    (pinned to the reference by the golden tests) step by step, including what happens AFTER done."""
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    osc = oenvs.OracleScene(scene)
+    seed = 77
+    env = vn.GraphEnv(world, seed=seed, obs_layout="aux5")
+    o = oenvs.GymGraphAuxiliaryEnv(osc, goals=list(scene.goals))
+    cands = [gu.initial_state_candidates(scene.maze, osc.graph, osc.optimal_actions, g) for g in scene.goals]
+    o.reset_source = ovec.PhiloxResetSource(seed, 0, cands, lambda t: o.optimal_distance(), False)
+    rng = np.random.RandomState(0)
+    for c in (0.1, None):
+        env.set_complexity(c)
+        o.set_complexity(c)
+        for ep in range(6):
+            ob, oob = env.reset(), o.reset()
+            assert env.state == o.state and env.goal == o.goal
+            for t in range(60):
+                a = int(rng.randint(0, 4))
+                (ob, r, d, info), (oob, orr, od, oinfo) = env.step(a), o.step(a)
+                assert (r, d) == (orr, od) and env.state == o.state
+                assert info.get("state") == oinfo.get("state") and info.get("win") == oinfo.get("win")
+                assert all(np.array_equal(x, y) for x, y in zip(ob, oob))
+                if d:
+                    break
+    assert np.array_equal(env.render("rgbarray"), ob[0])
+    with pytest.raises(Exception):
+        env.render("human")
+
+
+def test_thor_cached_single_env_returns_previous_obs_on_terminal():
+    """cached.py:90-97: on the terminal step the env returns the PREVIOUS observation pair."""
+    g = H.load("thor_cached")
+    scene = H.scene_from_golden(g, True, ("rgb",))
+    dist, _ = gu.compute_shortest_path_data(scene.maze)
+    _, graph, spd = gu.h5_tables(scene.maze, dist)
+    frames = scene.plane_frames("rgb")
+    goal = 14
+    world = T.compile_world([scene], T.THOR_CACHED, tasks=[(0, goal)])
+    # start next to the goal: find (s, a) with graph[s][a] == goal
+    s0, a0 = [(s, a) for s in range(graph.shape[0]) for a in range(4) if graph[s, a] == goal and s != goal][0]
+    env = vn.GraphEnv(world, obs_layout="pair", inject=(np.zeros((1, 4), np.int32), np.full((1, 4), s0, np.int32)))
+    o = oenvs.ThorCachedEnv(graph, frames, spd, tasks=[goal])
+    o.reset_source = lambda: (0, s0)
+    ob, oob = env.reset(), o.reset()
+    assert all(np.array_equal(x, y) for x, y in zip(ob, oob))
+    (ob, r, d, info), (oob, orr, od, _) = env.step(a0), o.step(a0)
+    assert d and od and r == orr == 1.0 and info == {}
+    assert all(np.array_equal(x, y) for x, y in zip(ob, oob))
+    assert np.array_equal(ob[0], frames[s0])             # previous observation, not the goal frame
+
+
+def test_scaled_float_observation_mode():
+    """scaled_float=True: leaves are what TransposeImage + ScaledFloatFrame produce (float32 CHW / 255)."""
+    import torch
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    a = vn.GraphVecEnv(world, 8, seed=1, max_episode_steps=9)
+    b = vn.GraphVecEnv(world, 8, seed=1, max_episode_steps=9, scaled_float=True, device_world=a.dw)
+    assert b.observation_space.spaces[0].spaces[0].shape == (3, 84, 84)       # thor_cached_auxiliary.py:55
+    (oa, _), (ob, _) = a.reset(), b.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(25):
+        act = rng.randint(0, 4, 8)
+        (oa, _), _, _, _ = a.step(act)
+        (ob, _), _, _, _ = b.step(act)
+        for x, y in zip(oa, ob):
+            # numpy true division like the reference's ScaledFloatFrame (torch's CUDA `x / 255.0` multiplies
+            # by a rounded reciprocal and differs in the last bit for 126 of the 256 byte values)
+            want = np.stack([ovec.transpose_scale(f) for f in x.cpu().numpy()])
+            assert y.dtype == torch.float32 and np.array_equal(y.cpu().numpy(), want)
