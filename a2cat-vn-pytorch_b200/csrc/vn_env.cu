@@ -509,10 +509,12 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
 static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
                           const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask,
                           const vn_step_out_t *out, void *stream, bool reset, int32_t *actions_copy = nullptr) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    if (envs->n_envs == 0) return VN_OK;  // an empty shard (more ranks than envs): nothing to do, nothing to check
     VN_REQUIRE(tab && tab->adj && tab->task_goal && tab->task_cand_off && tab->task_prefix && tab->cand_state,
                "tables: null pointer");
     VN_REQUIRE(tab->n_tasks > 0, "tables: n_tasks=%d", tab->n_tasks);
-    VN_REQUIRE(envs && envs->state && envs->goal && envs->task && envs->elapsed && envs->epoch && envs->ep_return &&
+    VN_REQUIRE(envs->state && envs->goal && envs->task && envs->elapsed && envs->epoch && envs->ep_return &&
                    envs->ep_length && envs->task_lo && envs->task_cnt,
                "envs: null pointer");
     VN_REQUIRE(envs->n_envs >= 0, "envs: n_envs=%d", envs->n_envs);
@@ -546,9 +548,11 @@ static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const v
 
 static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant,
                           void *stream) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    if (envs->n_envs == 0) return VN_OK;
     int32_t rc = validate_store(store);
     if (rc) return rc;
-    VN_REQUIRE(envs && envs->goal && envs->n_envs >= 0, "envs: null pointer");
+    VN_REQUIRE(envs->goal, "envs: null pointer");
     VN_REQUIRE(out && out->obs_state, "out: obs_state is required");
     GatherParams gp;
     gp.store = *store;
@@ -571,6 +575,8 @@ static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const 
 static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
                         const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask, const vn_step_out_t *out,
                         int32_t variant, void *stream, bool reset) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    if (envs->n_envs == 0) return VN_OK;
     int32_t rc = validate_store(store);  // fail before anything is enqueued
     if (rc) return rc;
     rc = run_scalar(tab, envs, rules, inj, actions, mask, out, stream, reset);
@@ -637,6 +643,8 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
                          const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
                          int32_t *dev_actions_copy, const vn_step_out_t *out, void *ready_event,
                          int32_t gather_variant, void *stream) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    if (envs->n_envs == 0) return VN_OK;
     int32_t rc = vn::validate_store(store);
     if (rc) return rc;
     VN_REQUIRE(host_actions, "step_host: host_actions is null");

@@ -208,6 +208,9 @@ def reward_prediction_labels(rewards, with_lists=True):
     r = rewards.contiguous().float()
     n = r.numel()
     labels = torch.empty(r.shape, dtype=torch.int8, device=r.device)
+    if n == 0:
+        e = torch.empty(0, dtype=torch.int32, device=r.device)
+        return labels, (e if with_lists else None), (e.clone() if with_lists else None)
     scratch = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int32, device=r.device)
     counts = torch.zeros(2, dtype=torch.int32, device=r.device)
     zero = torch.empty(n, dtype=torch.int32, device=r.device) if with_lists else None

@@ -477,3 +477,66 @@ def test_scaled_float_observation_mode():
             # by a rounded reciprocal and differs in the last bit for 126 of the 256 byte values)
             want = np.stack([ovec.transpose_scale(f) for f in x.cpu().numpy()])
             assert y.dtype == torch.float32 and np.array_equal(y.cpu().numpy(), want)
+
+
+def test_edge_cases_empty_ragged_and_errors():
+    import torch
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    # ragged sharding: 3 envs over 4 ranks -> one rank owns nothing; every call is a no-op there
+    envs = [vn.GraphVecEnv(world, 3, seed=4, rank=r, world_size=4, max_episode_steps=5) for r in range(4)]
+    assert [e.num_envs for e in envs] == [1, 1, 1, 0]
+    empty = envs[3]
+    obs = empty.reset()
+    _, r, d, infos = empty.step(np.zeros(0, np.int32))
+    assert r.shape == (0,) and d.shape == (0,) and len(infos) == 0 and obs[0][0].shape == (0, 84, 84, 3)
+    # the three 1-env shards together equal one 3-env env
+    whole = vn.GraphVecEnv(world, 3, seed=4, max_episode_steps=5, device_world=envs[0].dw)
+    whole.reset()
+    [e.reset() for e in envs[:3]]
+    rng = np.random.RandomState(0)
+    for _ in range(30):
+        a = rng.randint(0, 4, 3)
+        _, rw, dw_, _ = whole.step(a)
+        parts = [e.step(a[i:i + 1]) for i, e in enumerate(envs[:3])]
+        assert np.array_equal(rw, np.concatenate([p[1] for p in parts]))
+        assert np.array_equal(dw_, np.concatenate([p[2] for p in parts]))
+    # action containers: list, int64 CUDA tensor, int32 CPU tensor
+    e = vn.GraphVecEnv(world, 4, seed=1, max_episode_steps=50, device_world=envs[0].dw)
+    e.reset()
+    e.step([0, 1, 2, 3])
+    e.step(torch.tensor([0, 1, 2, 3], device="cuda"))
+    e.step(torch.tensor([0, 1, 2, 3], dtype=torch.int32))
+    with pytest.raises(ValueError):
+        e.step([0, 1, 2])
+    with pytest.raises(RuntimeError):
+        e.step_wait()
+    # an action outside [0, 4) has no transition in the reference (graph.util.step returns None): collision here
+    before = e.state.clone()
+    _, r, d, _ = e.step([7, -3, 4, 99])
+    assert torch.equal(e.state, before) and (r == 0).all() and not d.any()
+    e.close()
+    with pytest.raises(RuntimeError):
+        e.reset()
+    # bad env_tasks
+    with pytest.raises(ValueError):
+        vn.GraphVecEnv(world, 2, env_tasks=[[0, 3], [0, 1]], device_world=envs[0].dw)
+
+
+def test_rollout_edge_cases():
+    import torch
+    from oracle import rollout as orl
+    R = vn.rollout
+    # T = 1
+    r = torch.tensor([[1.0], [0.5]], device="cuda")
+    d = torch.tensor([[1], [0]], dtype=torch.uint8, device="cuda")
+    v = torch.tensor([3.0, 4.0], device="cuda")
+    got = R.nstep_returns(r, d, v, 0.9).cpu().numpy()
+    assert np.array_equal(got, orl.nstep_returns(r.cpu().numpy(), d.cpu().numpy(), v.cpu().numpy(), 0.9))
+    # no rewards at all / all non-zero
+    for arr in (np.zeros(100, np.float32), np.ones(100, np.float32) * -1):
+        lab, z, nz = R.reward_prediction_labels(torch.from_numpy(arr).cuda())
+        assert len(z) + len(nz) == 100 and (len(nz) == 0 or len(z) == 0)
+        assert np.array_equal(lab.cpu().numpy(), orl.rp_labels(arr))
+    lab, z, nz = R.reward_prediction_labels(torch.zeros(0, device="cuda"))
+    assert lab.numel() == 0 and z.numel() == 0 and nz.numel() == 0
