@@ -358,6 +358,92 @@ __global__ void __launch_bounds__(kRpBlock) vn_rp_scatter_kernel(const float *__
     }
 }
 
+// =====================================================================================================
+// device-side UNREAL replay ring: uniform sampling of valid windows, one thread per env
+// =====================================================================================================
+struct ReplayParams {
+    const int32_t *before, *after, *goal, *action;  // [cap][n] time-major ring
+    const float *reward;
+    const uint8_t *done;
+    int32_t n, cap, head, count;                     // head = next slot to write, count = filled slots (<= cap)
+    int32_t length;                                  // transitions per sampled window
+    int32_t mode;                                    // 0 sequence, 1 reward-prediction (length is 3 history steps)
+    int32_t env_id_base;
+    uint32_t call;                                   // sample counter (RNG counter word)
+    uint64_t seed;
+    int32_t *o_states, *o_goals, *o_actions;         // [n][length+1], [n][length+1], [n][length]
+    float *o_rewards;                                // [n][length]
+    uint8_t *o_dones;                                // [n][length]
+    int32_t *o_start;                                // [n] chronological index of the window start, -1 if none
+    int8_t *o_label;                                 // [n] RP class of the predicted reward (mode 1)
+};
+
+// A window of L transitions starting at chronological index i is valid when it lies inside the ring and no
+// transition except possibly the last one ends an episode (sequences never straddle an episode boundary).
+// In RP mode the window is 3 history transitions + the transition whose reward is classified, and the
+// candidates are split by that reward being zero / non-zero (50/50 skewed sampling).
+__global__ void __launch_bounds__(128) vn_replay_sample_kernel(const ReplayParams p) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    const int L = p.mode == 1 ? 4 : p.length;
+    const int oldest = (p.head - p.count + p.cap) % p.cap;
+    const Philox4 d = philox4x32_10((uint32_t)(p.env_id_base + e), p.call, 0x5EB1A7u, (uint32_t)p.mode,
+                                    (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    int n_valid[2] = {0, 0};  // [0] all (mode 0) or zero-reward (mode 1); [1] non-zero reward (mode 1)
+    int start = -1, cls = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int want = -1;
+        if (pass == 1) {
+            if (p.mode == 1) {
+                cls = (d.v[1] & 1u) ? 1 : 0;                   // fair coin between the two classes
+                if (n_valid[cls] == 0) cls ^= 1;               // fall back to the non-empty class
+                if (n_valid[cls] == 0) break;                  // nothing to sample ("could not sample")
+            } else if (n_valid[0] == 0) {
+                break;
+            }
+            want = (int)__umulhi(d.v[0], (uint32_t)n_valid[cls]);
+        }
+        int clean = 0;  // consecutive non-terminal transitions ending just before the current one
+        int seen[2] = {0, 0};
+        for (int i = 0; i < p.count; ++i) {
+            const int slot = (oldest + i) % p.cap;
+            // window [i - L + 1, i] ends at i: valid iff the L - 1 transitions before i are non-terminal
+            if (i >= L - 1 && clean >= L - 1) {
+                int c = 0;
+                if (p.mode == 1) c = p.reward[(size_t)slot * p.n + e] != 0.0f;
+                if (pass == 0) {
+                    n_valid[c]++;
+                } else if (c == cls) {
+                    if (seen[c] == want) {
+                        start = i - L + 1;
+                        break;
+                    }
+                    seen[c]++;
+                }
+            }
+            clean = p.done[(size_t)slot * p.n + e] ? 0 : clean + 1;
+        }
+    }
+    p.o_start[e] = start;
+    if (start < 0) return;
+    for (int k = 0; k < L; ++k) {
+        const size_t at = (size_t)((oldest + start + k) % p.cap) * p.n + e;
+        p.o_states[(size_t)e * (L + 1) + k] = p.before[at];
+        p.o_goals[(size_t)e * (L + 1) + k] = p.goal[at];
+        p.o_actions[(size_t)e * L + k] = p.action[at];
+        p.o_rewards[(size_t)e * L + k] = p.reward[at];
+        p.o_dones[(size_t)e * L + k] = p.done[at];
+        if (k == L - 1) {
+            p.o_states[(size_t)e * (L + 1) + L] = p.after[at];
+            p.o_goals[(size_t)e * (L + 1) + L] = p.goal[at];
+            if (p.o_label) {
+                const float r = p.reward[at];
+                p.o_label[e] = r > 0.f ? 1 : (r < 0.f ? 2 : 0);
+            }
+        }
+    }
+}
+
 static int32_t pool_geom(int h, int w, int c, int cell, int out_h, int out_w, PoolGeom *g) {
     VN_REQUIRE(h > 0 && w > 0 && c > 0 && cell > 0 && out_h > 0 && out_w > 0, "pool: bad geometry");
     VN_REQUIRE(out_h * cell <= h && out_w * cell <= w, "pool: output %dx%d * cell %d exceeds frame %dx%d", out_h,
@@ -484,6 +570,45 @@ int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int3
     vn::vn_pixel_control_list_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         *store, plane, states, t, g, pos, count, max_count, out);
     return vn::check_launch("vn_pixel_control_list_kernel");
+}
+
+int32_t vn_replay_sample(const vn_replay_t *ring, int32_t length, int32_t mode, uint64_t seed, uint32_t call,
+                         int32_t env_id_base, int32_t *o_states, int32_t *o_goals, int32_t *o_actions,
+                         float *o_rewards, uint8_t *o_dones, int32_t *o_start, int8_t *o_label, void *stream) {
+    VN_REQUIRE(ring && ring->before && ring->after && ring->goal && ring->action && ring->reward && ring->done,
+               "replay_sample: null ring pointer");
+    VN_REQUIRE(ring->n >= 0 && ring->cap > 0 && ring->count >= 0 && ring->count <= ring->cap && ring->head >= 0 &&
+                   ring->head < ring->cap,
+               "replay_sample: bad ring geometry");
+    VN_REQUIRE(mode == 0 || mode == 1, "replay_sample: mode=%d", mode);
+    VN_REQUIRE(mode == 1 || length >= 1, "replay_sample: length=%d", length);
+    VN_REQUIRE(o_states && o_goals && o_actions && o_rewards && o_dones && o_start, "replay_sample: null output");
+    if (ring->n == 0) return VN_OK;
+    vn::ReplayParams p;
+    p.before = ring->before;
+    p.after = ring->after;
+    p.goal = ring->goal;
+    p.action = ring->action;
+    p.reward = ring->reward;
+    p.done = ring->done;
+    p.n = ring->n;
+    p.cap = ring->cap;
+    p.head = ring->head;
+    p.count = ring->count;
+    p.length = length;
+    p.mode = mode;
+    p.env_id_base = env_id_base;
+    p.call = call;
+    p.seed = seed;
+    p.o_states = o_states;
+    p.o_goals = o_goals;
+    p.o_actions = o_actions;
+    p.o_rewards = o_rewards;
+    p.o_dones = o_dones;
+    p.o_start = o_start;
+    p.o_label = o_label;
+    vn::vn_replay_sample_kernel<<<(ring->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    return vn::check_launch("vn_replay_sample_kernel");
 }
 
 int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t m, int32_t h, int32_t w,

@@ -58,6 +58,11 @@ class StepOut(C.Structure):
                 ("host_pack", _P)]
 
 
+class Replay(C.Structure):
+    _fields_ = [("before", _P), ("after", _P), ("goal", _P), ("action", _P), ("reward", _P), ("done", _P),
+                ("n", C.c_int32), ("cap", C.c_int32), ("head", C.c_int32), ("count", C.c_int32)]
+
+
 class VnError(RuntimeError):
     pass
 
@@ -68,7 +73,7 @@ _lib = None
 EXPORTS = ("vn_abi_version", "vn_last_error", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
            "vn_env_gather", "vn_env_step_host", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_nstep_returns", "vn_discounted_backup", "vn_pixel_control",
-           "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list",
+           "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_replay_sample",
            "vn_aux_target", "vn_rp_labels")
 
 
@@ -113,6 +118,7 @@ def load(build_if_missing=True):
         "vn_transition_rows": (i32, [_P, _P, i32, i32, _P, _P, _P, _P]),
         "vn_gather_rows": (i32, [_P, i64, _P, i64, _P, _P]),
         "vn_pixel_control_list": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, i32, _P, _P, i32, _P, _P]),
+        "vn_replay_sample": (i32, [C.POINTER(Replay), i32, i32, u64, C.c_uint32, i32, _P, _P, _P, _P, _P, _P, _P, _P]),
         "vn_aux_target": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, _P, _P]),
         "vn_rp_labels": (i32, [_P, i32, _P, _P, _P, _P, _P, _P]),
     }

@@ -269,3 +269,82 @@ class RolloutBuffer:
 
     def reward_prediction(self):
         return reward_prediction_labels(self.rewards.t().contiguous())
+
+
+class ReplayRing:
+    """Device-side UNREAL experience replay (deep_rl's replay behind
+    ``self.replay.sample_sequence()`` at experiments/ai2_auxiliary/trainer.py:29).  PARITY UNPINNED: deep_rl
+    is not vendored; the sampling rule is documented in include/vn_b200.h (vn_replay_sample) and restated
+    in oracle/rollout.py.
+
+    Holds state indices (24 bytes per env step), never frames; ``frames()`` / ``policy_input`` re-gather what
+    a loss needs from the HBM store.  The reference keeps ~2,000 frames in total (500 per env)."""
+
+    def __init__(self, dw: DeviceWorld, num_envs, capacity=500, seed=0, env_id_base=0):
+        self.dw, self.N, self.cap, self.seed, self.env_id_base = dw, num_envs, capacity, seed, env_id_base
+        dev = dw.device
+        z = lambda dt: torch.zeros((capacity, num_envs), dtype=dt, device=dev)
+        self.before, self.after, self.goal, self.action = z(torch.int32), z(torch.int32), z(torch.int32), z(torch.int32)
+        self.reward, self.done = z(torch.float32), z(torch.uint8)
+        self.head, self.count, self.calls = 0, 0, 0
+        self._prev = None
+
+    def start(self, env):
+        """Remember the observation the next inserted step starts from (after reset())."""
+        self._prev = env.obs_state.clone()
+
+    def insert(self, env, actions):
+        """Call after env.step(actions)."""
+        if self._prev is None:
+            raise RuntimeError("ReplayRing.start(env) must be called after env.reset()")
+        h = self.head
+        self.before[h].copy_(self._prev)
+        self.after[h].copy_(env.obs_state)
+        self.goal[h].copy_(env.goal)
+        self.action[h].copy_(actions.to(torch.int32) if torch.is_tensor(actions) else torch.as_tensor(actions))
+        self.reward[h].copy_(env.reward)
+        self.done[h].copy_(env.done)
+        self._prev.copy_(env.obs_state)
+        self.head = (h + 1) % self.cap
+        self.count = min(self.count + 1, self.cap)
+
+    def _sample(self, length, mode):
+        lib = L.load()
+        Lw = 4 if mode == 1 else length
+        dev, n = self.dw.device, self.N
+        out = dict(states=torch.zeros((n, Lw + 1), dtype=torch.int32, device=dev),
+                   goals=torch.zeros((n, Lw + 1), dtype=torch.int32, device=dev),
+                   actions=torch.zeros((n, Lw), dtype=torch.int32, device=dev),
+                   rewards=torch.zeros((n, Lw), dtype=torch.float32, device=dev),
+                   dones=torch.zeros((n, Lw), dtype=torch.uint8, device=dev),
+                   start=torch.full((n,), -1, dtype=torch.int32, device=dev))
+        if mode == 1:
+            out["label"] = torch.zeros(n, dtype=torch.int8, device=dev)
+        ring = L.Replay(self.before.data_ptr(), self.after.data_ptr(), self.goal.data_ptr(), self.action.data_ptr(),
+                        self.reward.data_ptr(), self.done.data_ptr(), n, self.cap, self.head, self.count)
+        with torch.cuda.device(dev):
+            L.check(lib.vn_replay_sample(C.byref(ring), Lw, mode, C.c_uint64(self.seed), self.calls, self.env_id_base,
+                                         out["states"].data_ptr(), out["goals"].data_ptr(), out["actions"].data_ptr(),
+                                         out["rewards"].data_ptr(), out["dones"].data_ptr(), out["start"].data_ptr(),
+                                         L.ptr(out.get("label")), torch.cuda.current_stream(dev).cuda_stream))
+        self.calls += 1
+        return out
+
+    def sample_sequence(self, length):
+        """One window of ``length`` transitions per env (uniform over the env's valid windows): dict of
+        states / goals [N, length+1], actions / rewards / dones [N, length], start [N] (-1 = none yet)."""
+        return self._sample(length, 0)
+
+    def sample_rp_sequence(self):
+        """Reward-prediction sample per env: 3 history observations (states[:, :3]), the class of the reward
+        that followed (label: 0 zero / 1 positive / 2 negative), zero / non-zero drawn 50/50."""
+        return self._sample(4, 1)
+
+    def frames(self, sample, plane="rgb", scaled_float=False, goal=False):
+        """Gathers the observation (or goal) frames of a sample: uint8 [N, L+1, H, W, C] or float32 CHW."""
+        from .vec_env import gather_plane
+        idx = sample["goals" if goal else "states"]
+        if scaled_float:
+            return policy_input(self.dw, idx, plane)
+        out = gather_plane(self.dw, plane, idx.reshape(-1))
+        return out.view(tuple(idx.shape) + tuple(out.shape[1:]))

@@ -249,6 +249,30 @@ int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int3
                               int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w,
                               const int32_t *pos, const int32_t *count, int32_t max_count, float *out, void *stream);
 
+/* Device-side UNREAL experience replay (deep_rl's replay behind `self.replay.sample_sequence()`,
+ * experiments/ai2_auxiliary/trainer.py:29, and sample_rp_sequence).
+ * The ring holds state INDICES, not frames: per inserted env step the state observed before the action,
+ * the state observed after it (post auto-reset), goal, action, reward, done; time-major [cap][n]. */
+typedef struct vn_replay {
+    const int32_t *before, *after, *goal, *action;
+    const float *reward;
+    const uint8_t *done;
+    int32_t n, cap;
+    int32_t head;  /* next slot to be written */
+    int32_t count; /* filled slots, <= cap */
+} vn_replay_t;
+
+/* One window per env, uniform over the env's valid windows (inside the ring, no episode end except on
+ * the last transition), drawn with Philox keyed by (seed, env_id_base + env, call).
+ *   mode 0: `length` transitions -> o_states/o_goals [n][length+1], o_actions/o_rewards/o_dones [n][length]
+ *   mode 1: reward prediction - 3 history transitions + the transition whose reward is classified
+ *           (length ignored, windows of 4), zero / non-zero reward classes drawn 50/50 (the other class
+ *           when one is empty); o_label [n] = 0 zero, 1 positive, 2 negative.
+ * o_start[n] = chronological index of the window, -1 when the env has no valid window (outputs untouched). */
+int32_t vn_replay_sample(const vn_replay_t *ring, int32_t length, int32_t mode, uint64_t seed, uint32_t call,
+                         int32_t env_id_base, int32_t *o_states, int32_t *o_goals, int32_t *o_actions,
+                         float *o_rewards, uint8_t *o_dones, int32_t *o_start, int8_t *o_label, void *stream);
+
 /* compute_auxiliary_target (experiments/ai2_auxiliary/trainer.py:9-15) from the store:
  * out[i] = avg_pool_cell(crop(plane(idx[i]) / 255)), [m][c][out_h][out_w] float32. */
 int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t m, int32_t h, int32_t w,

@@ -182,3 +182,49 @@ def test_rollout_buffer_end_to_end(dw):
     labels, zero, nonzero = buf.reward_prediction()
     assert np.array_equal(labels.cpu().numpy(), orl.rp_labels(buf.rewards.t().cpu().numpy()))
     assert buf.dones.sum() > 0
+
+
+def test_replay_ring_sampling(dw):
+    """Device replay ring vs its oracle restatement (bit-exact draws), plus the defining properties: windows
+    lie inside one episode, RP classes are balanced, frames re-gathered from the store."""
+    import torch
+    N, cap = 24, 64
+    env = vn.GraphVecEnv(dw.world, N, seed=21, max_episode_steps=9, device_world=dw, host_outputs=False, obs_layout="frame")
+    env.set_complexity(0.25)
+    env.reset()
+    ring = vn.rollout.ReplayRing(dw, N, capacity=cap, seed=99)
+    ring.start(env)
+    assert (ring.sample_sequence(5)["start"] == -1).all()           # nothing stored yet
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for step in range(150):                                         # wraps the ring twice
+        a = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+        env.step(a)
+        ring.insert(env, a)
+    host = {k: getattr(ring, k).cpu().numpy() for k in ("before", "after", "reward", "done", "action")}
+    labels = []
+    for trial in range(30):
+        for mode, length in ((0, 6), (1, 4)):
+            call = ring.calls
+            smp = ring.sample_sequence(length) if mode == 0 else ring.sample_rp_sequence()
+            st = smp["start"].cpu().numpy()
+            for e in range(N):
+                want = orl.replay_sample(host["before"][:, e], host["after"][:, e], host["reward"][:, e], host["done"][:, e],
+                                         ring.head, ring.count, length, mode, 99, e, call)
+                assert st[e] == want[0]
+                if want[0] >= 0:
+                    assert smp["states"][e].cpu().tolist() == want[1]
+                    d = smp["dones"][e].cpu().numpy()
+                    assert not d[:-1].any()                             # never straddles an episode boundary
+                    if mode == 1:
+                        assert int(smp["label"][e]) == want[2]
+                        labels.append(want[2] != 0)
+    # skewed sampling: non-zero rewards are drawn far more often than their share of the ring (an env whose
+    # ring holds no valid non-zero window falls back to the zero class, so the rate stays below 1/2)
+    base = host["reward"].astype(bool).mean()
+    assert base < 0.05 and 2 * base < np.mean(labels) < 0.6
+    smp = ring.sample_sequence(6)
+    fr = ring.frames(smp, "rgb")
+    assert fr.shape == (N, 7, 84, 84, 3)
+    assert torch.equal(fr[3, 2], dw.plane_view("rgb")[int(smp["states"][3, 2])])
+    ff = ring.frames(smp, "rgb", scaled_float=True)
+    assert ff.shape == (N, 7, 3, 84, 84)
