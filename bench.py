@@ -166,8 +166,19 @@ def _cpu_world(n_envs, seed):
         e = oenvs.GymGraphRgbdGoalEnv(osc, goals=goal)
         e.set_complexity(_CPU.get("hardness", HARDNESS))
         e.reset_source = ovec.ReferenceStyleResetSource(osc, [goal], lambda t, e=e: e.optimal_distance(), seed + i)
-        envs.append(ovec.RewardCollector(ovec.TimeLimit(e, MAX_EPISODE_STEPS)))
-    return ovec.VecEnv(envs)
+        tl = ovec.TimeLimit(e, MAX_EPISODE_STEPS)
+        envs.append(ovec.RewardCollector(tl))
+    ve = ovec.VecEnv(envs)
+    ve._time_limits = [w.env for w in envs]
+    return ve
+
+
+def _randomise_phases(ve, seed):
+    """After reset(): put every env at a random phase of its 900-step episode so that a bounded sample sees
+    time-limit resets at the steady-state rate (1 / 900 per env-step) instead of none at all."""
+    rng = np.random.RandomState(seed + 4242)
+    for tl in ve._time_limits:
+        tl._elapsed = int(rng.randint(0, MAX_EPISODE_STEPS))
 
 
 def _cpu_worker(conn, n_envs, seed):
@@ -178,7 +189,9 @@ def _cpu_worker(conn, n_envs, seed):
         if cmd == "step":
             conn.send(ve.step(data)[:3])
         elif cmd == "reset":
-            conn.send(ve.reset())
+            ve.reset()
+            _randomise_phases(ve, seed)
+            conn.send(None)
         else:
             conn.close()
             return
@@ -191,6 +204,7 @@ def cpu_run(n_envs, steps, warmup, workers, seed=0):
     if workers <= 1:
         ve = _cpu_world(n_envs, seed)
         ve.reset()
+        _randomise_phases(ve, seed)
         for _ in range(warmup):
             ve.step(rng.randint(0, 4, n_envs))
         t0 = time.perf_counter()
@@ -257,7 +271,8 @@ def run_reference(args):
         "config": {"workload": WORKLOAD, "sample": "%d envs x %d vector steps" % (n_envs, steps)},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": workers, "kind": "port",
                          "sample": "%d envs x %d vector steps over %d worker processes (pipes), oracle port of "
-                                   "GoalGymGraphAuxiliaryEnv incl. per-reset candidate enumeration; p_reset=%.4f"
+                                   "GoalGymGraphAuxiliaryEnv incl. per-reset candidate enumeration, episode phases "
+                                   "randomised to the steady state; p_reset=%.5f"
                                    % (n_envs, steps, workers, nres / max(1, n_envs * steps))},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -433,10 +448,13 @@ def run_cuda(args):
 
     cpu_baseline = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline and args.workload == "c2":
-        v, nres, cdt = cpu_run(16, 400, 3, 1)
+        # bounded sample (~15 s of CPU work): 32 envs x 4,000 vector steps cross the 900-step TimeLimit about four
+        # times per env, so the reference's per-reset candidate enumeration (~0.1 s each here) is included
+        v, nres, cdt = cpu_run(32, 4000, 3, 1)
         cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                        "sample": "16 envs x 400 vector steps, one process, sequential + np.stack (DummyVecEnv "
-                                  "equivalent), %.1f s, p_reset=%.4f" % (cdt, nres / (16 * 400.0))}
+                        "sample": "32 envs x 4000 vector steps, one process, sequential + np.stack (DummyVecEnv "
+                                  "equivalent), episode phases randomised, %.1f s, p_reset=%.5f"
+                                  % (cdt, nres / (32 * 4000.0))}
 
     if rank == 0:
         line = {
