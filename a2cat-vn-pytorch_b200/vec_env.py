@@ -104,8 +104,8 @@ class GraphVecEnv:
         """
         world            tables.World (compiled scenes) - or pass a ready ``device_world``
         num_envs         TOTAL number of envs of the job; this process owns shard_range(num_envs, rank, world_size)
-        env_tasks        per GLOBAL env (lo, count) range into world.tasks (default: env i owns all tasks
-                         of scene i % n_scenes ... see _default_env_tasks)
+        env_tasks        per GLOBAL env (lo, count) range into world.tasks the env draws its task from on reset
+                         (default: tasks dealt round-robin, one per env - see _default_env_tasks)
         inject           optional (task [n_local, R] int32, start [n_local, R] int32 GLOBAL states) reset stream
         host_outputs     rewards / dones as numpy (reference behaviour) or as CUDA tensors
         scaled_float     observation leaves as float32 CHW in [0, 1] - what TransposeImage + ScaledFloatFrame
@@ -237,7 +237,6 @@ class GraphVecEnv:
         self._pack_np = self._pack_host.numpy()
         self._ready = C.c_void_p()
         L.check(self.lib.vn_event_create(C.byref(self._ready)))
-        self._p_inject = C.byref(self._c_inject) if self._c_inject is not None else None
 
     # ------------------------------------------------------------------ construction helpers
     def _default_env_tasks(self, num_envs):
@@ -330,6 +329,13 @@ class GraphVecEnv:
                                          self._stream()))
         self.kernel_launches += 2
         self._pending = "device"
+
+    def step_enqueue(self, actions):
+        """Device-resident loops: enqueue one vectorised step for CUDA int32 ``actions`` and return at once.
+        Nothing is copied to the host; ``env.reward`` / ``env.done`` / the observation buffers hold the
+        results in stream order."""
+        self.step_async(actions)
+        self._pending = False
 
     def _unpack(self, host):
         n = self.num_envs

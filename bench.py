@@ -322,8 +322,7 @@ def run_cuda(args):
 
     def device_loop(k0, k):
         for i in range(k0, k0 + k):
-            env.step_async(actions[i % n_rows])
-            env._pending = False
+            env.step_enqueue(actions[i % n_rows])
 
     device_loop(0, args.mix)      # un-timed: lets the state distribution settle (random-walk mixing)
     device_loop(0, W)
@@ -395,7 +394,7 @@ def run_cuda(args):
     del pairs
 
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(), "kernel": "vn_gather_%s_kernel" % args.gather_name(env),
+                "traffic": profiled_traffic(), "kernel": "vn_gather_%s_kernel" % ("ldg" if args.gather == "ldg" else "bulk"),
                 "kernel_ms": gather_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "same_size_copy_ms": copy_ms, "same_size_copy_gbs": 2 * nb / (copy_ms * 1e-3) / 1e9,
                 "step_frac": (N * (2 * F_OBS + p_reset * 2 * F_GOAL + 40)) / (ms * 1e-3 / K) / 1e9 / peak
@@ -497,8 +496,7 @@ def run_rollout(args):
     gen = torch.Generator(device=dev).manual_seed(3)
     for _ in range(T):
         a = torch.randint(0, 4, (N,), device=dev, generator=gen, dtype=torch.int32)
-        env.step_async(a)
-        env._pending = False
+        env.step_enqueue(a)
         buf.insert(env, a)
     states = buf.states.t().contiguous()          # [N, T+1]
     goals = buf.goals[:-1].t().contiguous()
@@ -568,7 +566,6 @@ def main():
     ap.add_argument("--mix", type=int, default=1000, help="un-timed steps before warm-up")
     ap.add_argument("--envs-per-gpu", type=int, default=None, help="development: override the 4,096 envs per GPU")
     args = ap.parse_args()
-    args.gather_name = lambda env: {0: "auto", 1: "ldg", 2: "bulk"}[env.gather]
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "c5":
