@@ -320,7 +320,17 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    graph_len = 0
+    if args.cuda_graph:
+        # launch-bound batches (C1): replay CUDA graphs of `graph_len` steps instead of 2 launches per step
+        graph_len = min(64, n_rows)
+        graph = env.capture_steps(actions[:graph_len])
+
     def device_loop(k0, k):
+        if graph_len:
+            for _ in range((k + graph_len - 1) // graph_len):
+                graph.replay()
+            return
         for i in range(k0, k0 + k):
             env.step_enqueue(actions[i % n_rows])
 
@@ -332,6 +342,8 @@ def run_cuda(args):
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = env.kernel_launches
+    if graph_len:
+        K = ((K + graph_len - 1) // graph_len) * graph_len      # whole graphs
     ev0.record()
     device_loop(W, K)
     if world_size > 1:
@@ -342,7 +354,7 @@ def run_cuda(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    launches = env.kernel_launches - launches0
+    launches = 2 * K if graph_len else env.kernel_launches - launches0
     if world_size > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -466,6 +478,7 @@ def run_cuda(args):
                              % (env.dw.nbytes() / 1e6, N * F_OBS / 1e6),
                        "gather": args.gather, "p_reset": p_reset, "collision_rate": coll,
                        "max_episode_steps": MAX_EPISODE_STEPS, "hardness": hardness, "mix_steps": args.mix,
+                       "cuda_graph_steps": graph_len,
                        "parallelism": "env-sharded x%d, no data-path collective" % world_size},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline,
@@ -559,6 +572,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay 64-step CUDA graphs in the device-resident loop")
     ap.add_argument("--quick", action="store_true", help="development: device-resident number + roofline only")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "rgb"],
                     help="BASELINE.json config; c2 is the headline, the others are secondary lines")
