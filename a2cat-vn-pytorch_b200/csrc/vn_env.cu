@@ -237,6 +237,7 @@ struct GatherParams {
     const uint8_t *did_reset;  // [n] goal planes are rewritten only where set (NULL = always)
     uint8_t *obs[VN_MAX_PLANES];
     uint8_t *goal_obs[VN_MAX_PLANES];
+    unsigned int *sched;  // optional ticket counters (dynamic scheduling), see vn_gather_bulk_kernel
     int32_t n;
 };
 
@@ -299,7 +300,9 @@ __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherPar
 // Work unit = (env, slice): each plane is cut into `split` slices of whole 16-byte units, so that
 // split > 1 gives more, smaller CTAs per SM.  Units are handed out by an atomic ticket counter
 // (persistent CTAs, dynamic scheduling): no CTA idles while another still has a queue of records.
-__device__ unsigned int g_sched[64][2];  // [slot][0] next ticket, [slot][1] CTAs finished; self-resetting
+// The ticket counter is CALLER-OWNED scratch (vn_step_out_t.sched: [0] next ticket, [1] CTAs finished), zero
+// before the first launch and re-armed by the last CTA of every launch, so gathers of different env batches
+// on different streams never share a counter.  Without scratch the units are dealt statically.
 
 struct BulkHints {
     int mode;  // bit 0: loads evict_last, bit 1: stores evict_first
@@ -354,7 +357,7 @@ __device__ __forceinline__ void bulk_copy_slice(const vn_store_t &st, const uint
     bulk_commit();
 }
 
-__global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p, int split, int slot, int dynamic,
+__global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p, int split, unsigned int *sched,
                                                             int hint_mode) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -370,7 +373,8 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     hints.load_policy = (hint_mode & 1) ? l2_policy_evict_last() : 0;
     hints.store_policy = (hint_mode & 2) ? l2_policy_evict_first() : 0;
     const int units = p.n * split;
-    int u = dynamic ? (int)atomicAdd(&g_sched[slot][0], 1u) : (int)blockIdx.x;
+    const bool dynamic = sched != nullptr;
+    int u = dynamic ? (int)atomicAdd(&sched[0], 1u) : (int)blockIdx.x;
     while (u < units) {
         const int env = u / split, slice = u - env * split;
         const uint8_t *src = p.store.base + (size_t)p.obs_state[env] * p.store.state_pitch;
@@ -379,15 +383,15 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
             const uint8_t *gsrc = p.store.base + (size_t)p.goal[env] * p.store.state_pitch;
             bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints);
         }
-        u = dynamic ? (int)atomicAdd(&g_sched[slot][0], 1u) : u + (int)gridDim.x;
+        u = dynamic ? (int)atomicAdd(&sched[0], 1u) : u + (int)gridDim.x;
     }
     bulk_wait_read<0>();
     if (dynamic) {
         // last CTA out re-arms the slot for the launch that will reuse it
         __threadfence();
-        if (atomicAdd(&g_sched[slot][1], 1u) == gridDim.x - 1) {
-            g_sched[slot][0] = 0;
-            g_sched[slot][1] = 0;
+        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
+            sched[0] = 0;
+            sched[1] = 0;
             __threadfence();
         }
     }
@@ -459,15 +463,20 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-static int g_sm_count = 0;
+constexpr int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 static int sm_count() {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int cached[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!cached[dev]) {
+        cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (cached[dev] <= 0) cached[dev] = 148;
     }
-    return g_sm_count;
+    return cached[dev];
 }
 
 static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream_t stream) {
@@ -509,18 +518,17 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         }
         const int smem = max(smem_obs, smem_goal);
         VN_REQUIRE(smem <= 200 * 1024, "gather(bulk): %d bytes of planes per env exceed shared memory", smem);
-        static int configured = 0;
-        if (smem > configured) {
+        static int configured[kMaxDevices] = {0};  // the attribute is per device
+        const int dev = current_device();
+        if (smem > configured[dev]) {
             cudaFuncSetAttribute(vn_gather_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            configured = smem;
+            configured[dev] = smem;
         }
         int per_sm = max(1, min(32, (220 * 1024) / (smem + 1024)));
         if (env_per_sm > 0) per_sm = min(per_sm, env_per_sm);
         const int grid = (int)min((int64_t)gp.n * split, (int64_t)sm_count() * per_sm);
-        static unsigned launch_seq = 0;
-        const int slot = (int)(launch_seq++ & 63u);
-        launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, split, slot, env_dynamic,
-                   env_hints);
+        launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, split,
+                   env_dynamic ? gp.sched : nullptr, env_hints);
         return check_launch("vn_gather_bulk_kernel");
     }
     set_error("gather: unknown variant %d", variant);
@@ -588,6 +596,7 @@ static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const 
     }
     gp.goal = any_goal ? envs->goal : nullptr;
     gp.did_reset = out->did_reset;
+    gp.sched = out->sched;
     VN_REQUIRE(!any_goal || out->did_reset, "out: did_reset is required when goal planes are emitted");
     if (!any_goal && !any_obs) return VN_OK;
     return launch_gather(gp, variant, static_cast<cudaStream_t>(stream));
@@ -729,6 +738,7 @@ int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *i
     gp.obs_state = idx;
     gp.goal = nullptr;
     gp.did_reset = nullptr;
+    gp.sched = nullptr;  // static unit assignment: no scratch in this signature
     gp.n = n;
     for (int pl = 0; pl < VN_MAX_PLANES; ++pl) {
         gp.obs[pl] = (pl == plane) ? out : nullptr;

@@ -3,6 +3,19 @@
 // and the fused gather -> float32 CHW conversion for the policy input.
 #include "vn_common.cuh"
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember the largest request per device
+#define VN_ENSURE_SMEM(kernel, bytes)                                                              \
+    do {                                                                                           \
+        static int configured_[64] = {0};                                                          \
+        int dev_ = 0;                                                                              \
+        cudaGetDevice(&dev_);                                                                      \
+        dev_ = (dev_ >= 0 && dev_ < 64) ? dev_ : 0;                                                \
+        if ((bytes) > configured_[dev_]) {                                                         \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes));    \
+            configured_[dev_] = (bytes);                                                           \
+        }                                                                                          \
+    } while (0)
+
 namespace vn {
 
 // =====================================================================================================
@@ -509,11 +522,7 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
     const int fb = (h * w * c + 15) & ~15;
     const int smem = 256 * 32 * 4 + 2 * fb;
     VN_REQUIRE(smem <= 220 * 1024, "pixel_control: frame too large for shared memory");
-    static int configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(vn::vn_pixel_control_kernel<kChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = smem;
-    }
+    VN_ENSURE_SMEM(vn::vn_pixel_control_kernel<kChunk>, smem);
     const int64_t blocks = (int64_t)n * ((t + kChunk - 1) / kChunk);
     VN_REQUIRE(blocks < (1ll << 31), "pixel_control: too many blocks");
     vn::vn_pixel_control_kernel<kChunk><<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -561,11 +570,7 @@ int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int3
     const int fb = (h * w * c + 15) & ~15;
     const int smem = 256 * 32 * 4 + 2 * fb;
     VN_REQUIRE(smem <= 220 * 1024, "pixel_control_list: frame too large for shared memory");
-    static int configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(vn::vn_pixel_control_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = smem;
-    }
+    VN_ENSURE_SMEM(vn::vn_pixel_control_list_kernel, smem);
     const int grid = max_count < 148 * 3 ? max_count : 148 * 3;
     vn::vn_pixel_control_list_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         *store, plane, states, t, g, pos, count, max_count, out);
@@ -622,11 +627,7 @@ int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx
     if (m == 0) return VN_OK;
     const int smem = 256 * 32 * 4 + ((h * w * c + 15) & ~15);
     VN_REQUIRE(smem <= 220 * 1024, "aux_target: frame too large for shared memory");
-    static int configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(vn::vn_aux_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = smem;
-    }
+    VN_ENSURE_SMEM(vn::vn_aux_target_kernel, smem);
     const int grid = m < 148 * 8 ? m : 148 * 8;
     vn::vn_aux_target_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, m, g, out);
     return vn::check_launch("vn_aux_target_kernel");
@@ -640,11 +641,7 @@ int32_t vn_gather_plane_f32_chw(const vn_store_t *store, int32_t plane, const in
     if (n == 0) return VN_OK;
     const int smem = (h * w * c + 15) & ~15;
     VN_REQUIRE(smem <= 220 * 1024, "gather_plane_f32_chw: frame too large for shared memory");
-    static int configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(vn::vn_gather_f32_chw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = smem;
-    }
+    VN_ENSURE_SMEM(vn::vn_gather_f32_chw_kernel, smem);
     const int grid = n < 148 * 8 ? n : 148 * 8;
     vn::vn_gather_f32_chw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, n, h, w,
                                                                                         c, out);

@@ -55,7 +55,7 @@ class StepOut(C.Structure):
     _fields_ = [("obs", _P * VN_MAX_PLANES), ("goal_obs", _P * VN_MAX_PLANES), ("reward", _P), ("done", _P),
                 ("truncated", _P), ("win", _P), ("did_reset", _P), ("last_action_reward", _P),
                 ("episode_return", _P), ("episode_length", _P), ("info_state", _P), ("obs_state", _P), ("stats", _P),
-                ("host_pack", _P)]
+                ("sched", _P), ("host_pack", _P)]
 
 
 class Replay(C.Structure):

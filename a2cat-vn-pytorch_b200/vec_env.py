@@ -170,6 +170,7 @@ class GraphVecEnv:
             self.obs_state = i32()
             self.stats = torch.zeros(L.VN_N_STATS, dtype=torch.int64, device=self.device)
             self.actions_dev = i32()
+            self._sched = torch.zeros(2, dtype=torch.int32, device=self.device)     # gather ticket counters
             self.obs_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
                                            dtype=torch.uint8, device=self.device) for p in self.obs_planes}
             self.goal_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
@@ -204,6 +205,7 @@ class GraphVecEnv:
         out.last_action_reward = self.lar.data_ptr()
         out.episode_return, out.episode_length = self.episode_return.data_ptr(), self.episode_length.data_ptr()
         out.info_state, out.obs_state, out.stats = self.info_state.data_ptr(), self.obs_state.data_ptr(), self.stats.data_ptr()
+        out.sched = self._sched.data_ptr()
         self._c_out = out
         # same outputs + the mapped pinned host mirror of the per-env scalars (host-actions path)
         out_h = L.StepOut()

@@ -140,6 +140,8 @@ typedef struct vn_step_out {
     int32_t *info_state;              /* [n_envs] info['state']: state after the move, before auto-reset */
     int32_t *obs_state;               /* [n_envs] state whose frames were gathered (scratch, required) */
     uint64_t *stats;                  /* [VN_N_STATS] running sums, see VN_STAT_* */
+    uint32_t *sched;                  /* optional scratch of 2 uint32, zeroed once by the caller: ticket counters of the
+                                         gather's dynamic scheduler (self re-arming; one per env batch / stream) */
     uint8_t *host_pack;               /* optional MAPPED PINNED HOST block of 20 * n_envs bytes ("host pack") that the
                                          scalar kernel also writes, n = n_envs:
                                            [0, 4n) reward f32 | [4n, 8n) episode_return f32 | [8n, 12n) episode_length i32
