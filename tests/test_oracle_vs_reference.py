@@ -62,3 +62,43 @@ def test_reference_reset_cost_is_what_the_cpu_baseline_models():
     pots, d = gu.initial_state_candidates(maze, dist, act, goal)
     n, p, idx = inj.calls[0]
     assert n == len(pots) and np.array_equal(p, gu.initial_state_weights(d, 7.5)) and pots[idx] == s
+
+
+def test_loader_consumes_a_reference_pickle(tmp_path):
+    """A scene pickled the way the reference stores them (ThorGridWorld, graph/multi_graph_no_tp.py) and read
+    back with the reference's own load_graph (graph/util.py:69-79) goes through loaders.scene_from_thor_grid_world
+    into the same tables / frames as the synthetic scene it was exported from."""
+    import importlib
+    import pickle
+    from oracle import ref_harness as rh
+    vn = importlib.import_module("a2cat-vn-pytorch_b200")
+    T = vn.tables
+    ref = rh.ref_modules()
+    scene = H.scenes.make_maze_scene((9, 8), 0.2, 31, n_goals=2, planes=("rgb", "depth", "segmentation"))
+    X, Y = scene.maze.shape
+    arrs = {}
+    for plane, c in (("rgb", 3), ("depth", 1), ("segmentation", 3)):
+        a = np.zeros((X, Y, 4, 84, 84, c), np.uint8)
+        a[scene.cells[:, 0], scene.cells[:, 1]] = scene.plane_frames(plane).reshape(scene.n_cells, 4, 84, 84, c)
+        arrs[plane] = a
+    world = ref.thor_world.ThorGridWorld(scene.maze.copy(), arrs["rgb"], arrs["depth"], arrs["segmentation"])
+    world.goals = list(scene.goals)
+    path = tmp_path / "scene.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(world, f)
+    graph = ref.util.load_graph(str(path))                       # adds graph.graph / graph.optimal_actions
+    loaded = vn.loaders.scene_from_thor_grid_world(graph, graph.goals)
+    w0, w1 = T.compile_world([scene], T.GYM_GRAPH), T.compile_world([loaded], T.GYM_GRAPH)
+    assert np.array_equal(w0.adj, w1.adj) and np.array_equal(w0.cand_state, w1.cand_state)
+    assert all(t.max_dist == int(np.max(graph.graph)) for t in w1.tasks)          # largest_distance, graph.py:35
+    for p in ("rgb", "depth", "segmentation"):
+        assert np.array_equal(loaded.plane_frames(p), scene.plane_frames(p))
+    # GraphResize hoisted: what the reference would render per step at another screen size
+    rz = ref.core.GraphResize(graph, (44, 44))
+    small = vn.loaders.scene_from_thor_grid_world(graph, graph.goals, screen_size=(44, 44))
+    for s in (0, 17, scene.n_states - 1):
+        x, y, r = scene.state_tuple(s)
+        rgb, depth, seg = rz.render((x, y), r, modes=["rgb", "depth", "segmentation"])
+        assert np.array_equal(small.plane_frames("rgb", [s])[0], rgb)
+        assert np.array_equal(small.plane_frames("depth", [s])[0], depth)
+        assert np.array_equal(small.plane_frames("segmentation", [s])[0], seg)
