@@ -28,10 +28,15 @@ def _resize_frames(frames, hw):
 def scene_from_thor_grid_world(graph, goals, screen_size=None, planes=("rgb", "depth", "segmentation"), scene_id=0,
                                name="thor"):
     """``graph``: any object with the ThorGridWorld attributes.  Frames are compacted to free cells
-    (state = free_cell_rank * 4 + rotation) and resized once to ``screen_size`` (default: stored size)."""
+    (state = free_cell_rank * 4 + rotation) and resized once to ``screen_size`` (default: stored size).
+    Pass ``planes`` including ``tp_rgb`` / ``tp_depth`` / ``tp_segmentation`` for the third-person variant
+    (graph/thor_graph.py), whose ``render`` returns the 6-tuple of ``obs_layout="thor6"``."""
     maze = np.asarray(graph._maze).astype(bool)
     xs, ys = np.nonzero(maze)
     src = {"rgb": graph._observations, "depth": graph._depths, "segmentation": graph._segmentations}
+    for name, attr in (("tp_rgb", "_tp_observations"), ("tp_depth", "_tp_depths"), ("tp_segmentation", "_tp_segmentations")):
+        if hasattr(graph, attr):                    # graph/thor_graph.py:6-13 (third-person camera of the 2nd agent)
+            src[name] = getattr(graph, attr)
     hw = tuple(screen_size) if screen_size is not None else tuple(src["rgb"].shape[3:5])
     explicit = {}
     for p in planes:

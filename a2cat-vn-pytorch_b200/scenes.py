@@ -17,9 +17,11 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-PLANE_NAMES = ("rgb", "depth", "segmentation")
-PLANE_CHANNELS = {"rgb": 3, "depth": 1, "segmentation": 3}
-PLANE_ID = {"rgb": 0, "depth": 1, "segmentation": 2}
+#: first-person planes (graph/multi_graph_no_tp.py:6-25) and the third-person ones the two-agent scenes add
+#: (graph/thor_graph.py:6-36: ``_tp_observations`` / ``_tp_depths`` / ``_tp_segmentations``)
+PLANE_NAMES = ("rgb", "depth", "segmentation", "tp_rgb", "tp_depth", "tp_segmentation")
+PLANE_CHANNELS = {"rgb": 3, "depth": 1, "segmentation": 3, "tp_rgb": 3, "tp_depth": 1, "tp_segmentation": 3}
+PLANE_ID = {"rgb": 0, "depth": 1, "segmentation": 2, "tp_rgb": 3, "tp_depth": 4, "tp_segmentation": 5}
 
 _M64 = (1 << 64) - 1
 

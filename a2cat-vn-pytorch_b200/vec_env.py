@@ -37,6 +37,8 @@ OBS_LAYOUTS = {
     "pair": ("rgb", "goal_rgb"),
     # THORCachedEnv.process, environments/gym_thor_cached.py:89-92
     "dict": {"image": "rgb", "goal": "goal_rgb"},
+    # ThorGridWorld.render of the third-person variant, graph/thor_graph.py:15-36 (modes rgb, depth, segmentation)
+    "thor6": ("rgb", "depth", "segmentation", "tp_rgb", "tp_depth", "tp_segmentation"),
     # BASELINE.json configs[1]: "84x84 RGB+depth+goal"
     "rgbd_goal": ("rgb", "goal_rgb", "depth"),
 }

@@ -577,3 +577,23 @@ def test_cuda_graph_capture_is_bit_identical():
         assert all(torch.equal(x, y) for x, y in zip(a.goal_buf.values(), b.goal_buf.values()))
         acts.copy_(torch.randint(0, 4, (S, N), device="cuda", dtype=torch.int32))   # new content, same graph
     assert db.sum() > 0
+
+
+def test_third_person_planes_six_tuple():
+    """graph/thor_graph.py: scenes with third-person planes; render returns (rgb, depth, seg, tp_rgb, tp_depth,
+    tp_seg).  Six planes in one store record, gathered by both kernel variants."""
+    import torch
+    planes = ("rgb", "depth", "segmentation", "tp_rgb", "tp_depth", "tp_segmentation")
+    scene = H.scenes.make_maze_scene((10, 10), 0.25, 2, n_goals=1, planes=planes)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    assert world.layout.state_pitch == 2 * (21248 + 7168 + 21248)
+    for gather in ("bulk", "ldg"):
+        env = vn.GraphVecEnv(world, 40, seed=2, max_episode_steps=11, obs_layout="thor6", unreal_wrapper=False,
+                             gather=gather)
+        obs = env.reset()
+        rng = np.random.RandomState(1)
+        for _ in range(20):
+            obs, _, _, _ = env.step(rng.randint(0, 4, 40))
+        s = env.state.cpu().numpy()
+        for leaf, name in zip(obs, planes):
+            assert np.array_equal(leaf.cpu().numpy(), scene.plane_frames(name, s)), (gather, name)

@@ -236,3 +236,25 @@ def test_loaders_thor_grid_world_and_h5():
     wb = T.compile_world([h5], T.THOR_CACHED, tasks=[(0, 5), (0, 40)])
     assert np.array_equal(wa.adj, wb.adj) and np.array_equal(wa.cand_state, wb.cand_state)
     assert np.array_equal(wa.task_cand_off, wb.task_cand_off)
+
+
+def test_loader_third_person_planes():
+    L = vn.loaders
+    scene = H.scenes.make_maze_scene((6, 6), 0.2, 4, n_goals=1,
+                                     planes=("rgb", "depth", "segmentation", "tp_rgb", "tp_depth", "tp_segmentation"))
+    X, Y = scene.maze.shape
+
+    class TGW:      # duck-typed graph/thor_graph.py:6-13
+        pass
+    g = TGW()
+    g._maze = scene.maze
+    for attr, plane, c in (("_observations", "rgb", 3), ("_depths", "depth", 1), ("_segmentations", "segmentation", 3),
+                           ("_tp_observations", "tp_rgb", 3), ("_tp_depths", "tp_depth", 1),
+                           ("_tp_segmentations", "tp_segmentation", 3)):
+        a = np.zeros((X, Y, 4, 84, 84, c), np.uint8)
+        a[scene.cells[:, 0], scene.cells[:, 1]] = scene.plane_frames(plane).reshape(scene.n_cells, 4, 84, 84, c)
+        setattr(g, attr, a)
+    loaded = L.scene_from_thor_grid_world(g, scene.goals, planes=scene.planes)
+    for p in scene.planes:
+        assert np.array_equal(loaded.plane_frames(p), scene.plane_frames(p))
+    assert not np.array_equal(scene.plane_frames("rgb"), scene.plane_frames("tp_rgb"))
