@@ -355,3 +355,48 @@ def compile_world(scenes: Sequence[GridScene], family: Family, tasks: Optional[S
     goal = np.array([t.goal_state + base[t.scene] for t in built], np.int32)
     return World(family, scenes, base, np.concatenate(adjs, 0), built, goal, off.astype(np.int32), cand,
                  StoreLayout.make(planes, scenes[0].frame_hw))
+
+
+# --------------------------------------------------------------------------- evaluation services
+def optimal_policy_table(world: World, task_index: int):
+    """Shortest action sequences on the STATE graph of one task (the
+    reference only keeps grid-level ``optimal_actions``, graph/util.py:146-176, which ignore rotations).
+
+    Returns ``(dist, action)`` over the task's scene states (local indices): ``dist[s]`` = fewest actions
+    from ``s`` to the goal state (-1 if unreachable), ``action[s]`` = the lowest-numbered action that starts
+    such a sequence (-1 at the goal / unreachable).  Reverse BFS over ``adj`` from the goal."""
+    from collections import deque
+    t = world.tasks[task_index]
+    base = int(world.scene_base[t.scene])
+    n = world.scenes[t.scene].n_states
+    adj = world.adj[base:base + n]
+    local = np.where(adj >= 0, adj - base, -1)
+    rev = [[] for _ in range(n)]
+    for s in range(n):
+        for a in range(4):
+            d = int(local[s, a])
+            if d >= 0 and d != s:
+                rev[d].append(s)
+    goal_compare = world.family.goal_compare
+    goals = [t.goal_state] if goal_compare == 0 else \
+        ([(t.goal_state >> 2) * 4 + r for r in range(4)] if goal_compare == 1 else [])
+    dist = np.full(n, -1, np.int32)
+    q = deque()
+    for g in goals:
+        dist[g] = 0
+        q.append(g)
+    while q:
+        d = q.popleft()
+        for s in rev[d]:
+            if dist[s] < 0:
+                dist[s] = dist[d] + 1
+                q.append(s)
+    action = np.full(n, -1, np.int32)
+    for s in range(n):
+        if dist[s] > 0:
+            for a in range(4):
+                d = int(local[s, a])
+                if d >= 0 and dist[d] == dist[s] - 1:
+                    action[s] = a
+                    break
+    return dist, action

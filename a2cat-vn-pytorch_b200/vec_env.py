@@ -445,6 +445,26 @@ class GraphVecEnv:
             self.stats.zero_()
         return dict(zip(L.STAT_NAMES, out.tolist()))
 
+    def optimal_actions(self):
+        """Evaluation service: for every env the first action of a shortest
+        action sequence to its current goal, and the remaining distance, from per-task tables computed once
+        on the host (tables.optimal_policy_table) and kept on the device.  Returns (actions, dist) int32 [N]."""
+        if not hasattr(self, "_opt"):
+            from .tables import optimal_policy_table
+            S = self.world.n_states
+            T_ = len(self.world.tasks)
+            act = np.full((T_, S), -1, np.int32)
+            dst = np.full((T_, S), -1, np.int32)
+            for ti, t in enumerate(self.world.tasks):
+                b = int(self.world.scene_base[t.scene])
+                d, a = optimal_policy_table(self.world, ti)
+                act[ti, b:b + len(a)] = a
+                dst[ti, b:b + len(d)] = d
+            self._opt = (torch.from_numpy(act).to(self.device), torch.from_numpy(dst).to(self.device))
+        act, dst = self._opt
+        t, s = self.task.long(), self.state.long()
+        return act[t, s], dst[t, s]
+
     def state_dict(self):
         keys = ("state", "goal", "task", "elapsed", "epoch", "ep_return", "ep_length", "stats")
         d = {k: getattr(self, k).cpu().clone() for k in keys}

@@ -597,3 +597,35 @@ def test_third_person_planes_six_tuple():
         s = env.state.cpu().numpy()
         for leaf, name in zip(obs, planes):
             assert np.array_equal(leaf.cpu().numpy(), scene.plane_frames(name, s)), (gather, name)
+
+
+def test_optimal_policy_reaches_every_goal_in_the_shortest_number_of_actions():
+    """End-to-end property of adjacency + goal test + reward + auto-reset: an agent that follows the
+    state-graph shortest paths wins every episode in exactly dist(start) steps (SPL = 1)."""
+    import torch
+    scene = H.scenes.make_thor_scene(300, (30, 30), seed=4, n_goals=3, planes=("rgb",))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    N = 512
+    env = vn.GraphVecEnv(world, N, seed=8, max_episode_steps=900, obs_layout="frame", host_outputs=False)
+    env.reset()
+    a, d0 = env.optimal_actions()
+    assert (d0 > 0).all()
+    remaining = d0.clone()
+    wins = torch.zeros(N, dtype=torch.int64, device="cuda")
+    for t in range(200):
+        a, d = env.optimal_actions()
+        assert torch.equal(d, remaining)
+        _, rew, done, _ = env.step(a)
+        remaining = remaining - 1
+        reached = remaining == 0
+        assert torch.equal(done, reached) and torch.equal(rew == 1.0, reached)
+        wins += reached
+        # auto-reset: new episode, new distance
+        _, dn = env.optimal_actions()
+        remaining = torch.where(reached, dn, remaining)
+    st = env.episode_stats()
+    assert st["episodes"] == st["successes"] == int(wins.sum()) and st["collisions"] == 0 and st["truncations"] == 0
+    assert st["length_sum"] > 0
+    # oriented shortest paths are never shorter than the grid distance the curriculum uses minus nothing odd:
+    dist, act = T.optimal_policy_table(world, 0)
+    assert dist[world.tasks[0].goal_state] == 0 and (dist >= 0).all()
