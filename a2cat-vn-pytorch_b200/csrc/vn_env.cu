@@ -622,6 +622,19 @@ static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const v
 extern "C" {
 
 int32_t vn_abi_version(void) { return VN_ABI_VERSION; }
+
+int32_t vn_abi_struct_size(int32_t which) {
+    switch (which) {
+        case 0: return (int32_t)sizeof(vn_store_t);
+        case 1: return (int32_t)sizeof(vn_tables_t);
+        case 2: return (int32_t)sizeof(vn_envs_t);
+        case 3: return (int32_t)sizeof(vn_rules_t);
+        case 4: return (int32_t)sizeof(vn_inject_t);
+        case 5: return (int32_t)sizeof(vn_step_out_t);
+        case 6: return (int32_t)sizeof(vn_replay_t);
+        default: return -1;
+    }
+}
 const char *vn_last_error(void) { return vn::g_error.c_str(); }
 
 int32_t vn_fill_store(const vn_store_t *store, int32_t record0, int32_t n_records, uint64_t seed, int32_t scene,

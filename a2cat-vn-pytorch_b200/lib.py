@@ -70,7 +70,7 @@ class VnError(RuntimeError):
 _lib = None
 
 #: every symbol include/vn_b200.h declares
-EXPORTS = ("vn_abi_version", "vn_last_error", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
+EXPORTS = ("vn_abi_version", "vn_abi_struct_size", "vn_last_error", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
            "vn_env_gather", "vn_env_step_host", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_nstep_returns", "vn_discounted_backup", "vn_pixel_control",
            "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_replay_sample",
@@ -100,6 +100,7 @@ def load(build_if_missing=True):
     S, T, E, R, I, O = (C.POINTER(x) for x in (Store, Tables, Envs, Rules, Inject, StepOut))
     sig = {
         "vn_abi_version": (i32, []),
+        "vn_abi_struct_size": (i32, [i32]),
         "vn_last_error": (C.c_char_p, []),
         "vn_fill_store": (i32, [S, i32, i32, u64, i32, i32, C.POINTER(i32), _P]),
         "vn_env_reset": (i32, [S, T, E, R, I, _P, O, i32, _P]),
@@ -127,6 +128,10 @@ def load(build_if_missing=True):
         fn.restype, fn.argtypes = res, args
     if lib.vn_abi_version() != 1:
         raise VnError("libvn_b200.so ABI version %d, expected 1" % lib.vn_abi_version())
+    for which, mirror in enumerate((Store, Tables, Envs, Rules, Inject, StepOut, Replay)):
+        if lib.vn_abi_struct_size(which) != C.sizeof(mirror):
+            raise VnError("libvn_b200.so is stale: sizeof(%s) is %d in the library, %d in lib.py - rebuild with "
+                          "`python __graft_entry__.py`" % (mirror.__name__, lib.vn_abi_struct_size(which), C.sizeof(mirror)))
     _lib = lib
     return lib
 

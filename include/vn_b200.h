@@ -155,6 +155,9 @@ typedef struct vn_step_out {
 #define VN_GATHER_BULK 2     /* cp.async.bulk (TMA engine) global->shared->global, mbarrier-tracked */
 
 int32_t vn_abi_version(void);
+/* sizeof of the descriptor structs as compiled into the library (0 store, 1 tables, 2 envs, 3 rules, 4 inject,
+ * 5 step_out, 6 replay; -1 otherwise): a binding checks its mirrors against these at load time. */
+int32_t vn_abi_struct_size(int32_t which);
 const char *vn_last_error(void);
 
 /* Fills the store with the synthetic frame hash (a2cat-vn-pytorch_b200/scenes.py frame_bytes):

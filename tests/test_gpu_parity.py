@@ -629,3 +629,52 @@ def test_optimal_policy_reaches_every_goal_in_the_shortest_number_of_actions():
     # oriented shortest paths are never shorter than the grid distance the curriculum uses minus nothing odd:
     dist, act = T.optimal_policy_table(world, 0)
     assert dist[world.tasks[0].goal_state] == 0 and (dist >= 0).all()
+
+
+def test_c1_maze_graph_frames_a2c_n5_end_to_end():
+    """BASELINE.json configs[0]: 10x10 grid maze, 16 envs, 84x84 RGB cached observation, A2C n = 5.
+    The frames are MazeGraph.render (graph/maze_graph.py:20-24) hoisted through GraphResize((84, 84)) at store
+    build time (scenes.render_maze_frames, pinned by tests/golden/maze_render.npz); the env is the
+    SimpleGraphEnv family; 5-step rollouts feed the n-step return builder.  Everything vs the oracle."""
+    import torch
+    from oracle import rollout as orl
+    maze = H.scenes.random_maze((10, 10), 0.25, 0)
+    goal = tuple(int(v) for v in np.argwhere(maze)[0])               # DungeonGraph convention: first free cell
+    plain = H.scenes.GridScene(maze, [goal], False, (84, 84), ("rgb",))
+    frames = H.scenes.render_maze_frames(plain, goal, (84, 84))
+    scene = H.scenes.GridScene(maze, [goal], False, (84, 84), ("rgb",), explicit={"rgb": frames})
+    world = T.compile_world([scene], T.SIMPLE_GRAPH)
+    N, n_step, seed, limit = 16, 5, 31, 100
+    env = vn.GraphVecEnv(world, N, seed=seed, max_episode_steps=limit, obs_layout="frame", unreal_wrapper=False)
+    osc = oenvs.OracleScene(scene)
+    oes = []
+    for i in range(N):
+        e = oenvs.SimpleGraphEnv(osc, goal=goal)
+        cands = [gu.initial_position_candidates(maze, osc.graph, goal)]
+        e.reset_source = ovec.PhiloxResetSource(seed, i, cands, lambda t, e=e: e.optimal_distance(), True)
+        oes.append(ovec.TimeLimit(e, limit))
+    ov = ovec.VecEnv(oes)
+    env.set_complexity(0.5)
+    [e.set_complexity(0.5) for e in oes]
+    obs, (oobs, _) = env.reset(), ov.reset()
+    buf = vn.rollout.RolloutBuffer(env.dw, N, n_step)
+    rng = np.random.RandomState(2)
+    total_done = 0
+    for it in range(40):                                            # 40 A2C iterations of n = 5 steps
+        buf.start(env)
+        R, D = np.zeros((N, n_step), np.float32), np.zeros((N, n_step), bool)
+        for t in range(n_step):
+            a = rng.randint(0, 4, N)
+            obs, r, d, _ = env.step(a)
+            (oobs, _), orr, od, _ = ov.step(a)
+            buf.insert(env, torch.from_numpy(a))
+            assert np.array_equal(d, od) and np.array_equal(f32bits(r), f32bits(orr))
+            assert np.array_equal(obs.cpu().numpy(), np.rint(oobs * 255).astype(np.uint8))
+            R[:, t], D[:, t] = orr, od
+        v = rng.randn(N).astype(np.float32)
+        got = buf.returns(torch.from_numpy(v).cuda(), 0.99).cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), orl.nstep_returns(R, D, v, 0.99).view(np.uint32))
+        total_done += int(D.sum())
+    assert total_done > 5
+    # the rendered frames themselves: free = white, walls = black, agent red, goal green (before the resize)
+    assert frames.shape == (scene.n_cells, 84, 84, 3) and frames.max() == 255
