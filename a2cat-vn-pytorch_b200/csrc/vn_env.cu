@@ -60,7 +60,13 @@ __device__ __forceinline__ void pdl_wait_then_release() {
 
 template <bool kReset>
 __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
-    pdl_wait_then_release();
+    // Pipelined mode (VN_STEP_ACTIONS_READY + gather_desc): nothing this kernel reads was produced by its
+    // immediate predecessor - the previous gather - and what it writes for the next gather goes to the other
+    // half of the double-buffered descriptor, so it runs WHILE the previous gather is still copying and only
+    // waits for it at the very end (which also orders the next gather behind the previous one).
+    const bool defer_wait = (p.out.flags & VN_STEP_ACTIONS_READY) && p.out.gather_desc != nullptr;
+    if (!defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int flags = p.rules.flags;
     uint32_t st_episodes = 0, st_len = 0, st_succ = 0, st_coll = 0, st_steps = 0, st_trunc = 0, st_resets = 0;
@@ -202,6 +208,9 @@ __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
         p.env.ep_length[i] = ep_len;
         p.out.obs_state[i] = obs_s;
         if (p.out.did_reset) p.out.did_reset[i] = do_reset;
+        if (p.out.gather_desc)  // what the gather of THIS step needs: record to copy, goal record (or -1)
+            reinterpret_cast<int2 *>(p.out.gather_desc)[(size_t)(p.out.parity & 1) * p.env.n_envs + i] =
+                make_int2(obs_s, do_reset ? g : -1);
     }
 
     if (p.out.stats) {
@@ -225,6 +234,7 @@ __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
             if (rs) atomicAdd(st + VN_STAT_RESETS, (unsigned long long)rs);
         }
     }
+    if (defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // =====================================================================================================
@@ -232,6 +242,7 @@ __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
 // =====================================================================================================
 struct GatherParams {
     vn_store_t store;
+    const int2 *desc;          // [n] (record, goal record or -1) written by the step kernel; overrides the three below
     const int32_t *obs_state;  // [n] record to gather for the observation planes
     const int32_t *goal;       // [n] record of the goal planes (may be NULL)
     const uint8_t *did_reset;  // [n] goal planes are rewritten only where set (NULL = always)
@@ -270,7 +281,15 @@ __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherPar
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int env = blockIdx.x; env < p.n; env += gridDim.x) {
-        const int rec = __ldg(p.obs_state + env);
+        int rec, grec = -1;
+        if (p.desc) {
+            const int2 d = __ldg(p.desc + env);
+            rec = d.x;
+            grec = d.y;
+        } else {
+            rec = __ldg(p.obs_state + env);
+            if (p.goal && (!p.did_reset || __ldg(p.did_reset + env))) grec = __ldg(p.goal + env);
+        }
         const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
 #pragma unroll 1
         for (int pl = 0; pl < p.store.n_planes; ++pl) {
@@ -279,8 +298,8 @@ __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherPar
                                                   p.obs[pl] + (size_t)env * p.store.plane_bytes[pl],
                                                   p.store.plane_bytes[pl] >> 4);
         }
-        if (p.goal && (!p.did_reset || __ldg(p.did_reset + env))) {
-            const uint8_t *gsrc = p.store.base + (size_t)__ldg(p.goal + env) * p.store.state_pitch;
+        if (grec >= 0) {
+            const uint8_t *gsrc = p.store.base + (size_t)grec * p.store.state_pitch;
 #pragma unroll 1
             for (int pl = 0; pl < p.store.n_planes; ++pl) {
                 if (p.goal_obs[pl])
@@ -377,10 +396,19 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     int u = dynamic ? (int)atomicAdd(&sched[0], 1u) : (int)blockIdx.x;
     while (u < units) {
         const int env = u / split, slice = u - env * split;
-        const uint8_t *src = p.store.base + (size_t)p.obs_state[env] * p.store.state_pitch;
+        int rec, grec = -1;
+        if (p.desc) {
+            const int2 d = p.desc[env];
+            rec = d.x;
+            grec = d.y;
+        } else {
+            rec = p.obs_state[env];
+            if (p.goal && (!p.did_reset || p.did_reset[env])) grec = p.goal[env];
+        }
+        const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
         bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, &bar, parity, hints);
-        if (p.goal && (!p.did_reset || p.did_reset[env])) {
-            const uint8_t *gsrc = p.store.base + (size_t)p.goal[env] * p.store.state_pitch;
+        if (grec >= 0) {
+            const uint8_t *gsrc = p.store.base + (size_t)grec * p.store.state_pitch;
             bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints);
         }
         u = dynamic ? (int)atomicAdd(&sched[0], 1u) : u + (int)gridDim.x;
@@ -597,6 +625,9 @@ static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const 
     gp.goal = any_goal ? envs->goal : nullptr;
     gp.did_reset = out->did_reset;
     gp.sched = out->sched;
+    gp.desc = out->gather_desc
+                  ? reinterpret_cast<const int2 *>(out->gather_desc) + (size_t)(out->parity & 1) * envs->n_envs
+                  : nullptr;
     VN_REQUIRE(!any_goal || out->did_reset, "out: did_reset is required when goal planes are emitted");
     if (!any_goal && !any_obs) return VN_OK;
     return launch_gather(gp, variant, static_cast<cudaStream_t>(stream));
@@ -751,6 +782,7 @@ int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *i
     gp.obs_state = idx;
     gp.goal = nullptr;
     gp.did_reset = nullptr;
+    gp.desc = nullptr;
     gp.sched = nullptr;  // static unit assignment: no scratch in this signature
     gp.n = n;
     for (int pl = 0; pl < VN_MAX_PLANES; ++pl) {

@@ -20,6 +20,7 @@ RULE_NOOP_ACTION = 0x20
 RULE_AUTO_RESET = 0x40
 
 GATHER_AUTO, GATHER_LDG, GATHER_BULK = 0, 1, 2
+STEP_ACTIONS_READY = 0x01
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "steps", "truncations", "resets")
 
 _P = C.c_void_p
@@ -55,7 +56,7 @@ class StepOut(C.Structure):
     _fields_ = [("obs", _P * VN_MAX_PLANES), ("goal_obs", _P * VN_MAX_PLANES), ("reward", _P), ("done", _P),
                 ("truncated", _P), ("win", _P), ("did_reset", _P), ("last_action_reward", _P),
                 ("episode_return", _P), ("episode_length", _P), ("info_state", _P), ("obs_state", _P), ("stats", _P),
-                ("sched", _P), ("host_pack", _P)]
+                ("gather_desc", _P), ("parity", C.c_int32), ("flags", C.c_int32), ("sched", _P), ("host_pack", _P)]
 
 
 class Replay(C.Structure):

@@ -173,6 +173,7 @@ class GraphVecEnv:
             self.stats = torch.zeros(L.VN_N_STATS, dtype=torch.int64, device=self.device)
             self.actions_dev = i32()
             self._sched = torch.zeros(2, dtype=torch.int32, device=self.device)     # gather ticket counters
+            self._gather_desc = torch.zeros((2, max(n, 1), 2), dtype=torch.int32, device=self.device)
             self.obs_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
                                            dtype=torch.uint8, device=self.device) for p in self.obs_planes}
             self.goal_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
@@ -208,6 +209,7 @@ class GraphVecEnv:
         out.episode_return, out.episode_length = self.episode_return.data_ptr(), self.episode_length.data_ptr()
         out.info_state, out.obs_state, out.stats = self.info_state.data_ptr(), self.obs_state.data_ptr(), self.stats.data_ptr()
         out.sched = self._sched.data_ptr()
+        out.gather_desc = self._gather_desc.data_ptr()
         self._c_out = out
         # same outputs + the mapped pinned host mirror of the per-env scalars (host-actions path)
         out_h = L.StepOut()
@@ -235,6 +237,7 @@ class GraphVecEnv:
         self._pending = False
         self.closed = False
         self.kernel_launches = 0
+        self._calls = 0          # parity of the double-buffered gather descriptors
         # host path: pinned staging seen as numpy views + an event recorded after the scalar results
         # have landed on the host (the gather is still running when step() returns)
         self._actions_np = self._actions_host.numpy()
@@ -289,6 +292,7 @@ class GraphVecEnv:
         m = None
         if mask is not None:
             m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8)
+        self._tick(self._c_out, 0)
         with torch.cuda.device(self.device):
             L.check(self.lib.vn_env_reset(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
                                           C.byref(self._c_rules),
@@ -297,7 +301,15 @@ class GraphVecEnv:
         self.kernel_launches += 2
         return self._obs()
 
-    def step_async(self, actions):
+    def _tick(self, out, flags):
+        self._calls += 1
+        out.parity = self._calls & 1
+        out.flags = flags
+
+    def step_async(self, actions, actions_ready=False):
+        """``actions_ready=True`` promises that the action buffer was complete before the previous step's
+        gather was enqueued (pre-computed action streams, CUDA-graph replays): the scalar kernel of this step
+        then overlaps the previous gather (include/vn_b200.h VN_STEP_ACTIONS_READY)."""
         self._check_open()
         inj = C.byref(self._c_inject) if self._c_inject is not None else None
         if self.host_outputs and not (torch.is_tensor(actions) and actions.is_cuda):
@@ -308,6 +320,8 @@ class GraphVecEnv:
                 raise ValueError("expected %d actions, got %d" % (self.num_envs, a.size))
             self._actions_np[:] = a
             self._last_actions = self._actions_np
+            # host actions were written just now, after the previous ready_event: never produced by the gather
+            self._tick(self._c_out_host, L.STEP_ACTIONS_READY)
             with torch.cuda.device(self.device):
                 L.check(self.lib.vn_env_step_host(
                     C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs), C.byref(self._c_rules),
@@ -327,6 +341,7 @@ class GraphVecEnv:
         if a.numel() != self.num_envs:
             raise ValueError("expected %d actions, got %d" % (self.num_envs, a.numel()))
         self._last_actions = a
+        self._tick(self._c_out, L.STEP_ACTIONS_READY if actions_ready else 0)
         with torch.cuda.device(self.device):
             L.check(self.lib.vn_env_step(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
                                          C.byref(self._c_rules), inj, a.data_ptr(), C.byref(self._c_out), self.gather,
@@ -334,11 +349,11 @@ class GraphVecEnv:
         self.kernel_launches += 2
         self._pending = "device"
 
-    def step_enqueue(self, actions):
+    def step_enqueue(self, actions, actions_ready=False):
         """Device-resident loops: enqueue one vectorised step for CUDA int32 ``actions`` and return at once.
         Nothing is copied to the host; ``env.reward`` / ``env.done`` / the observation buffers hold the
-        results in stream order."""
-        self.step_async(actions)
+        results in stream order.  See step_async for ``actions_ready``."""
+        self.step_async(actions, actions_ready)
         self._pending = False
 
     def capture_steps(self, actions, after_step=None):
@@ -362,7 +377,8 @@ class GraphVecEnv:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             for t in range(actions.shape[0]):
-                self.step_enqueue(actions[t])
+                # the action tensor is complete before the graph is launched -> pipelined mode is safe
+                self.step_enqueue(actions[t], actions_ready=True)
                 if after_step is not None:
                     after_step(t)
         self._restore(saved)

@@ -48,6 +48,12 @@ extern "C" {
 #define VN_RULE_NOOP_ACTION 0x20          /* graph/env.py:118-120: action -1 is a no-op with reward 0.0 */
 #define VN_RULE_AUTO_RESET 0x40           /* baselines VecEnv worker: if done: ob = env.reset() */
 
+/* vn_step_out_t.flags */
+#define VN_STEP_ACTIONS_READY 0x01 /* the caller guarantees that the action buffer was complete before the PREVIOUS
+                                      call's gather was enqueued (e.g. a pre-computed action stream, or host actions
+                                      written after the previous ready_event): with gather_desc set, the scalar
+                                      kernel then overlaps the previous gather instead of waiting for it */
+
 /* vn_rules_t.goal_compare */
 #define VN_GOAL_FULL 0     /* gym_graph/graph.py:60-61 position and rotation; cached.py:83 index equality */
 #define VN_GOAL_POSITION 1 /* position only (state >> 2) */
@@ -140,6 +146,10 @@ typedef struct vn_step_out {
     int32_t *info_state;              /* [n_envs] info['state']: state after the move, before auto-reset */
     int32_t *obs_state;               /* [n_envs] state whose frames were gathered (scratch, required) */
     uint64_t *stats;                  /* [VN_N_STATS] running sums, see VN_STAT_* */
+    int32_t *gather_desc;             /* optional scratch [2][n_envs][2] int32: double-buffered (record, goal record or -1)
+                                         descriptors handed from the scalar half to the gather half of step `parity` */
+    int32_t parity;                   /* step counter (only bit 0 is used); the caller increments it every reset / step */
+    int32_t flags;                    /* VN_STEP_* */
     uint32_t *sched;                  /* optional scratch of 2 uint32, zeroed once by the caller: ticket counters of the
                                          gather's dynamic scheduler (self re-arming; one per env batch / stream) */
     uint8_t *host_pack;               /* optional MAPPED PINNED HOST block of 20 * n_envs bytes ("host pack") that the

@@ -678,3 +678,32 @@ def test_c1_maze_graph_frames_a2c_n5_end_to_end():
     assert total_done > 5
     # the rendered frames themselves: free = white, walls = black, agent red, goal green (before the resize)
     assert frames.shape == (scene.n_cells, 84, 84, 3) and frames.max() == 255
+
+
+def test_pipelined_mode_equals_serial_mode():
+    """VN_STEP_ACTIONS_READY: the scalar kernel of step t+1 overlaps the gather of step t (double-buffered
+    gather descriptors).  Results must not change - checked with frequent resets so that goal rows are rewritten."""
+    import torch
+    scene = H.scenes.make_thor_scene(200, (20, 25), seed=2, n_goals=4, planes=("rgb", "depth", "segmentation"))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    N, S = 2048, 150
+    a = vn.GraphVecEnv(world, N, seed=6, max_episode_steps=4, host_outputs=False)
+    b = vn.GraphVecEnv(world, N, seed=6, max_episode_steps=4, host_outputs=False, device_world=a.dw)
+    a.set_complexity(0.3)
+    a.reset()
+    b.reset()
+    acts = torch.randint(0, 4, (S, N), device="cuda", dtype=torch.int32)
+    torch.cuda.synchronize()
+    for t in range(S):
+        a.step_enqueue(acts[t])
+        b.step_enqueue(acts[t], actions_ready=True)
+        if t % 7 == 0 or t == S - 1:
+            torch.cuda.synchronize()
+            assert torch.equal(a._pack, b._pack) and torch.equal(a.state, b.state) and torch.equal(a.lar, b.lar)
+            for x, y in zip(list(a.obs_buf.values()) + list(a.goal_buf.values()),
+                            list(b.obs_buf.values()) + list(b.goal_buf.values())):
+                assert torch.equal(x, y)
+            s = b.state.long()
+            assert torch.equal(b.obs_buf["rgb"], b.dw.plane_view("rgb")[s])
+            assert torch.equal(b.goal_buf["segmentation"], b.dw.plane_view("segmentation")[b.goal.long()])
+    assert a.episode_stats() == b.episode_stats() and a.episode_stats()["episodes"] > N
