@@ -7,6 +7,7 @@
 //   K2 vn_gather_*      one CTA per env: copies the env's observation planes (and, only if the env just
 //                       reset, its goal planes) from the HBM store into the contiguous policy batch.
 //                       >99.9 % of the bytes; HBM-bound; two variants (LDG.128 registers / bulk async copy).
+#include <atomic>
 #include <cstdlib>
 #include <string>
 
@@ -15,6 +16,7 @@
 namespace vn {
 
 static thread_local std::string g_error;
+static std::atomic<long long> g_launches{0};  // statistics only: kernels enqueued by this library, all threads
 
 void set_error(const char *fmt, ...) {
     char buf[512];
@@ -26,6 +28,7 @@ void set_error(const char *fmt, ...) {
 }
 
 int32_t check_launch(const char *what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -46,6 +49,7 @@ struct StepParams {
     const int32_t *actions;  // NULL in reset mode
     const uint8_t *mask;     // reset mode only
     int32_t *actions_copy;   // optional device copy of the actions (host-actions path)
+    int32_t skip_rows;       // VN_STEP_SKIP_UNCHANGED is set AND the gather half can honour it (descriptors / fused)
 };
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
@@ -58,6 +62,178 @@ __device__ __forceinline__ void pdl_wait_then_release() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Per-env statistics contributions of one step (summed over a warp, or added directly by the fused kernel).
+struct EnvStats {
+    uint32_t episodes = 0, len = 0, succ = 0, coll = 0, steps = 0, trunc = 0, resets = 0, skipped = 0;
+    float ret = 0.f;
+};
+
+// One env, one step (or reset): everything the reference does between receiving the action and calling
+// observe().  Returns the store record whose frames must be in the batch (rec; -1 = the batch row already
+// holds it, VN_STEP_SKIP_UNCHANGED) and the goal record to (re)write (grec; -1 = none).
+template <bool kReset>
+__device__ __forceinline__ void step_env(const StepParams &p, const int i, EnvStats &st, int &rec, int &grec) {
+    const int flags = p.rules.flags;
+    int s = p.env.state[i];
+    int g = p.env.goal[i];
+    float ep_ret = p.env.ep_return[i];
+    int ep_len = p.env.ep_length[i];
+    int elapsed = p.env.elapsed[i];
+    // record gathered by the previous call (the scratch is persistent): only read when rows may be skipped
+    const bool may_skip = !kReset && p.skip_rows;
+    const int prev_obs = may_skip ? p.out.obs_state[i] : -1;
+    int obs_s = s;
+    bool do_reset;
+
+    if (kReset) {
+        do_reset = p.mask ? (p.mask[i] != 0) : true;
+    } else {
+        const int a = p.actions[i];  // may live in mapped pinned host memory (vn_env_step_host)
+        if (p.actions_copy) p.actions_copy[i] = a;
+        const int s_old = s;
+        bool terminal = false, collided = false;
+        float r;
+        if ((flags & VN_RULE_NOOP_ACTION) && a < 0) {
+            r = 0.0f;  // graph/env.py:118-120: latest observation, 0.0, not done
+        } else {
+            // graph.util.step + is_valid_state folded into one table lookup; an action outside
+            // [0, 4) has no transition in the reference (step() returns None) and is a collision here
+            const int nxt = (a >= 0 && a < 4) ? __ldg(p.tab.adj + (size_t)s * 4 + a) : -1;
+            collided = nxt < 0;
+            if (!collided) s = nxt;
+            bool at_goal;
+            if (p.rules.goal_compare == VN_GOAL_FULL)
+                at_goal = (s == g);
+            else if (p.rules.goal_compare == VN_GOAL_POSITION)
+                at_goal = ((s >> 2) == (g >> 2));
+            else
+                at_goal = false;
+            terminal = at_goal && !(collided && (flags & VN_RULE_COLLISION_SKIPS_GOAL));
+            r = (flags & VN_RULE_NEG_STEP_REWARD) ? -p.rules.reward_step : p.rules.reward_step;
+            if (terminal) r = p.rules.reward_goal;
+            if (collided) r = p.rules.reward_collision;
+        }
+        bool done = terminal, trunc = false, at_limit = false;
+        elapsed += 1;
+        ep_ret += r;
+        ep_len += 1;
+        if (p.rules.max_episode_steps > 0 && elapsed >= p.rules.max_episode_steps) {
+            at_limit = true;  // gym TimeLimit: info['TimeLimit.truncated'] = not done; done = True
+            trunc = !done;
+            done = true;
+        }
+        do_reset = done && (flags & VN_RULE_AUTO_RESET);
+        obs_s = (terminal && (flags & VN_RULE_TERM_PREV_OBS) && !do_reset) ? s_old : s;
+
+        const uint8_t trunc_code = at_limit ? (trunc ? 1 : 2) : 0;
+        if (p.out.reward) p.out.reward[i] = r;
+        if (p.out.done) p.out.done[i] = done;
+        if (p.out.truncated) p.out.truncated[i] = trunc_code;
+        if (p.out.win) p.out.win[i] = terminal;
+        if (p.out.info_state) p.out.info_state[i] = s;
+        if (p.out.host_pack) {
+            // mirror of the per-env scalars written straight into mapped pinned host memory
+            // (layout: vn_b200.h "host pack"): the host reads them after the event that follows
+            // this kernel, with no copy-engine operation on the critical path
+            uint8_t *hp = p.out.host_pack;
+            const size_t n = (size_t)p.env.n_envs;
+            reinterpret_cast<float *>(hp)[i] = r;
+            reinterpret_cast<int32_t *>(hp + 12 * n)[i] = s;
+            hp[16 * n + i] = done;
+            hp[17 * n + i] = trunc_code;
+            hp[18 * n + i] = terminal;
+            hp[19 * n + i] = do_reset;
+            if (done) {
+                reinterpret_cast<float *>(hp + 4 * n)[i] = ep_ret;
+                reinterpret_cast<int32_t *>(hp + 8 * n)[i] = ep_len;
+            }
+        }
+        if (done) {
+            if (p.out.episode_return) p.out.episode_return[i] = ep_ret;
+            if (p.out.episode_length) p.out.episode_length[i] = ep_len;
+            st.episodes = 1;
+            st.len = (uint32_t)ep_len;
+            st.ret = ep_ret;
+            st.succ = terminal;
+            st.trunc = trunc;
+        }
+        st.coll = collided;
+        st.steps = 1;
+        if (p.out.last_action_reward) {
+            // UnrealEnvBaseWrapper: one_hot(action) ++ [clip(r, -1, 1)]; zeros right after a reset
+            float *lar = p.out.last_action_reward + (size_t)i * (p.rules.n_actions + 1);
+            for (int k = 0; k < p.rules.n_actions; ++k) lar[k] = (!do_reset && k == a) ? 1.0f : 0.0f;
+            lar[p.rules.n_actions] = do_reset ? 0.0f : fminf(fmaxf(r, -1.0f), 1.0f);
+        }
+    }
+
+    if (do_reset) {
+        const uint32_t e = p.env.epoch[i];
+        const int tlo = p.env.task_lo[i];
+        int t, start;
+        if (p.inj.start) {
+            const uint32_t k = e < (uint32_t)p.inj.stride ? e : (uint32_t)p.inj.stride - 1;
+            const size_t at = (size_t)i * p.inj.stride + k;
+            t = tlo + (p.inj.task ? p.inj.task[at] : 0);
+            start = p.inj.start[at];
+        } else {
+            const Philox4 d = philox4x32_10((uint32_t)(p.env.env_id_base + i), e, 0u, 0u, (uint32_t)p.rules.seed,
+                                            (uint32_t)(p.rules.seed >> 32));
+            t = tlo + (int)__umulhi(d.v[0], (uint32_t)p.env.task_cnt[i]);
+            const int lo = __ldg(p.tab.task_cand_off + t);
+            const int cnt = __ldg(p.tab.task_cand_off + t + 1) - lo;
+            const int pre = __ldg(p.tab.task_prefix + t);
+            int idx;
+            if ((flags & VN_RULE_TWO_LEVEL) && pre < cnt && d.v[1] >= 3865470566u) {
+                idx = pre + (int)__umulhi(d.v[2], (uint32_t)(cnt - pre));  // the 0.1 bucket, util.py:112-113
+            } else {
+                idx = (int)__umulhi(d.v[2], (uint32_t)pre);
+            }
+            start = __ldg(p.tab.cand_state + lo + idx);
+        }
+        s = start;
+        g = __ldg(p.tab.task_goal + t);
+        p.env.task[i] = t;
+        p.env.goal[i] = g;
+        p.env.epoch[i] = e + 1;
+        elapsed = 0;
+        ep_ret = 0.f;
+        ep_len = 0;
+        obs_s = s;
+        st.resets = 1;
+        if (kReset && p.out.last_action_reward) {
+            float *lar = p.out.last_action_reward + (size_t)i * (p.rules.n_actions + 1);
+            for (int k = 0; k <= p.rules.n_actions; ++k) lar[k] = 0.0f;
+        }
+    }
+    p.env.state[i] = s;
+    p.env.elapsed[i] = elapsed;
+    p.env.ep_return[i] = ep_ret;
+    p.env.ep_length[i] = ep_len;
+    p.out.obs_state[i] = obs_s;
+    if (p.out.did_reset) p.out.did_reset[i] = do_reset;
+    // the batch row of an env whose record did not change (collision, no-op) already holds the right frames
+    const bool same = may_skip && obs_s == prev_obs;
+    st.skipped = same;
+    rec = same ? -1 : obs_s;
+    grec = do_reset ? g : -1;
+}
+
+__device__ __forceinline__ void add_stats(uint64_t *stats, const EnvStats &s) {
+    unsigned long long *st = reinterpret_cast<unsigned long long *>(stats);
+    if (s.episodes) {
+        atomicAdd(st + VN_STAT_EPISODES, (unsigned long long)s.episodes);
+        atomicAdd(reinterpret_cast<double *>(st + VN_STAT_RETURN_SUM), (double)s.ret);
+        atomicAdd(st + VN_STAT_LENGTH_SUM, (unsigned long long)s.len);
+        if (s.succ) atomicAdd(st + VN_STAT_SUCCESSES, (unsigned long long)s.succ);
+        if (s.trunc) atomicAdd(st + VN_STAT_TRUNCATIONS, (unsigned long long)s.trunc);
+    }
+    if (s.coll) atomicAdd(st + VN_STAT_COLLISIONS, (unsigned long long)s.coll);
+    if (s.steps) atomicAdd(st + VN_STAT_STEPS, (unsigned long long)s.steps);
+    if (s.resets) atomicAdd(st + VN_STAT_RESETS, (unsigned long long)s.resets);
+    if (s.skipped) atomicAdd(st + VN_STAT_ROWS_SKIPPED, (unsigned long long)s.skipped);
+}
+
 template <bool kReset>
 __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
     // Pipelined mode (VN_STEP_ACTIONS_READY + gather_desc): nothing this kernel reads was produced by its
@@ -68,171 +244,30 @@ __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
     if (!defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int flags = p.rules.flags;
-    uint32_t st_episodes = 0, st_len = 0, st_succ = 0, st_coll = 0, st_steps = 0, st_trunc = 0, st_resets = 0;
-    float st_ret = 0.f;
-
+    EnvStats st;
     if (i < p.env.n_envs) {
-        int s = p.env.state[i];
-        int g = p.env.goal[i];
-        float ep_ret = p.env.ep_return[i];
-        int ep_len = p.env.ep_length[i];
-        int elapsed = p.env.elapsed[i];
-        int obs_s = s;
-        bool do_reset;
-
-        if (kReset) {
-            do_reset = p.mask ? (p.mask[i] != 0) : true;
-        } else {
-            const int a = p.actions[i];  // may live in mapped pinned host memory (vn_env_step_host)
-            if (p.actions_copy) p.actions_copy[i] = a;
-            const int s_old = s;
-            bool terminal = false, collided = false;
-            float r;
-            if ((flags & VN_RULE_NOOP_ACTION) && a < 0) {
-                r = 0.0f;  // graph/env.py:118-120: latest observation, 0.0, not done
-            } else {
-                // graph.util.step + is_valid_state folded into one table lookup; an action outside
-                // [0, 4) has no transition in the reference (step() returns None) and is a collision here
-                const int nxt = (a >= 0 && a < 4) ? __ldg(p.tab.adj + (size_t)s * 4 + a) : -1;
-                collided = nxt < 0;
-                if (!collided) s = nxt;
-                bool at_goal;
-                if (p.rules.goal_compare == VN_GOAL_FULL)
-                    at_goal = (s == g);
-                else if (p.rules.goal_compare == VN_GOAL_POSITION)
-                    at_goal = ((s >> 2) == (g >> 2));
-                else
-                    at_goal = false;
-                terminal = at_goal && !(collided && (flags & VN_RULE_COLLISION_SKIPS_GOAL));
-                r = (flags & VN_RULE_NEG_STEP_REWARD) ? -p.rules.reward_step : p.rules.reward_step;
-                if (terminal) r = p.rules.reward_goal;
-                if (collided) r = p.rules.reward_collision;
-            }
-            bool done = terminal, trunc = false, at_limit = false;
-            elapsed += 1;
-            ep_ret += r;
-            ep_len += 1;
-            if (p.rules.max_episode_steps > 0 && elapsed >= p.rules.max_episode_steps) {
-                at_limit = true;  // gym TimeLimit: info['TimeLimit.truncated'] = not done; done = True
-                trunc = !done;
-                done = true;
-            }
-            do_reset = done && (flags & VN_RULE_AUTO_RESET);
-            obs_s = (terminal && (flags & VN_RULE_TERM_PREV_OBS) && !do_reset) ? s_old : s;
-
-            const uint8_t trunc_code = at_limit ? (trunc ? 1 : 2) : 0;
-            if (p.out.reward) p.out.reward[i] = r;
-            if (p.out.done) p.out.done[i] = done;
-            if (p.out.truncated) p.out.truncated[i] = trunc_code;
-            if (p.out.win) p.out.win[i] = terminal;
-            if (p.out.info_state) p.out.info_state[i] = s;
-            if (p.out.host_pack) {
-                // mirror of the per-env scalars written straight into mapped pinned host memory
-                // (layout: vn_b200.h "host pack"): the host reads them after the event that follows
-                // this kernel, with no copy-engine operation on the critical path
-                uint8_t *hp = p.out.host_pack;
-                const size_t n = (size_t)p.env.n_envs;
-                reinterpret_cast<float *>(hp)[i] = r;
-                reinterpret_cast<int32_t *>(hp + 12 * n)[i] = s;
-                hp[16 * n + i] = done;
-                hp[17 * n + i] = trunc_code;
-                hp[18 * n + i] = terminal;
-                hp[19 * n + i] = do_reset;
-                if (done) {
-                    reinterpret_cast<float *>(hp + 4 * n)[i] = ep_ret;
-                    reinterpret_cast<int32_t *>(hp + 8 * n)[i] = ep_len;
-                }
-            }
-            if (done) {
-                if (p.out.episode_return) p.out.episode_return[i] = ep_ret;
-                if (p.out.episode_length) p.out.episode_length[i] = ep_len;
-                st_episodes = 1;
-                st_len = (uint32_t)ep_len;
-                st_ret = ep_ret;
-                st_succ = terminal;
-                st_trunc = trunc;
-            }
-            st_coll = collided;
-            st_steps = 1;
-            if (p.out.last_action_reward) {
-                // UnrealEnvBaseWrapper: one_hot(action) ++ [clip(r, -1, 1)]; zeros right after a reset
-                float *lar = p.out.last_action_reward + (size_t)i * (p.rules.n_actions + 1);
-                for (int k = 0; k < p.rules.n_actions; ++k) lar[k] = (!do_reset && k == a) ? 1.0f : 0.0f;
-                lar[p.rules.n_actions] = do_reset ? 0.0f : fminf(fmaxf(r, -1.0f), 1.0f);
-            }
-        }
-
-        if (do_reset) {
-            const uint32_t e = p.env.epoch[i];
-            const int tlo = p.env.task_lo[i];
-            int t, start;
-            if (p.inj.start) {
-                const uint32_t k = e < (uint32_t)p.inj.stride ? e : (uint32_t)p.inj.stride - 1;
-                const size_t at = (size_t)i * p.inj.stride + k;
-                t = tlo + (p.inj.task ? p.inj.task[at] : 0);
-                start = p.inj.start[at];
-            } else {
-                const Philox4 d = philox4x32_10((uint32_t)(p.env.env_id_base + i), e, 0u, 0u, (uint32_t)p.rules.seed,
-                                                (uint32_t)(p.rules.seed >> 32));
-                t = tlo + (int)__umulhi(d.v[0], (uint32_t)p.env.task_cnt[i]);
-                const int lo = __ldg(p.tab.task_cand_off + t);
-                const int cnt = __ldg(p.tab.task_cand_off + t + 1) - lo;
-                const int pre = __ldg(p.tab.task_prefix + t);
-                int idx;
-                if ((flags & VN_RULE_TWO_LEVEL) && pre < cnt && d.v[1] >= 3865470566u) {
-                    idx = pre + (int)__umulhi(d.v[2], (uint32_t)(cnt - pre));  // the 0.1 bucket, util.py:112-113
-                } else {
-                    idx = (int)__umulhi(d.v[2], (uint32_t)pre);
-                }
-                start = __ldg(p.tab.cand_state + lo + idx);
-            }
-            s = start;
-            g = __ldg(p.tab.task_goal + t);
-            p.env.task[i] = t;
-            p.env.goal[i] = g;
-            p.env.epoch[i] = e + 1;
-            elapsed = 0;
-            ep_ret = 0.f;
-            ep_len = 0;
-            obs_s = s;
-            st_resets = 1;
-            if (kReset && p.out.last_action_reward) {
-                float *lar = p.out.last_action_reward + (size_t)i * (p.rules.n_actions + 1);
-                for (int k = 0; k <= p.rules.n_actions; ++k) lar[k] = 0.0f;
-            }
-        }
-        p.env.state[i] = s;
-        p.env.elapsed[i] = elapsed;
-        p.env.ep_return[i] = ep_ret;
-        p.env.ep_length[i] = ep_len;
-        p.out.obs_state[i] = obs_s;
-        if (p.out.did_reset) p.out.did_reset[i] = do_reset;
-        if (p.out.gather_desc)  // what the gather of THIS step needs: record to copy, goal record (or -1)
+        int rec, grec;
+        step_env<kReset>(p, i, st, rec, grec);
+        if (p.out.gather_desc)  // what the gather of THIS step needs: record to copy (or -1), goal record (or -1)
             reinterpret_cast<int2 *>(p.out.gather_desc)[(size_t)(p.out.parity & 1) * p.env.n_envs + i] =
-                make_int2(obs_s, do_reset ? g : -1);
+                make_int2(rec, grec);
     }
 
     if (p.out.stats) {
         // warp-aggregated statistics: one atomic per counter per warp
-        const uint32_t e = warp_sum(st_episodes), l = warp_sum(st_len), su = warp_sum(st_succ), c = warp_sum(st_coll),
-                       n = warp_sum(st_steps), tr = warp_sum(st_trunc), rs = warp_sum(st_resets);
-        float ret = st_ret;
+        EnvStats w;
+        w.episodes = warp_sum(st.episodes);
+        w.len = warp_sum(st.len);
+        w.succ = warp_sum(st.succ);
+        w.coll = warp_sum(st.coll);
+        w.steps = warp_sum(st.steps);
+        w.trunc = warp_sum(st.trunc);
+        w.resets = warp_sum(st.resets);
+        w.skipped = warp_sum(st.skipped);
+        w.ret = st.ret;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ret += __shfl_xor_sync(0xffffffffu, ret, o);
-        if ((threadIdx.x & 31) == 0) {
-            unsigned long long *st = reinterpret_cast<unsigned long long *>(p.out.stats);
-            if (e) {
-                atomicAdd(st + VN_STAT_EPISODES, (unsigned long long)e);
-                atomicAdd(reinterpret_cast<double *>(st + VN_STAT_RETURN_SUM), (double)ret);
-                atomicAdd(st + VN_STAT_LENGTH_SUM, (unsigned long long)l);
-                if (su) atomicAdd(st + VN_STAT_SUCCESSES, (unsigned long long)su);
-                if (tr) atomicAdd(st + VN_STAT_TRUNCATIONS, (unsigned long long)tr);
-            }
-            if (c) atomicAdd(st + VN_STAT_COLLISIONS, (unsigned long long)c);
-            if (n) atomicAdd(st + VN_STAT_STEPS, (unsigned long long)n);
-            if (rs) atomicAdd(st + VN_STAT_RESETS, (unsigned long long)rs);
-        }
+        for (int o = 16; o > 0; o >>= 1) w.ret += __shfl_xor_sync(0xffffffffu, w.ret, o);
+        if ((threadIdx.x & 31) == 0) add_stats(p.out.stats, w);
     }
     if (defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
@@ -290,13 +325,15 @@ __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherPar
             rec = __ldg(p.obs_state + env);
             if (p.goal && (!p.did_reset || __ldg(p.did_reset + env))) grec = __ldg(p.goal + env);
         }
-        const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
+        if (rec >= 0) {  // rec < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
+            const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
 #pragma unroll 1
-        for (int pl = 0; pl < p.store.n_planes; ++pl) {
-            if (p.obs[pl])
-                copy_segment16<kThreads, kUnroll>(src + p.store.plane_off[pl],
-                                                  p.obs[pl] + (size_t)env * p.store.plane_bytes[pl],
-                                                  p.store.plane_bytes[pl] >> 4);
+            for (int pl = 0; pl < p.store.n_planes; ++pl) {
+                if (p.obs[pl])
+                    copy_segment16<kThreads, kUnroll>(src + p.store.plane_off[pl],
+                                                      p.obs[pl] + (size_t)env * p.store.plane_bytes[pl],
+                                                      p.store.plane_bytes[pl] >> 4);
+            }
         }
         if (grec >= 0) {
             const uint8_t *gsrc = p.store.base + (size_t)grec * p.store.state_pitch;
@@ -405,8 +442,10 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
             rec = p.obs_state[env];
             if (p.goal && (!p.did_reset || p.did_reset[env])) grec = p.goal[env];
         }
-        const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
-        bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, &bar, parity, hints);
+        if (rec >= 0) {  // rec < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
+            const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
+            bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, &bar, parity, hints);
+        }
         if (grec >= 0) {
             const uint8_t *gsrc = p.store.base + (size_t)grec * p.store.state_pitch;
             bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints);
@@ -423,6 +462,75 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
             __threadfence();
         }
     }
+}
+
+// ---- fused single launch for small batches ----------------------------------------------------------
+// A batch of at most one env per SM (C1: 16 envs) is bound by launch latency and by the chain of dependent
+// memory round trips, not by bandwidth, so ONE kernel does both halves: one CTA per env, thread 0 steps the
+// env, then lane 0 of warp w moves slice w of every plane - the observation record and, after a reset, the goal
+// record, both in flight at once - with bulk async copies through a record-shaped region of shared memory.
+constexpr int kFusedWarps = 4;
+
+template <bool kReset>
+__global__ void __launch_bounds__(kFusedWarps * 32) vn_step_fused_kernel(const StepParams sp, const GatherParams gp) {
+    extern __shared__ __align__(128) uint8_t smem[];  // [state_pitch] observation record (+ [state_pitch] goal record)
+    __shared__ uint64_t bar[kFusedWarps];
+    __shared__ int s_rec, s_grec;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < kFusedWarps) mbar_init(&bar[threadIdx.x], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int env = blockIdx.x;
+    if (threadIdx.x == 0) {
+        EnvStats st;
+        int rec, grec;
+        step_env<kReset>(sp, env, st, rec, grec);
+        if (sp.out.stats) add_stats(sp.out.stats, st);
+        s_rec = rec;
+        s_grec = gp.goal ? grec : -1;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) != 0) return;
+    const vn_store_t &S = gp.store;
+    const uint8_t *src[2] = {s_rec >= 0 ? S.base + (size_t)s_rec * S.state_pitch : nullptr,
+                             s_grec >= 0 ? S.base + (size_t)s_grec * S.state_pitch : nullptr};
+    uint8_t *const *dst[2] = {gp.obs, gp.goal_obs};
+    uint32_t total = 0;
+    for (int k = 0; k < 2; ++k)
+        if (src[k])
+            for (int pl = 0; pl < S.n_planes; ++pl)
+                if (dst[k][pl]) {
+                    const int n16 = S.plane_bytes[pl] >> 4, per = (n16 + kFusedWarps - 1) / kFusedWarps;
+                    const int lo = min(warp * per, n16), hi = min(lo + per, n16);
+                    total += (uint32_t)(hi - lo) << 4;
+                }
+    if (total == 0) return;
+    mbar_expect_tx(&bar[warp], total);
+    for (int k = 0; k < 2; ++k)
+        if (src[k])
+            for (int pl = 0; pl < S.n_planes; ++pl)
+                if (dst[k][pl]) {
+                    const int n16 = S.plane_bytes[pl] >> 4, per = (n16 + kFusedWarps - 1) / kFusedWarps;
+                    const int lo = min(warp * per, n16), hi = min(lo + per, n16);
+                    if (hi > lo)
+                        bulk_g2s(smem + (size_t)k * S.state_pitch + S.plane_off[pl] + ((size_t)lo << 4),
+                                 src[k] + S.plane_off[pl] + ((size_t)lo << 4), (uint32_t)(hi - lo) << 4, &bar[warp]);
+                }
+    mbar_wait(&bar[warp], 0);
+    for (int k = 0; k < 2; ++k)
+        if (src[k])
+            for (int pl = 0; pl < S.n_planes; ++pl)
+                if (dst[k][pl]) {
+                    const int n16 = S.plane_bytes[pl] >> 4, per = (n16 + kFusedWarps - 1) / kFusedWarps;
+                    const int lo = min(warp * per, n16), hi = min(lo + per, n16);
+                    if (hi > lo)
+                        bulk_s2g(dst[k][pl] + (size_t)env * S.plane_bytes[pl] + ((size_t)lo << 4),
+                                 smem + (size_t)k * S.state_pitch + S.plane_off[pl] + ((size_t)lo << 4),
+                                 (uint32_t)(hi - lo) << 4);
+                }
+    bulk_commit();
+    bulk_wait_read<0>();
 }
 
 // =====================================================================================================
@@ -515,6 +623,7 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         VN_REQUIRE(!gp.goal_obs[pl] || (reinterpret_cast<uintptr_t>(gp.goal_obs[pl]) & 15) == 0,
                    "gather: goal_obs[%d] must be 16-byte aligned", pl);
     }
+    if (variant == VN_GATHER_FUSED) variant = VN_GATHER_BULK;  // no scalar half here: the fused launch does not apply
     if (variant == VN_GATHER_AUTO) {
         // measured on B200 (profiles/): the bulk-copy variant reaches 94 % of the copy peak, LDG.128 86 %
         int per_env = 0;
@@ -563,25 +672,20 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
     return VN_EINVAL;
 }
 
-static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
-                          const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask,
-                          const vn_step_out_t *out, void *stream, bool reset, int32_t *actions_copy = nullptr) {
-    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
-    if (envs->n_envs == 0) return VN_OK;  // an empty shard (more ranks than envs): nothing to do, nothing to check
+static int32_t make_step_params(StepParams &sp, const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
+                                const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask,
+                                const vn_step_out_t *out, bool reset, int32_t *actions_copy) {
     VN_REQUIRE(tab && tab->adj && tab->task_goal && tab->task_cand_off && tab->task_prefix && tab->cand_state,
                "tables: null pointer");
     VN_REQUIRE(tab->n_tasks > 0, "tables: n_tasks=%d", tab->n_tasks);
     VN_REQUIRE(envs->state && envs->goal && envs->task && envs->elapsed && envs->epoch && envs->ep_return &&
                    envs->ep_length && envs->task_lo && envs->task_cnt,
                "envs: null pointer");
-    VN_REQUIRE(envs->n_envs >= 0, "envs: n_envs=%d", envs->n_envs);
     VN_REQUIRE(rules && rules->n_actions >= 1 && rules->n_actions <= 16, "rules: n_actions");
     VN_REQUIRE(rules->goal_compare >= 0 && rules->goal_compare <= 2, "rules: goal_compare=%d", rules->goal_compare);
     VN_REQUIRE(out && out->obs_state, "out: obs_state scratch is required");
     VN_REQUIRE(reset || actions, "step: actions is null");
     VN_REQUIRE(!inj || !inj->start || inj->stride > 0, "inject: stride=%d", inj ? inj->stride : 0);
-    if (envs->n_envs == 0) return VN_OK;
-    StepParams sp;
     sp.tab = *tab;
     sp.env = *envs;
     sp.rules = *rules;
@@ -593,6 +697,19 @@ static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const v
     sp.actions = actions;
     sp.mask = mask;
     sp.actions_copy = actions_copy;
+    // rows can only be skipped when the gather half learns about it through the descriptors
+    sp.skip_rows = (out->flags & VN_STEP_SKIP_UNCHANGED) && out->gather_desc != nullptr;
+    return VN_OK;
+}
+
+static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
+                          const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask,
+                          const vn_step_out_t *out, void *stream, bool reset, int32_t *actions_copy = nullptr) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    if (envs->n_envs == 0) return VN_OK;  // an empty shard (more ranks than envs): nothing to do, nothing to check
+    StepParams sp;
+    int32_t rc = make_step_params(sp, tab, envs, rules, inj, actions, mask, out, reset, actions_copy);
+    if (rc) return rc;
     const int threads = 128;
     const int blocks = (envs->n_envs + threads - 1) / threads;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -603,15 +720,13 @@ static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const v
     return check_launch("vn_step_kernel");
 }
 
-static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant,
-                          void *stream) {
-    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
-    if (envs->n_envs == 0) return VN_OK;
+// *any = whether there is anything to gather at all
+static int32_t make_gather_params(GatherParams &gp, const vn_store_t *store, const vn_envs_t *envs,
+                                  const vn_step_out_t *out, bool *any) {
     int32_t rc = validate_store(store);
     if (rc) return rc;
     VN_REQUIRE(envs->goal, "envs: null pointer");
     VN_REQUIRE(out && out->obs_state, "out: obs_state is required");
-    GatherParams gp;
     gp.store = *store;
     gp.obs_state = out->obs_state;
     gp.n = envs->n_envs;
@@ -629,8 +744,80 @@ static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const 
                   ? reinterpret_cast<const int2 *>(out->gather_desc) + (size_t)(out->parity & 1) * envs->n_envs
                   : nullptr;
     VN_REQUIRE(!any_goal || out->did_reset, "out: did_reset is required when goal planes are emitted");
-    if (!any_goal && !any_obs) return VN_OK;
+    *any = any_goal || any_obs;
+    return VN_OK;
+}
+
+static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant,
+                          void *stream) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    if (envs->n_envs == 0) return VN_OK;
+    GatherParams gp;
+    bool any = false;
+    int32_t rc = make_gather_params(gp, store, envs, out, &any);
+    if (rc) return rc;
+    if (!any) return VN_OK;
+    if (variant == VN_GATHER_FUSED) variant = VN_GATHER_BULK;  // the halves were requested separately
     return launch_gather(gp, variant, static_cast<cudaStream_t>(stream));
+}
+
+// Whether vn_env_step / vn_env_reset / vn_env_step_host run as the single fused launch: on request
+// (VN_GATHER_FUSED), or by default (VN_GATHER_AUTO) for batches of at most one env per SM.
+static int32_t fused_smem_bytes(const vn_store_t *store, const vn_step_out_t *out) {
+    bool any_goal = false;
+    for (int pl = 0; pl < store->n_planes; ++pl) any_goal |= out->goal_obs[pl] != nullptr;
+    const int64_t smem = store->state_pitch * (any_goal ? 2 : 1);
+    return smem <= 200 * 1024 ? (int32_t)smem : -1;
+}
+
+static int32_t run_fused(const vn_store_t *store, const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
+                         const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask, const vn_step_out_t *out,
+                         void *stream, bool reset, int32_t *actions_copy, int32_t smem) {
+    StepParams sp;
+    int32_t rc = make_step_params(sp, tab, envs, rules, inj, actions, mask, out, reset, actions_copy);
+    if (rc) return rc;
+    sp.skip_rows = (out->flags & VN_STEP_SKIP_UNCHANGED) != 0;  // the record index never leaves the kernel
+    GatherParams gp;
+    bool any = false;
+    rc = make_gather_params(gp, store, envs, out, &any);
+    if (rc) return rc;
+    for (int pl = 0; pl < gp.store.n_planes; ++pl) {
+        VN_REQUIRE(!gp.obs[pl] || (reinterpret_cast<uintptr_t>(gp.obs[pl]) & 15) == 0,
+                   "gather: obs[%d] must be 16-byte aligned", pl);
+        VN_REQUIRE(!gp.goal_obs[pl] || (reinterpret_cast<uintptr_t>(gp.goal_obs[pl]) & 15) == 0,
+                   "gather: goal_obs[%d] must be 16-byte aligned", pl);
+    }
+    static int configured[kMaxDevices][2] = {{0, 0}};  // the attribute is per device and per instantiation
+    const int dev = current_device();
+    if (smem > configured[dev][reset]) {
+        if (reset)
+            cudaFuncSetAttribute(vn_step_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        else
+            cudaFuncSetAttribute(vn_step_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured[dev][reset] = smem;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (reset)
+        launch_pdl(vn_step_fused_kernel<true>, dim3(envs->n_envs), dim3(kFusedWarps * 32), (size_t)smem, st, sp, gp);
+    else
+        launch_pdl(vn_step_fused_kernel<false>, dim3(envs->n_envs), dim3(kFusedWarps * 32), (size_t)smem, st, sp, gp);
+    return check_launch("vn_step_fused_kernel");
+}
+
+// -1: error already set; 0: two launches; > 0: fused, shared memory bytes
+static int32_t choose_fused(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant) {
+    if (variant != VN_GATHER_FUSED && !(variant == VN_GATHER_AUTO && envs->n_envs <= sm_count())) return 0;
+    static const bool off = getenv("VN_NO_FUSED") && atoi(getenv("VN_NO_FUSED"));
+    if (off && variant == VN_GATHER_AUTO) return 0;
+    if (!out) return 0;  // reported by the parameter checks
+    const int32_t smem = fused_smem_bytes(store, out);
+    if (smem < 0) {
+        if (variant == VN_GATHER_AUTO) return 0;
+        set_error("gather(fused): a %lld-byte record (x2 with goal planes) exceeds shared memory",
+                  (long long)store->state_pitch);
+        return -1;
+    }
+    return smem;
 }
 
 static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
@@ -640,6 +827,9 @@ static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const v
     if (envs->n_envs == 0) return VN_OK;
     int32_t rc = validate_store(store);  // fail before anything is enqueued
     if (rc) return rc;
+    const int32_t fused = choose_fused(store, envs, out, variant);
+    if (fused < 0) return VN_EINVAL;
+    if (fused > 0) return run_fused(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, fused);
     rc = run_scalar(tab, envs, rules, inj, actions, mask, out, stream, reset);
     if (rc) return rc;
     return run_gather(store, envs, out, variant, stream);
@@ -667,6 +857,7 @@ int32_t vn_abi_struct_size(int32_t which) {
     }
 }
 const char *vn_last_error(void) { return vn::g_error.c_str(); }
+int64_t vn_launch_count(void) { return (int64_t)vn::g_launches.load(std::memory_order_relaxed); }
 
 int32_t vn_fill_store(const vn_store_t *store, int32_t record0, int32_t n_records, uint64_t seed, int32_t scene,
                       int32_t state0, const int32_t *plane_ids, void *stream) {
@@ -731,8 +922,14 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
                        pa.devicePointer != nullptr,
                    "step_host: out->host_pack must be pinned (page-locked, device-mapped) host memory");
     }
+    const int32_t fused = vn::choose_fused(store, envs, out, gather_variant);
+    if (fused < 0) return VN_EINVAL;
     // the scalar kernel reads the actions from, and mirrors its per-env results to, mapped host memory
-    rc = vn::run_scalar(tables, envs, rules, inject, host_actions, nullptr, out, stream, false, dev_actions_copy);
+    if (fused > 0)
+        rc = vn::run_fused(store, tables, envs, rules, inject, host_actions, nullptr, out, stream, false,
+                           dev_actions_copy, fused);
+    else
+        rc = vn::run_scalar(tables, envs, rules, inject, host_actions, nullptr, out, stream, false, dev_actions_copy);
     if (rc) return rc;
     if (ready_event) {
         cudaError_t e = cudaEventRecord(static_cast<cudaEvent_t>(ready_event), static_cast<cudaStream_t>(stream));
@@ -741,6 +938,7 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
             return VN_ECUDA;
         }
     }
+    if (fused > 0) return VN_OK;
     return vn::run_gather(store, envs, out, gather_variant, stream);
 }
 

@@ -9,7 +9,7 @@ import os
 from . import build as _build
 
 VN_MAX_PLANES = 6
-VN_N_STATS = 8
+VN_N_STATS = 9
 
 RULE_COLLISION_SKIPS_GOAL = 0x01
 RULE_NEG_STEP_REWARD = 0x02
@@ -19,9 +19,12 @@ RULE_TWO_LEVEL = 0x10
 RULE_NOOP_ACTION = 0x20
 RULE_AUTO_RESET = 0x40
 
-GATHER_AUTO, GATHER_LDG, GATHER_BULK = 0, 1, 2
+GATHER_AUTO, GATHER_LDG, GATHER_BULK, GATHER_FUSED = 0, 1, 2, 3
 STEP_ACTIONS_READY = 0x01
-STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "steps", "truncations", "resets")
+STEP_SKIP_UNCHANGED = 0x02
+ABI_VERSION = 2
+STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "steps", "truncations", "resets",
+              "rows_skipped")
 
 _P = C.c_void_p
 
@@ -71,7 +74,7 @@ class VnError(RuntimeError):
 _lib = None
 
 #: every symbol include/vn_b200.h declares
-EXPORTS = ("vn_abi_version", "vn_abi_struct_size", "vn_last_error", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
+EXPORTS = ("vn_abi_version", "vn_abi_struct_size", "vn_last_error", "vn_launch_count", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
            "vn_env_gather", "vn_env_step_host", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_nstep_returns", "vn_discounted_backup", "vn_pixel_control",
            "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_replay_sample",
@@ -103,6 +106,7 @@ def load(build_if_missing=True):
         "vn_abi_version": (i32, []),
         "vn_abi_struct_size": (i32, [i32]),
         "vn_last_error": (C.c_char_p, []),
+        "vn_launch_count": (i64, []),
         "vn_fill_store": (i32, [S, i32, i32, u64, i32, i32, C.POINTER(i32), _P]),
         "vn_env_reset": (i32, [S, T, E, R, I, _P, O, i32, _P]),
         "vn_env_step": (i32, [S, T, E, R, I, _P, O, i32, _P]),
@@ -127,8 +131,9 @@ def load(build_if_missing=True):
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.vn_abi_version() != 1:
-        raise VnError("libvn_b200.so ABI version %d, expected 1" % lib.vn_abi_version())
+    if lib.vn_abi_version() != ABI_VERSION:
+        raise VnError("libvn_b200.so ABI version %d, expected %d - rebuild with `python __graft_entry__.py`"
+                      % (lib.vn_abi_version(), ABI_VERSION))
     for which, mirror in enumerate((Store, Tables, Envs, Rules, Inject, StepOut, Replay)):
         if lib.vn_abi_struct_size(which) != C.sizeof(mirror):
             raise VnError("libvn_b200.so is stale: sizeof(%s) is %d in the library, %d in lib.py - rebuild with "

@@ -14,7 +14,8 @@ Reference surface kept:
 
 What changes: observations are ``uint8`` CUDA tensors (views of persistent batch buffers that the
 next ``step`` overwrites) instead of pickled float32 numpy arrays; the goal leaves are rewritten only
-for envs that reset; all envs advance in two kernel launches.
+for envs that reset; all envs advance in two kernel launches (one for small batches), and the row of an env whose state did not
+change is not copied again.
 """
 import ctypes as C
 
@@ -102,7 +103,7 @@ class GraphVecEnv:
     def __init__(self, world, num_envs, *, device="cuda", seed=0, max_episode_steps=900, rewards=(1.0, 0.0, 0.0),
                  obs_layout="aux5", unreal_wrapper=True, env_tasks=None, auto_reset=True, rank=0, world_size=1,
                  gather="auto", inject=None, host_outputs=True, device_world=None, scaled_float=False,
-                 episode_info=True):
+                 episode_info=True, skip_unchanged=True):
         """
         world            tables.World (compiled scenes) - or pass a ready ``device_world``
         num_envs         TOTAL number of envs of the job; this process owns shard_range(num_envs, rank, world_size)
@@ -113,6 +114,13 @@ class GraphVecEnv:
         scaled_float     observation leaves as float32 CHW in [0, 1] - what TransposeImage + ScaledFloatFrame
                          (experiments/thor_cached_auxiliary.py:61-62) hand to the model - produced by one fused
                          gather/convert kernel per leaf instead of the uint8 HWC batch
+        gather           "auto" | "ldg" | "bulk" | "fused" (include/vn_b200.h VN_GATHER_*); "auto" runs the whole step
+                         as ONE fused launch for batches of at most one env per SM and as scalar kernel + bulk-copy
+                         gather otherwise
+        skip_unchanged   the observation leaves are views of persistent batch buffers owned by this object, so the
+                         row of an env whose state did not change (collision, no-op) is not copied again
+                         (VN_STEP_SKIP_UNCHANGED).  Pass False if the returned observation tensors are modified in
+                         place between steps.
         """
         self.dw = device_world if device_world is not None else DeviceWorld(world, device)
         self.world: World = self.dw.world
@@ -131,7 +139,9 @@ class GraphVecEnv:
         self.scaled_float = scaled_float
         self.episode_info = episode_info     # RewardCollector's info['episode'] (create_envs wraps with it, :60)
         self.n_actions = 4
-        self.gather = {"auto": L.GATHER_AUTO, "ldg": L.GATHER_LDG, "bulk": L.GATHER_BULK}[gather]
+        self.gather = {"auto": L.GATHER_AUTO, "ldg": L.GATHER_LDG, "bulk": L.GATHER_BULK,
+                       "fused": L.GATHER_FUSED}[gather]
+        self._step_flags = L.STEP_SKIP_UNCHANGED if skip_unchanged else 0
         lay = self.world.layout
         self.leaves = resolve_layout(obs_layout)
         names = self.leaves.values() if isinstance(self.leaves, dict) else \
@@ -236,7 +246,7 @@ class GraphVecEnv:
         self.set_hardness = self.set_complexity     # experiments/thor_cached_auxiliary.py:68
         self._pending = False
         self.closed = False
-        self.kernel_launches = 0
+        self._launches0 = self.lib.vn_launch_count()
         self._calls = 0          # parity of the double-buffered gather descriptors
         # host path: pinned staging seen as numpy views + an event recorded after the scalar results
         # have landed on the host (the gather is still running when step() returns)
@@ -244,6 +254,11 @@ class GraphVecEnv:
         self._pack_np = self._pack_host.numpy()
         self._ready = C.c_void_p()
         L.check(self.lib.vn_event_create(C.byref(self._ready)))
+
+    @property
+    def kernel_launches(self):
+        """Kernels the library enqueued since this object was built (process-wide counter, vn_launch_count)."""
+        return int(self.lib.vn_launch_count() - self._launches0)
 
     # ------------------------------------------------------------------ construction helpers
     def _default_env_tasks(self, num_envs):
@@ -298,7 +313,6 @@ class GraphVecEnv:
                                           C.byref(self._c_rules),
                                           C.byref(self._c_inject) if self._c_inject is not None else None,
                                           L.ptr(m), C.byref(self._c_out), self.gather, self._stream()))
-        self.kernel_launches += 2
         return self._obs()
 
     def _tick(self, out, flags):
@@ -321,14 +335,13 @@ class GraphVecEnv:
             self._actions_np[:] = a
             self._last_actions = self._actions_np
             # host actions were written just now, after the previous ready_event: never produced by the gather
-            self._tick(self._c_out_host, L.STEP_ACTIONS_READY)
+            self._tick(self._c_out_host, L.STEP_ACTIONS_READY | self._step_flags)
             with torch.cuda.device(self.device):
                 L.check(self.lib.vn_env_step_host(
                     C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs), C.byref(self._c_rules),
                     inj, self._actions_host.data_ptr(), self.actions_dev.data_ptr(), C.byref(self._c_out_host),
                     self._ready, self.gather, self._stream()))
             self._pending = "host"
-            self.kernel_launches += 2
             return
         if torch.is_tensor(actions) and actions.is_cuda:
             a = actions if actions.dtype == torch.int32 else actions.to(torch.int32)
@@ -341,12 +354,11 @@ class GraphVecEnv:
         if a.numel() != self.num_envs:
             raise ValueError("expected %d actions, got %d" % (self.num_envs, a.numel()))
         self._last_actions = a
-        self._tick(self._c_out, L.STEP_ACTIONS_READY if actions_ready else 0)
+        self._tick(self._c_out, (L.STEP_ACTIONS_READY if actions_ready else 0) | self._step_flags)
         with torch.cuda.device(self.device):
             L.check(self.lib.vn_env_step(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
                                          C.byref(self._c_rules), inj, a.data_ptr(), C.byref(self._c_out), self.gather,
                                          self._stream()))
-        self.kernel_launches += 2
         self._pending = "device"
 
     def step_enqueue(self, actions, actions_ready=False):
@@ -500,6 +512,7 @@ class GraphVecEnv:
             gather_plane(self.dw, p, self.state, out=buf, variant=self.gather)
         for p, buf in self.goal_buf.items():
             gather_plane(self.dw, p, self.goal, out=buf, variant=self.gather)
+        self.obs_state.copy_(self.state)       # the rows now hold the frames of `state` (skip_unchanged compares to it)
         return self._obs()
 
 

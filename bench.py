@@ -321,6 +321,9 @@ def run_cuda(args):
         torch.cuda.synchronize(dev)
 
     graph_len = 0
+    l0 = env.kernel_launches
+    env.step_enqueue(actions[0])
+    launches_per_step = env.kernel_launches - l0        # 1 (fused launch, small batches) or 2 (scalar + gather)
     if args.cuda_graph:
         # launch-bound batches (C1): replay CUDA graphs of `graph_len` steps instead of 2 launches per step
         graph_len = min(64, n_rows)
@@ -356,7 +359,7 @@ def run_cuda(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop()
-    launches = 2 * K if graph_len else env.kernel_launches - launches0
+    launches = launches_per_step * K if graph_len else env.kernel_launches - launches0
     if world_size > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -365,6 +368,7 @@ def run_cuda(args):
     value = n_total * K / (ms * 1e-3)
     p_reset = stats["resets"] / max(1.0, stats["steps"])
     coll = stats["collisions"] / max(1.0, stats["steps"])
+    p_skip = stats["rows_skipped"] / max(1.0, stats["steps"])   # rows whose record did not change: not copied again
 
     # ---- roofline of the dominant kernel (the frame gather): instrumented pass, events around K2 only
     Kr = min(K, 500)
@@ -375,6 +379,7 @@ def run_cuda(args):
     torch.cuda.synchronize(dev)
     for i in range(Kr):
         a = actions[(W + K + i) % n_rows]
+        env._tick(env._c_out, env._step_flags)      # serial mode: next descriptor half, no overlap with the previous gather
         L.check(env.lib.vn_env_step_scalar(C.byref(env.dw.tables), C.byref(env._c_envs), C.byref(env._c_rules), None,
                                            a.data_ptr(), C.byref(env._c_out), stream))
         es[i][0].record()
@@ -385,9 +390,19 @@ def run_cuda(args):
     gather_ms = float(np.mean([a.elapsed_time(b) for a, b in es]))
     rs = env.episode_stats()
     p_reset_r = rs["resets"] / max(1.0, rs["steps"])
-    alg_bytes = N * (2 * F_OBS + p_reset_r * 2 * F_GOAL)
+    p_skip_r = rs["rows_skipped"] / max(1.0, rs["steps"])
+    # algorithmic bytes of one launch: one read + one write of every observation row that
+    # CHANGED (rows of envs that collided hold the right frames already and are skipped, like the goal rows of envs
+    # that did not reset), plus the goal rows of the envs that reset
+    iso_bytes = N * ((1 - p_skip_r) * 2 * F_OBS + p_reset_r * 2 * F_GOAL)
     peak, peak_src = measured_peak()
-    achieved = alg_bytes / (gather_ms * 1e-3) / 1e9
+    iso_achieved = iso_bytes / (gather_ms * 1e-3) / 1e9
+    # in the timed region the scalar kernel of step k+1 overlaps the gather of step k (pipelined mode), so the
+    # gather's launch-to-launch period there is the step time: that is the kernel's duration in situ (an upper
+    # bound of it - everything else the step does is inside)
+    alg_bytes = N * ((1 - p_skip) * 2 * F_OBS + p_reset * 2 * F_GOAL)
+    situ_ms = ms / K
+    achieved = alg_bytes / (situ_ms * 1e-3) / 1e9
     # calibration: plain contiguous device copies of the SAME number of bytes (torch copy_, the operation the
     # measured peak was taken with, but at this kernel's size instead of 2 GiB), back to back over 4 distinct
     # (src, dst) pairs so that, like the gather in steady state, every copy starts with L2 full of the previous
@@ -407,12 +422,18 @@ def run_cuda(args):
     copy_ms = c0.elapsed_time(c1) / 200
     del pairs
 
+    kname = "vn_step_fused_kernel" if launches_per_step == 1 else \
+        "vn_gather_%s_kernel" % ("ldg" if args.gather == "ldg" else "bulk")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(), "kernel": "vn_gather_%s_kernel" % ("ldg" if args.gather == "ldg" else "bulk"),
-                "kernel_ms": gather_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "same_size_copy_ms": copy_ms, "same_size_copy_gbs": 2 * nb / (copy_ms * 1e-3) / 1e9,
-                "step_frac": (N * (2 * F_OBS + p_reset * 2 * F_GOAL + 40)) / (ms * 1e-3 / K) / 1e9 / peak
-                if world_size == 1 else None}
+                "traffic": profiled_traffic(), "kernel": kname,
+                "kernel_ms": situ_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "how": "in situ: CUDA events around the K timed steps / K launches (the scalar kernel overlaps the "
+                       "previous gather, so this is the gather's launch-to-launch period on this rank)",
+                "rows_skipped_rate": p_skip,
+                "isolated": {"kernel_ms": gather_ms, "achieved": iso_achieved, "frac": iso_achieved / peak,
+                             "algorithmic_bytes_per_launch": iso_bytes,
+                             "how": "CUDA events around each gather launch alone (serialised, includes launch latency)"},
+                "same_size_copy_ms": copy_ms, "same_size_copy_gbs": 2 * nb / (copy_ms * 1e-3) / 1e9}
 
     # ---- secondary line, same store: RGB-only observation (the north-star "84x84 cached-graph nav" target of
     # >= 1e9 env-steps/s on 8 GPUs refers to this 42,336 B/step variant)
@@ -439,13 +460,14 @@ def run_cuda(args):
             ms_r = float(t.item())
         secondary["rgb_only"] = {"value": n_total * Kr2 / (ms_r * 1e-3), "unit": "env-steps/s", "steps": Kr2,
                                  "ms_per_step": ms_r / Kr2, "algorithmic_bytes_per_env_step": 2 * F_RGB,
-                                 "step_frac": N * (2 * F_RGB + 40) / (ms_r * 1e-3 / Kr2) / 1e9 / peak}
+                                 "frac_if_every_row_were_copied": N * 2 * F_RGB / (ms_r * 1e-3 / Kr2) / 1e9 / peak}
         del env_r
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": ms / K, "kernel_ms": gather_ms, "frac": roofline["frac"],
-                              "step_frac": roofline["step_frac"], "p_reset": p_reset}))
+            print(json.dumps({"value": value, "ms_per_step": ms / K, "frac": roofline["frac"],
+                              "iso_kernel_ms": gather_ms, "iso_frac": roofline["isolated"]["frac"],
+                              "p_reset": p_reset, "p_skip": p_skip, "launches_per_step": launches_per_step}))
         if world_size > 1:
             dist.destroy_process_group()
         return
@@ -506,7 +528,8 @@ def run_cuda(args):
                        "store_bytes": env.dw.nbytes(), "batch_bytes_per_step": N * F_OBS,
                        "l2": "inputs larger than L2: %.0f MB store + %.0f MB batch written per step vs 126 MB L2"
                              % (env.dw.nbytes() / 1e6, N * F_OBS / 1e6),
-                       "gather": args.gather, "p_reset": p_reset, "collision_rate": coll,
+                       "gather": args.gather, "p_reset": p_reset, "collision_rate": coll, "rows_skipped_rate": p_skip,
+                       "launches_per_step": launches_per_step,
                        "max_episode_steps": MAX_EPISODE_STEPS, "hardness": hardness, "mix_steps": args.mix,
                        "cuda_graph_steps": graph_len,
                        "parallelism": "env-sharded x%d, no data-path collective" % world_size},

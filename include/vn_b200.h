@@ -15,7 +15,8 @@
  *     marked [host]; the descriptor structs themselves are read on the host during the call.
  *   - no allocation, no implicit synchronisation: kernels are enqueued on the caller's
  *     cudaStream_t (passed as void*; NULL = legacy default stream) and the call returns.
- *   - re-entrant: there is no global state apart from the thread-local error string.
+ *   - re-entrant: there is no global state apart from the thread-local error string and a launch
+ *     counter kept for statistics (vn_launch_count).
  *
  * State numbering: oriented scenes use state = free_cell_rank * 4 + rotation (the numbering of
  * graph/util.py:208-210,229-237 save_graph_as_h5), un-oriented ones state = free_cell_rank; with
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VN_ABI_VERSION 1
+#define VN_ABI_VERSION 2
 #define VN_MAX_PLANES 6 /* rgb, depth, segmentation (+ the 3 third-person planes of graph/thor_graph.py:25-31) */
 
 /* error codes */
@@ -53,6 +54,13 @@ extern "C" {
                                       call's gather was enqueued (e.g. a pre-computed action stream, or host actions
                                       written after the previous ready_event): with gather_desc set, the scalar
                                       kernel then overlaps the previous gather instead of waiting for it */
+#define VN_STEP_SKIP_UNCHANGED 0x02 /* the caller guarantees that out->obs[] are the SAME buffers as in the previous
+                                       reset / step call on these envs and that nothing else wrote to them: the row of
+                                       an env whose record did not change (collision, no-op action) is then not copied
+                                       again - the reference returns the same frame view in that case
+                                       (gym_graph/graph.py:69-72).  Honoured when gather_desc is set or the launch is
+                                       fused; out->obs_state must persist between calls.  Counted in
+                                       VN_STAT_ROWS_SKIPPED. */
 
 /* vn_rules_t.goal_compare */
 #define VN_GOAL_FULL 0     /* gym_graph/graph.py:60-61 position and rotation; cached.py:83 index equality */
@@ -68,7 +76,8 @@ extern "C" {
 #define VN_STAT_STEPS 5
 #define VN_STAT_TRUNCATIONS 6
 #define VN_STAT_RESETS 7
-#define VN_N_STATS 8
+#define VN_STAT_ROWS_SKIPPED 8 /* observation rows not re-copied under VN_STEP_SKIP_UNCHANGED */
+#define VN_N_STATS 9
 
 /* The cached-observation store resident in HBM.  Replaces the numpy arrays
  * ThorGridWorld._observations/_depths/_segmentations [X,Y,4,H,W,C] (graph/multi_graph_no_tp.py:6-25,
@@ -163,12 +172,17 @@ typedef struct vn_step_out {
 #define VN_GATHER_AUTO 0
 #define VN_GATHER_LDG 1      /* 16-byte vector loads/stores through registers */
 #define VN_GATHER_BULK 2     /* cp.async.bulk (TMA engine) global->shared->global, mbarrier-tracked */
+#define VN_GATHER_FUSED 3    /* vn_env_reset / vn_env_step / vn_env_step_host as ONE launch (CTA per env: scalar half, then
+                                bulk copies); what VN_GATHER_AUTO picks for batches of at most one env per SM, where the
+                                step is bound by launch latency.  Elsewhere it means VN_GATHER_BULK. */
 
 int32_t vn_abi_version(void);
 /* sizeof of the descriptor structs as compiled into the library (0 store, 1 tables, 2 envs, 3 rules, 4 inject,
  * 5 step_out, 6 replay; -1 otherwise): a binding checks its mirrors against these at load time. */
 int32_t vn_abi_struct_size(int32_t which);
 const char *vn_last_error(void);
+/* Kernels enqueued by the library so far (process-wide, monotonically increasing; statistics only). */
+int64_t vn_launch_count(void);
 
 /* Fills the store with the synthetic frame hash (a2cat-vn-pytorch_b200/scenes.py frame_bytes):
  * record r of this call holds local state state0 + r of scene `scene`.  Stands in for loading

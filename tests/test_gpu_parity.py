@@ -86,8 +86,9 @@ def starts_to_index(scene, starts, counts):
     return out
 
 
-@pytest.mark.parametrize("gather", ["ldg", "bulk"])
-def test_golden_gym_graph_auxiliary(gather):
+@pytest.mark.parametrize("gather,skip", [("ldg", True), ("bulk", True), ("bulk", False), ("fused", True),
+                                         ("fused", False), ("auto", True)])
+def test_golden_gym_graph_auxiliary(gather, skip):
     g = H.load("gym_graph_aux")
     scene = H.scene_from_golden(g, True, ("rgb", "depth", "segmentation"))
     goals = [tuple(int(v) for v in x) for x in g["goals"]]
@@ -95,12 +96,18 @@ def test_golden_gym_graph_auxiliary(gather):
     N = g["actions"].shape[1]
     env_tasks = np.tile(np.array([[0, len(goals)]], np.int32), (N, 1))
     rec, env = replay_device(g, world, dict(obs_layout="aux5", rewards=tuple(g["rewards_cfg"]), env_tasks=env_tasks,
-                                            gather=gather),
+                                            gather=gather, skip_unchanged=skip),
                              g["reset_choice"], starts_to_index(scene, g["reset_start"], g["reset_count"]), 5, 3)
     assert_equal(rec, g)
     st = env.episode_stats()
     assert st["episodes"] == g["dones"].sum() and st["successes"] == g["wins"].sum()
     assert st["steps"] == g["actions"].size and st["truncations"] == g["truncated"].sum()
+    # rows are skipped exactly when the env's record did not change: a collision that is not followed by a reset
+    same = (g["states"] == np.concatenate([g["reset_states"][None], g["post_states"][:-1]])).all(-1) & ~g["dones"]
+    assert st["rows_skipped"] == (same.sum() if skip else 0)
+    # one launch per step when fused, two otherwise (+ the reset)
+    per_step = 1 if gather in ("fused", "auto") else 2
+    assert env.kernel_launches == per_step * (g["actions"].shape[0] + 1)
 
 
 def test_golden_gym_graph_oriented():
@@ -587,7 +594,7 @@ def test_third_person_planes_six_tuple():
     scene = H.scenes.make_maze_scene((10, 10), 0.25, 2, n_goals=1, planes=planes)
     world = T.compile_world([scene], T.GYM_GRAPH)
     assert world.layout.state_pitch == 2 * (21248 + 7168 + 21248)
-    for gather in ("bulk", "ldg"):
+    for gather in ("bulk", "ldg", "fused"):
         env = vn.GraphVecEnv(world, 40, seed=2, max_episode_steps=11, obs_layout="thor6", unreal_wrapper=False,
                              gather=gather)
         obs = env.reset()
@@ -707,3 +714,53 @@ def test_pipelined_mode_equals_serial_mode():
             assert torch.equal(b.obs_buf["rgb"], b.dw.plane_view("rgb")[s])
             assert torch.equal(b.goal_buf["segmentation"], b.dw.plane_view("segmentation")[b.goal.long()])
     assert a.episode_stats() == b.episode_stats() and a.episode_stats()["episodes"] > N
+
+
+@pytest.mark.parametrize("family", ["gym_graph", "thor_cached", "simple"])
+def test_skipping_unchanged_rows_changes_nothing(family):
+    """VN_STEP_SKIP_UNCHANGED: rows of envs whose record did not change (collisions, no-ops, the previous
+    observation of a terminal THOR step) are not copied again.  The batch must stay byte-identical to the
+    always-copy run, in every launch mode, and the skipped rows are counted."""
+    import torch
+    if family == "simple":
+        scene = H.scenes.make_maze_scene((12, 12), 0.3, 3, n_goals=1, oriented=False, planes=("rgb",))
+        world, layout = T.compile_world([scene], T.SIMPLE_GRAPH), "frame"
+    else:
+        scene = H.scenes.make_thor_scene(150, (16, 20), seed=4, n_goals=3, planes=("rgb", "depth"))
+        if family == "gym_graph":
+            world, layout = T.compile_world([scene], T.GYM_GRAPH), "rgbd_goal"
+        else:       # flat-index goals, cached.py:39
+            world, layout = T.compile_world([scene], T.THOR_CACHED, tasks=[(0, 5), (0, 77), (0, 301)]), "pair"
+    for N, modes in ((1500, ("bulk", "ldg", "pipelined")), (24, ("auto", "fused"))):
+        S = 60
+        ref = vn.GraphVecEnv(world, N, seed=9, max_episode_steps=13, host_outputs=False, obs_layout=layout,
+                             skip_unchanged=False, gather="bulk")
+        envs = {m: vn.GraphVecEnv(world, N, seed=9, max_episode_steps=13, host_outputs=False, obs_layout=layout,
+                                  device_world=ref.dw, gather="bulk" if m == "pipelined" else m) for m in modes}
+        ref.reset()
+        [e.reset() for e in envs.values()]
+        lo = -1 if family == "simple" else 0          # SimpleGraphEnv: action -1 is a no-op (graph/env.py:118-120)
+        acts = torch.randint(lo, 4, (S, N), device="cuda", dtype=torch.int32)
+        torch.cuda.synchronize()
+        for t in range(S):
+            ref.step_enqueue(acts[t])
+            for m, e in envs.items():
+                e.step_enqueue(acts[t], actions_ready=(m == "pipelined"))
+            if t % 5 == 0 or t == S - 1:
+                torch.cuda.synchronize()
+                for m, e in envs.items():
+                    assert torch.equal(ref._pack, e._pack) and torch.equal(ref.state, e.state), (m, t)
+                    for x, y in zip(list(ref.obs_buf.values()) + list(ref.goal_buf.values()),
+                                    list(e.obs_buf.values()) + list(e.goal_buf.values())):
+                        assert torch.equal(x, y), (m, t)
+        base = ref.episode_stats()
+        assert base["rows_skipped"] == 0 and base["collisions"] > 0
+        for m, e in envs.items():
+            st = e.episode_stats()
+            assert st["rows_skipped"] > 0, m
+            assert {k: v for k, v in st.items() if k != "rows_skipped"} == \
+                   {k: v for k, v in base.items() if k != "rows_skipped"}, m
+            assert st["rows_skipped"] == envs[modes[0]].episode_stats()["rows_skipped"]
+        if family == "gym_graph":
+            # gym_graph: the record is unchanged exactly on a collision that does not end at the time limit
+            assert st["rows_skipped"] <= base["collisions"] and st["rows_skipped"] >= base["collisions"] - base["resets"]

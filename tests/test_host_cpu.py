@@ -141,11 +141,11 @@ def test_library_exports_every_declared_symbol():
     L = vn.lib
     lib = L.load()
     header = open(os.path.join(ROOT, "include", "vn_b200.h")).read()
-    declared = set(re.findall(r"^(?:int32_t|const char \*)\s*\*?(vn_[a-z0-9_]+)\(", header, re.M))
+    declared = set(re.findall(r"^(?:int32_t|int64_t|const char \*)\s*\*?(vn_[a-z0-9_]+)\(", header, re.M))
     assert declared == set(L.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.vn_abi_version() == 1
+    assert lib.vn_abi_version() == vn.lib.ABI_VERSION
     out = subprocess.run(["nm", "-D", "--defined-only", L.library_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (vn_[a-z0-9_]+)", out))
     assert declared <= exported
