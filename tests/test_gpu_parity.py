@@ -102,8 +102,8 @@ def test_golden_gym_graph_auxiliary(gather, skip):
     st = env.episode_stats()
     assert st["episodes"] == g["dones"].sum() and st["successes"] == g["wins"].sum()
     assert st["steps"] == g["actions"].size and st["truncations"] == g["truncated"].sum()
-    # rows are skipped exactly when the env's record did not change: a collision that is not followed by a reset
-    same = (g["states"] == np.concatenate([g["reset_states"][None], g["post_states"][:-1]])).all(-1) & ~g["dones"]
+    # rows are skipped exactly when the env's record did not change: a collision, or a reset onto the same state
+    same = (g["post_states"] == np.concatenate([g["reset_states"][None], g["post_states"][:-1]])).all(-1)
     assert st["rows_skipped"] == (same.sum() if skip else 0)
     # one launch per step when fused, two otherwise (+ the reset)
     per_step = 1 if gather in ("fused", "auto") else 2
