@@ -277,7 +277,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ CUDA arm
@@ -465,9 +465,9 @@ def run_cuda(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": ms / K, "frac": roofline["frac"],
-                              "iso_kernel_ms": gather_ms, "iso_frac": roofline["isolated"]["frac"],
-                              "p_reset": p_reset, "p_skip": p_skip, "launches_per_step": launches_per_step}))
+            emit({"value": value, "ms_per_step": ms / K, "frac": roofline["frac"],
+                  "iso_kernel_ms": gather_ms, "iso_frac": roofline["isolated"]["frac"],
+                  "p_reset": p_reset, "p_skip": p_skip, "launches_per_step": launches_per_step})
         if world_size > 1:
             dist.destroy_process_group()
         return
@@ -536,7 +536,7 @@ def run_cuda(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "secondary": secondary,
         }
-        print(json.dumps(line))
+        emit(line)
     if world_size > 1:
         dist.destroy_process_group()
 
@@ -614,16 +614,34 @@ def run_rollout(args):
                      "kernel_ms": ms_pc, "algorithmic_bytes_per_launch": pc_bytes, "peak_source": peak_src},
         "gpu_launches": 7,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else any library prints while the
+    benchmark runs (NCCL's version banner, warnings) was diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", action="store_true", help="replay 64-step CUDA graphs in the device-resident loop")
     ap.add_argument("--quick", action="store_true", help="development: device-resident number + roofline only")
