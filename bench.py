@@ -533,7 +533,7 @@ def run_cuda(args):
                        "max_episode_steps": MAX_EPISODE_STEPS, "hardness": hardness, "mix_steps": args.mix,
                        "cuda_graph_steps": graph_len,
                        "parallelism": "env-sharded x%d, no data-path collective" % world_size},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world_size, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "secondary": secondary,
         }
         emit(line)

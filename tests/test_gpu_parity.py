@@ -764,3 +764,53 @@ def test_skipping_unchanged_rows_changes_nothing(family):
         if family == "gym_graph":
             # gym_graph: the record is unchanged exactly on a collision that does not end at the time limit
             assert st["rows_skipped"] <= base["collisions"] and st["rows_skipped"] >= base["collisions"] - base["resets"]
+
+
+def test_outputs_stay_inside_their_buffers():
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are looked for with canaries: every
+    output and state array the kernels write is re-pointed into the middle of a guarded allocation, all launch
+    modes run with frequent resets, and the guard bytes on both sides must be untouched."""
+    import ctypes as C
+    import torch
+    G = 4096
+    scene = H.scenes.make_thor_scene(120, (14, 18), seed=5, n_goals=3, planes=("rgb", "depth", "segmentation"))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    lay = world.layout
+    for N, gather in ((23, "fused"), (23, "bulk"), (777, "bulk"), (777, "ldg")):
+        env = vn.GraphVecEnv(world, N, seed=3, max_episode_steps=5, host_outputs=False, obs_layout="aux5", gather=gather)
+        guards = []
+
+        def guarded(t):
+            raw = torch.full((t.numel() * t.element_size() + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+            inner = raw[G:G + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+            inner.copy_(t)
+            guards.append(raw)
+            return inner
+
+        for i, p in enumerate(lay.planes):
+            if p in env.obs_buf:
+                env.obs_buf[p] = guarded(env.obs_buf[p])
+                env._c_out.obs[i] = env.obs_buf[p].data_ptr()
+            if p in env.goal_buf:
+                env.goal_buf[p] = guarded(env.goal_buf[p])
+                env._c_out.goal_obs[i] = env.goal_buf[p].data_ptr()
+        env.lar = guarded(env.lar)
+        env._c_out.last_action_reward = env.lar.data_ptr()
+        env.obs_state = guarded(env.obs_state)
+        env._c_out.obs_state = env.obs_state.data_ptr()
+        env._gather_desc = guarded(env._gather_desc)
+        env._c_out.gather_desc = env._gather_desc.data_ptr()
+        for name in ("state", "goal", "task", "elapsed", "epoch", "ep_return", "ep_length"):
+            setattr(env, name, guarded(getattr(env, name)))
+            setattr(env._c_envs, name, getattr(env, name).data_ptr())
+        env.reset()
+        acts = torch.randint(0, 4, (40, N), device="cuda", dtype=torch.int32)
+        for t in range(40):
+            env.step_enqueue(acts[t], actions_ready=(t % 2 == 1 and gather == "bulk"))
+        torch.cuda.synchronize()
+        for raw in guards:
+            assert bool((raw[:G] == 0xA5).all()) and bool((raw[-G:] == 0xA5).all()), (N, gather)
+        s = env.state.long()
+        assert torch.equal(env.obs_buf["segmentation"], env.dw.plane_view("segmentation")[s])
+        assert torch.equal(env.goal_buf["rgb"], env.dw.plane_view("rgb")[env.goal.long()])
+        assert env.episode_stats()["resets"] > N
