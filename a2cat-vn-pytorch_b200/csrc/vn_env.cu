@@ -8,6 +8,7 @@
 //                       reset, its goal planes) from the HBM store into the contiguous policy batch.
 //                       >99.9 % of the bytes; HBM-bound; two variants (LDG.128 registers / bulk async copy).
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <string>
 
@@ -51,6 +52,8 @@ struct StepParams {
     int32_t *actions_copy;   // optional device copy of the actions (host-actions path)
     int32_t skip_rows;       // VN_STEP_SKIP_UNCHANGED is set AND the gather half can honour it (descriptors / fused)
 };
+
+constexpr int kStepThreads = 128;  // envs per block of the scalar half (= envs per host_seq word)
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 
@@ -234,8 +237,18 @@ __device__ __forceinline__ void add_stats(uint64_t *stats, const EnvStats &s) {
     if (s.skipped) atomicAdd(st + VN_STAT_ROWS_SKIPPED, (unsigned long long)s.skipped);
 }
 
+// Every thread of a block calls this after its writes to the mapped host pack: each writer makes its writes
+// visible system-wide, the block meets, and one thread publishes `seq` in the block's host word.  The host has the
+// scalars of all envs once every block's word shows `seq` (vn_host_wait_seq) - no device-wide counter, one
+// system-scope fence on the critical path.
+__device__ __forceinline__ void signal_host(const vn_step_out_t &out) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(out.host_seq + blockIdx.x) = out.seq;
+}
+
 template <bool kReset>
-__global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kStepThreads) vn_step_kernel(const StepParams p) {
     // Pipelined mode (VN_STEP_ACTIONS_READY + gather_desc): nothing this kernel reads was produced by its
     // immediate predecessor - the previous gather - and what it writes for the next gather goes to the other
     // half of the double-buffered descriptor, so it runs WHILE the previous gather is still copying and only
@@ -269,6 +282,7 @@ __global__ void __launch_bounds__(128) vn_step_kernel(const StepParams p) {
         for (int o = 16; o > 0; o >>= 1) w.ret += __shfl_xor_sync(0xffffffffu, w.ret, o);
         if ((threadIdx.x & 31) == 0) add_stats(p.out.stats, w);
     }
+    if (p.out.host_seq) signal_host(p.out);
     if (defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
@@ -490,7 +504,10 @@ __global__ void __launch_bounds__(kFusedWarps * 32) vn_step_fused_kernel(const S
         s_rec = rec;
         s_grec = gp.goal ? grec : -1;
     }
-    __syncthreads();
+    if (sp.out.host_seq)
+        signal_host(sp.out);  // contains the block barrier
+    else
+        __syncthreads();
     if ((threadIdx.x & 31) != 0) return;
     const vn_store_t &S = gp.store;
     const uint8_t *src[2] = {s_rec >= 0 ? S.base + (size_t)s_rec * S.state_pitch : nullptr,
@@ -710,7 +727,7 @@ static int32_t run_scalar(const vn_tables_t *tab, const vn_envs_t *envs, const v
     StepParams sp;
     int32_t rc = make_step_params(sp, tab, envs, rules, inj, actions, mask, out, reset, actions_copy);
     if (rc) return rc;
-    const int threads = 128;
+    const int threads = kStepThreads;
     const int blocks = (envs->n_envs + threads - 1) / threads;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (reset)
@@ -835,6 +852,25 @@ static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const v
     return run_gather(store, envs, out, variant, stream);
 }
 
+// Pinned + device-mapped?  The answer for the last few pointers is remembered per thread: the query costs about
+// a microsecond and the host-facing step asks about the same three buffers every call.
+static bool is_mapped_host(const void *p) {
+    constexpr int kSlots = 8;
+    static thread_local const void *known[kSlots] = {nullptr};
+    static thread_local int next = 0;
+    for (int i = 0; i < kSlots; ++i)
+        if (known[i] == p) return true;
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (pa.type != cudaMemoryTypeHost || pa.devicePointer == nullptr) return false;
+    known[next] = p;
+    next = (next + 1) % kSlots;
+    return true;
+}
+
 }  // namespace vn
 
 // =====================================================================================================
@@ -913,15 +949,12 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
     int32_t rc = vn::validate_store(store);
     if (rc) return rc;
     VN_REQUIRE(host_actions, "step_host: host_actions is null");
-    cudaPointerAttributes pa;
-    VN_REQUIRE(cudaPointerGetAttributes(&pa, host_actions) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
-                   pa.devicePointer != nullptr,
+    VN_REQUIRE(vn::is_mapped_host(host_actions),
                "step_host: host_actions must be pinned (page-locked, device-mapped) host memory");
-    if (out && out->host_pack) {
-        VN_REQUIRE(cudaPointerGetAttributes(&pa, out->host_pack) == cudaSuccess && pa.type == cudaMemoryTypeHost &&
-                       pa.devicePointer != nullptr,
-                   "step_host: out->host_pack must be pinned (page-locked, device-mapped) host memory");
-    }
+    VN_REQUIRE(!out || !out->host_pack || vn::is_mapped_host(out->host_pack),
+               "step_host: out->host_pack must be pinned (page-locked, device-mapped) host memory");
+    VN_REQUIRE(!out || !out->host_seq || vn::is_mapped_host(out->host_seq),
+               "step_host: out->host_seq must be pinned (page-locked, device-mapped) host memory");
     const int32_t fused = vn::choose_fused(store, envs, out, gather_variant);
     if (fused < 0) return VN_EINVAL;
     // the scalar kernel reads the actions from, and mirrors its per-env results to, mapped host memory
@@ -940,6 +973,56 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
     }
     if (fused > 0) return VN_OK;
     return vn::run_gather(store, envs, out, gather_variant, stream);
+}
+
+int32_t vn_env_host_seq_words(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
+                              int32_t gather_variant) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    int32_t rc = vn::validate_store(store);
+    if (rc) return rc;
+    const int32_t fused = vn::choose_fused(store, envs, out, gather_variant);
+    if (fused < 0) return VN_EINVAL;
+    if (envs->n_envs == 0) return 1;
+    return fused > 0 ? envs->n_envs : (envs->n_envs + vn::kStepThreads - 1) / vn::kStepThreads;
+}
+
+int32_t vn_host_wait_seq(const uint32_t *host_seq, int32_t words, uint32_t seq, void *stream, int64_t timeout_us) {
+    VN_REQUIRE(host_seq && words >= 1, "host_wait_seq: null or no words");
+    const volatile uint32_t *flag = host_seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    int64_t next_query_us = 50;
+    int32_t have = 0;  // words [0, have) have been seen with the new value (they do not change back)
+    for (uint64_t spin = 0;; ++spin) {
+        while (have < words && flag[have] == seq) ++have;
+        if (have == words) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return VN_OK;
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+        if ((spin & 255) != 255) continue;
+        const int64_t us =
+            std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (us >= next_query_us) {
+            next_query_us = us + 50;
+            const cudaError_t e = cudaStreamQuery(static_cast<cudaStream_t>(stream));
+            if (e == cudaSuccess) {  // everything enqueued has run: the words must have been written by now
+                while (have < words && flag[have] == seq) ++have;
+                if (have == words) return VN_OK;
+                vn::set_error("host_wait_seq: the stream drained but word %d is %u, not %u", have, flag[have], seq);
+                return VN_ECUDA;
+            }
+            if (e != cudaErrorNotReady) {
+                vn::set_error("host_wait_seq: %s", cudaGetErrorString(e));
+                return VN_ECUDA;
+            }
+        }
+        if (timeout_us > 0 && us > timeout_us) {
+            vn::set_error("host_wait_seq: timed out after %lld us", (long long)us);
+            return VN_ECUDA;
+        }
+    }
 }
 
 int32_t vn_event_create(void **event) {

@@ -27,6 +27,12 @@ from . import spaces
 from .store import DeviceWorld
 from .tables import World, Family
 
+try:        # raw handle of torch's current stream without building a torch.cuda.Stream object (0.2 us instead of 2 us)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:      # pragma: no cover - older / newer torch without the private helper
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+
 #: named observation layouts -> leaves.  A leaf is a store plane ("rgb", "depth", "segmentation") or the
 #: same plane of the goal state ("goal_rgb", "goal_segmentation").
 OBS_LAYOUTS = {
@@ -74,6 +80,8 @@ class LazyInfos:
     def _host(self):
         if callable(self._a):
             self._a = self._a()
+        if isinstance(self._a, np.ndarray):          # the raw host pack: split it on first use
+            self._a = self._env._unpack(self._a)
         if torch.is_tensor(self._noop):
             self._noop = self._noop.cpu().numpy()
         return self._a
@@ -182,7 +190,7 @@ class GraphVecEnv:
             self.obs_state = i32()
             self.stats = torch.zeros(L.VN_N_STATS, dtype=torch.int64, device=self.device)
             self.actions_dev = i32()
-            self._sched = torch.zeros(2, dtype=torch.int32, device=self.device)     # gather ticket counters
+            self._sched = torch.zeros(4, dtype=torch.int32, device=self.device)     # scheduler / completion counters
             self._gather_desc = torch.zeros((2, max(n, 1), 2), dtype=torch.int32, device=self.device)
             self.obs_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
                                            dtype=torch.uint8, device=self.device) for p in self.obs_planes}
@@ -225,7 +233,19 @@ class GraphVecEnv:
         out_h = L.StepOut()
         C.memmove(C.byref(out_h), C.byref(out), C.sizeof(L.StepOut))
         out_h.host_pack = self._pack_host.data_ptr()
+        # one sequence word per thread block of the scalar kernel, published once that block's scalars are on the host
+        self._seq_words = self.lib.vn_env_host_seq_words(C.byref(self.dw.store), C.byref(self._c_envs), C.byref(out_h),
+                                                         self.gather)
+        if self._seq_words <= 0:
+            L.check(self._seq_words)
+        self._seq_host = torch.zeros(self._seq_words, dtype=torch.int32).pin_memory()
+        out_h.host_seq = self._seq_host.data_ptr()
         self._c_out_host = out_h
+        self._seq = 0
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        # constant arguments of the per-step C calls, converted once
+        self._ref = dict(store=C.byref(self.dw.store), tables=C.byref(self.dw.tables), envs=C.byref(self._c_envs),
+                         rules=C.byref(self._c_rules), out=C.byref(self._c_out), out_host=C.byref(self._c_out_host))
 
         def frame(leaf):
             p = leaf[5:] if leaf.startswith("goal_") else leaf
@@ -245,15 +265,14 @@ class GraphVecEnv:
         self.action_space = spaces.Discrete(self.n_actions)
         self.set_hardness = self.set_complexity     # experiments/thor_cached_auxiliary.py:68
         self._pending = False
+        self._obs_cache = None
         self.closed = False
         self._launches0 = self.lib.vn_launch_count()
         self._calls = 0          # parity of the double-buffered gather descriptors
-        # host path: pinned staging seen as numpy views + an event recorded after the scalar results
-        # have landed on the host (the gather is still running when step() returns)
+        # host path: pinned staging seen as numpy views; the scalar kernel publishes a sequence word once its
+        # results have landed on the host (the gather is still running when step() returns)
         self._actions_np = self._actions_host.numpy()
         self._pack_np = self._pack_host.numpy()
-        self._ready = C.c_void_p()
-        L.check(self.lib.vn_event_create(C.byref(self._ready)))
 
     @property
     def kernel_launches(self):
@@ -281,7 +300,15 @@ class GraphVecEnv:
 
     # ------------------------------------------------------------------ reference surface
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        return _raw_stream(self._dev_index)
+
+    def _call(self, fn, *args):
+        """One C-ABI call with this env's device current (the guard is skipped when it already is)."""
+        if torch.cuda.current_device() == self._dev_index:
+            L.check(fn(*args))
+        else:
+            with torch.cuda.device(self.device):
+                L.check(fn(*args))
 
     def _leaf(self, name):
         if self.scaled_float:
@@ -292,6 +319,13 @@ class GraphVecEnv:
         return self.goal_buf[name[5:]] if name.startswith("goal_") else self.obs_buf[name]
 
     def _obs(self):
+        if not self.scaled_float:       # the leaves are the persistent batch buffers: build the structure once
+            if self._obs_cache is None:
+                self._obs_cache = self._build_obs()
+            return self._obs_cache
+        return self._build_obs()
+
+    def _build_obs(self):
         lv = self.leaves
         if isinstance(lv, dict):
             inner = {k: self._leaf(v) for k, v in lv.items()}
@@ -308,11 +342,10 @@ class GraphVecEnv:
         if mask is not None:
             m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8)
         self._tick(self._c_out, 0)
-        with torch.cuda.device(self.device):
-            L.check(self.lib.vn_env_reset(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
-                                          C.byref(self._c_rules),
-                                          C.byref(self._c_inject) if self._c_inject is not None else None,
-                                          L.ptr(m), C.byref(self._c_out), self.gather, self._stream()))
+        r = self._ref
+        self._call(self.lib.vn_env_reset, r["store"], r["tables"], r["envs"], r["rules"],
+                   C.byref(self._c_inject) if self._c_inject is not None else None,
+                   L.ptr(m), r["out"], self.gather, self._stream())
         return self._obs()
 
     def _tick(self, out, flags):
@@ -328,19 +361,21 @@ class GraphVecEnv:
         inj = C.byref(self._c_inject) if self._c_inject is not None else None
         if self.host_outputs and not (torch.is_tensor(actions) and actions.is_cuda):
             # reference-facing path: host actions in, host scalars out - ONE C call enqueues
-            # H2D, scalar kernel, D2H, event, gather kernel
+            # scalar kernel (reads / writes mapped pinned memory) and gather kernel
             a = np.asarray(actions.cpu() if torch.is_tensor(actions) else actions).reshape(-1)
             if a.size != self.num_envs:
                 raise ValueError("expected %d actions, got %d" % (self.num_envs, a.size))
             self._actions_np[:] = a
             self._last_actions = self._actions_np
-            # host actions were written just now, after the previous ready_event: never produced by the gather
+            # host actions were written just now, after the scalars of the previous step arrived: the previous
+            # scalar kernel has finished reading them, and the gather never produces them
             self._tick(self._c_out_host, L.STEP_ACTIONS_READY | self._step_flags)
-            with torch.cuda.device(self.device):
-                L.check(self.lib.vn_env_step_host(
-                    C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs), C.byref(self._c_rules),
-                    inj, self._actions_host.data_ptr(), self.actions_dev.data_ptr(), C.byref(self._c_out_host),
-                    self._ready, self.gather, self._stream()))
+            self._seq = (self._seq % 0x7FFFFFFF) + 1
+            self._c_out_host.seq = self._seq
+            r = self._ref
+            self._call(self.lib.vn_env_step_host, r["store"], r["tables"], r["envs"], r["rules"], inj,
+                       self._actions_host.data_ptr(), self.actions_dev.data_ptr(), r["out_host"], None,
+                       self.gather, self._stream())
             self._pending = "host"
             return
         if torch.is_tensor(actions) and actions.is_cuda:
@@ -355,10 +390,9 @@ class GraphVecEnv:
             raise ValueError("expected %d actions, got %d" % (self.num_envs, a.numel()))
         self._last_actions = a
         self._tick(self._c_out, (L.STEP_ACTIONS_READY if actions_ready else 0) | self._step_flags)
-        with torch.cuda.device(self.device):
-            L.check(self.lib.vn_env_step(C.byref(self.dw.store), C.byref(self.dw.tables), C.byref(self._c_envs),
-                                         C.byref(self._c_rules), inj, a.data_ptr(), C.byref(self._c_out), self.gather,
-                                         self._stream()))
+        r = self._ref
+        self._call(self.lib.vn_env_step, r["store"], r["tables"], r["envs"], r["rules"], inj, a.data_ptr(), r["out"],
+                   self.gather, self._stream())
         self._pending = "device"
 
     def step_enqueue(self, actions, actions_ready=False):
@@ -415,10 +449,15 @@ class GraphVecEnv:
         mode, self._pending = self._pending, False
         noop = (self._last_actions < 0) if self.family.noop_action else None
         if mode == "host":
-            # wait for the scalars only; the gather of this step is still in flight on the stream
-            L.check(self.lib.vn_event_wait(self._ready))
-            h = self._unpack(self._pack_np.copy())
-            return self._obs(), h["reward"], h["done"].view(np.bool_), LazyInfos(self, h, noop)
+            # wait for the scalars only (the kernel publishes a sequence word in pinned memory once they have all
+            # landed); the gather of this step is still in flight - or not even started - on the stream
+            n = self.num_envs
+            if n:
+                L.check(self.lib.vn_host_wait_seq(self._seq_host.data_ptr(), self._seq_words, self._seq, self._stream(),
+                                                  60_000_000))
+            h = self._pack_np.copy()
+            return (self._obs(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
+                    LazyInfos(self, h, noop))
         if self.host_outputs:
             self._pack_host.copy_(self._pack, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
@@ -432,9 +471,9 @@ class GraphVecEnv:
         return self.step_wait()
 
     def close(self):
-        if not self.closed and self._ready:
-            self.lib.vn_event_destroy(self._ready)
-            self._ready = C.c_void_p()
+        if not self.closed and torch.cuda.is_available():
+            # kernels in flight may still write the mapped pinned buffers this object owns
+            torch.cuda.synchronize(self.device)
         self.closed = True
 
     def _check_open(self):

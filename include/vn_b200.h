@@ -159,13 +159,21 @@ typedef struct vn_step_out {
                                          descriptors handed from the scalar half to the gather half of step `parity` */
     int32_t parity;                   /* step counter (only bit 0 is used); the caller increments it every reset / step */
     int32_t flags;                    /* VN_STEP_* */
-    uint32_t *sched;                  /* optional scratch of 2 uint32, zeroed once by the caller: ticket counters of the
-                                         gather's dynamic scheduler (self re-arming; one per env batch / stream) */
+    uint32_t *sched;                  /* optional scratch of 4 uint32, zeroed once by the caller: [0..1] ticket counters of
+                                         the gather's dynamic scheduler ([2..3] reserved; self re-arming; one scratch per
+                                         env batch / stream) */
     uint8_t *host_pack;               /* optional MAPPED PINNED HOST block of 20 * n_envs bytes ("host pack") that the
                                          scalar kernel also writes, n = n_envs:
                                            [0, 4n) reward f32 | [4n, 8n) episode_return f32 | [8n, 12n) episode_length i32
                                            | [12n, 16n) info_state i32 | [16n, 17n) done | [17n, 18n) truncated
                                            | [18n, 19n) win | [19n, 20n) did_reset */
+    uint32_t *host_seq;               /* optional MAPPED PINNED HOST words, one per thread block of the scalar half
+                                         (vn_env_host_seq_words of them): a block stores `seq` into its word once the scalars
+                                         of ITS envs are in host_pack (system-scope fence first); the host polls the words
+                                         with vn_host_wait_seq instead of waiting on an event - no stream operation between
+                                         the two halves, so the gather stays programmatically chained to the scalar half */
+    uint32_t seq;                     /* value to store; the caller changes it every call */
+    uint32_t reserved;
 } vn_step_out_t;
 
 /* gather kernel variants (all bit-identical) */
@@ -219,14 +227,23 @@ int32_t vn_env_gather(const vn_store_t *store, const vn_envs_t *envs, const vn_s
  * SubprocVecEnv.step).  host_actions and out->host_pack are PINNED host memory (device-mapped under
  * UVA).  Enqueues, in stream order: the scalar half - which reads the actions straight from
  * host_actions and mirrors the per-env scalars into out->host_pack over PCIe, so no copy-engine
- * operation sits on the critical path -; a record of ready_event; the gather half.  The host waits on
- * ready_event (vn_event_wait), i.e. for the scalars only, while the gather keeps running; the
+ * operation sits on the critical path -; a record of ready_event (optional); the gather half.  The
+ * host waits for the scalars only - on out->host_seq (vn_host_wait_seq, preferred: nothing sits between the
+ * two kernels) or on ready_event (vn_event_wait) - while the gather keeps running; the
  * observations stay in HBM, ordered before any later work on the same stream.  dev_actions_copy
  * (optional) receives a device copy of the actions for device-side consumers (rollout buffer). */
 int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
                          const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
                          int32_t *dev_actions_copy, const vn_step_out_t *out, void *ready_event,
                          int32_t gather_variant, void *stream);
+/* Number of host_seq words vn_env_step_host will publish for this batch (= thread blocks of its scalar half:
+ * one per env when the step runs as the fused launch, one per 128 envs otherwise); <= 0 on error. */
+int32_t vn_env_host_seq_words(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
+                              int32_t gather_variant);
+/* Spins (pause loop, no GIL under ctypes) until host_seq[0 .. words) all equal seq.  Every ~50 us it looks at the
+ * stream: a CUDA error, or a stream that drained without the words ever arriving, ends the wait with VN_ECUDA; so
+ * does timeout_us (> 0). */
+int32_t vn_host_wait_seq(const uint32_t *host_seq, int32_t words, uint32_t seq, void *stream, int64_t timeout_us);
 int32_t vn_event_create(void **event);   /* cudaEventDisableTiming */
 int32_t vn_event_destroy(void *event);
 int32_t vn_event_wait(void *event);      /* cudaEventSynchronize; releases the GIL under ctypes */

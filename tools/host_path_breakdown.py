@@ -45,8 +45,8 @@ def main():
     L = vn.lib
     t0 = time.perf_counter()
     for _ in range(K):
-        L.check(env.lib.vn_event_wait(env._ready))
-    print("vn_event_wait on a completed event: %.2f us" % (1e6 * (time.perf_counter() - t0) / K))
+        L.check(env.lib.vn_host_wait_seq(env._seq_host.data_ptr(), env._seq_words, env._seq, env._stream(), 1000000))
+    print("vn_host_wait_seq on a published word: %.2f us" % (1e6 * (time.perf_counter() - t0) / K))
     t0 = time.perf_counter()
     for _ in range(K):
         env._unpack(env._pack_np.copy())
@@ -59,11 +59,6 @@ def main():
     for _ in range(K):
         env._stream()
     print("_stream(): %.2f us" % (1e6 * (time.perf_counter() - t0) / K))
-    t0 = time.perf_counter()
-    for _ in range(K):
-        with torch.cuda.device(env.device):
-            pass
-    print("torch.cuda.device guard: %.2f us" % (1e6 * (time.perf_counter() - t0) / K))
     t0 = time.perf_counter()
     for i in range(K):
         env.step_async(acts[i % 256])
