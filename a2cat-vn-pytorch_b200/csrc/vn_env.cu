@@ -641,13 +641,8 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
                    "gather: goal_obs[%d] must be 16-byte aligned", pl);
     }
     if (variant == VN_GATHER_FUSED) variant = VN_GATHER_BULK;  // no scalar half here: the fused launch does not apply
-    if (variant == VN_GATHER_AUTO) {
-        // measured on B200 (profiles/): the bulk-copy variant reaches 94 % of the copy peak, LDG.128 86 %
-        int per_env = 0;
-        for (int pl = 0; pl < gp.store.n_planes; ++pl)
-            if (gp.obs[pl]) per_env += gp.store.plane_bytes[pl];
-        variant = per_env <= 100 * 1024 ? VN_GATHER_BULK : VN_GATHER_LDG;
-    }
+    // measured on B200 (profiles/): the bulk-copy variant reaches 94 % of the copy peak, LDG.128 86 %
+    if (variant == VN_GATHER_AUTO) variant = VN_GATHER_BULK;
     if (variant == VN_GATHER_LDG) {
         constexpr int kThreads = 256;
         launch_pdl(vn_gather_ldg_kernel<kThreads, 4>, dim3(gp.n), dim3(kThreads), 0, stream, gp);
@@ -664,6 +659,16 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         // slices until there are ~2 units per SM (latency-bound regime; one slice >= 2 KB)
         int split = env_split > 0 ? env_split : 1;
         if (env_split <= 0 && gp.n < 2 * sm_count()) split = min(16, (2 * sm_count() + gp.n - 1) / gp.n);
+        if (env_split <= 0) {
+            // large records (the reference's native 174 x 174 frames: 212 KB for rgb + depth + segmentation) are
+            // cut into slices of at most ~48 KB so that at least 4 CTAs stay resident per SM
+            int per_env = 0, per_goal = 0;
+            for (int pl = 0; pl < gp.store.n_planes; ++pl) {
+                if (gp.obs[pl]) per_env += gp.store.plane_bytes[pl];
+                if (gp.goal && gp.goal_obs[pl]) per_goal += gp.store.plane_bytes[pl];
+            }
+            split = max(split, (max(per_env, per_goal) + 48 * 1024 - 1) / (48 * 1024));
+        }
         int smem_obs = 0, smem_goal = 0;
         for (int pl = 0; pl < gp.store.n_planes; ++pl) {
             const int n16 = gp.store.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;

@@ -71,7 +71,8 @@ __device__ __forceinline__ void build_lut(float *lut) {
 __device__ __forceinline__ void load_frame(uint8_t *dst_smem, const uint8_t *src, int nbytes) {
     const int4 *s = reinterpret_cast<const int4 *>(src);
     int4 *d = reinterpret_cast<int4 *>(dst_smem);
-    for (int k = threadIdx.x; k < (nbytes >> 4); k += blockDim.x) d[k] = ld_stream16(s + k);
+    // whole 16-byte units: a frame that is not a multiple of 16 bytes is padded in the store (and in dst_smem)
+    for (int k = threadIdx.x; k < ((nbytes + 15) >> 4); k += blockDim.x) d[k] = ld_stream16(s + k);
 }
 
 struct PoolGeom {
@@ -500,8 +501,9 @@ int32_t vn_discounted_backup(const float *reward, const uint8_t *done, const flo
 static int32_t check_plane(const vn_store_t *store, int32_t plane, int h, int w, int c, const char *who) {
     VN_REQUIRE(store && store->base, "%s: store is null", who);
     VN_REQUIRE(plane >= 0 && plane < store->n_planes, "%s: plane=%d", who, plane);
-    VN_REQUIRE(store->plane_bytes[plane] == h * w * c, "%s: plane holds %d bytes, geometry says %d", who,
-               store->plane_bytes[plane], h * w * c);
+    VN_REQUIRE(store->plane_bytes[plane] == ((h * w * c + 15) & ~15),
+               "%s: plane holds %d bytes, geometry says %d (rounded up to 16)", who, store->plane_bytes[plane],
+               h * w * c);
     VN_REQUIRE((store->plane_bytes[plane] & 15) == 0 && (store->state_pitch & 15) == 0 &&
                    (store->plane_off[plane] & 15) == 0,
                "%s: store is not 16-byte aligned", who);

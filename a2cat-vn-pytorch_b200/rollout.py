@@ -59,7 +59,7 @@ def _geom(dw, plane, cell, output_size):
     lay = dw.world.layout
     pi = dw.plane_index(plane)
     h, w = lay.frame_hw
-    c = lay.plane_bytes[pi] // (h * w)
+    c = lay.channels[pi]
     if output_size is None:
         output_size = (h // cell, w // cell)
     return pi, h, w, c, int(output_size[0]), int(output_size[1])
@@ -347,4 +347,4 @@ class ReplayRing:
         if scaled_float:
             return policy_input(self.dw, idx, plane)
         out = gather_plane(self.dw, plane, idx.reshape(-1))
-        return out.view(tuple(idx.shape) + tuple(out.shape[1:]))
+        return out.reshape(tuple(idx.shape) + tuple(out.shape[1:]))     # a view unless the rows are padded

@@ -49,14 +49,15 @@ def frame_key(seed: int, scene: int, state, plane: int):
 
 def frame_bytes(seed: int, scene: int, state, plane: int, nbytes: int) -> np.ndarray:
     """uint8 ``[len(state), nbytes]`` (or ``[nbytes]`` for a scalar state): 8 bytes per hash word,
-    word ``w`` of the frame = splitmix64(key + w), little-endian.  ``nbytes`` must be a multiple of 8."""
-    assert nbytes % 8 == 0
+    word ``w`` of the frame = splitmix64(key + w), little-endian (a frame that is not a whole number of
+    words ends inside its last word)."""
     scalar = np.ndim(state) == 0
     key = np.atleast_1d(frame_key(seed, scene, state, plane))
-    words = np.arange(nbytes // 8, dtype=np.uint64)
+    nwords = -(-nbytes // 8)
+    words = np.arange(nwords, dtype=np.uint64)
     with np.errstate(over="ignore"):
         h = splitmix64(key[:, None] + words[None, :])
-    out = h.astype("<u8").view(np.uint8).reshape(len(key), nbytes)
+    out = np.ascontiguousarray(h.astype("<u8").view(np.uint8).reshape(len(key), nwords * 8)[:, :nbytes])
     return out[0] if scalar else out
 
 

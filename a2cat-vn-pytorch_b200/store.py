@@ -76,11 +76,11 @@ class DeviceWorld:
         lay = self.world.layout
         sc = self.world.scenes[scene_index]
         r0 = int(self.world.scene_base[scene_index])
-        for name, off, nb in zip(lay.planes, lay.plane_off, lay.plane_bytes):
+        for name, off, nb in zip(lay.planes, lay.plane_off, lay.frame_bytes):
             a = np.ascontiguousarray(planes[name]).reshape(sc.n_states, nb)
             self.frames[r0:r0 + sc.n_states, off:off + nb] = torch.from_numpy(a).to(self.device)
         pad = torch.ones(lay.state_pitch, dtype=torch.bool)
-        for off, nb in zip(lay.plane_off, lay.plane_bytes):
+        for off, nb in zip(lay.plane_off, lay.frame_bytes):
             pad[off:off + nb] = False
         if pad.any():
             self.frames[r0:r0 + sc.n_states][:, pad.to(self.device)] = 0
@@ -99,8 +99,7 @@ class DeviceWorld:
         lay = self.world.layout
         i = self.plane_index(name)
         h, w = lay.frame_hw
-        return self.frames[:, lay.plane_off[i]:lay.plane_off[i] + lay.plane_bytes[i]].view(-1, h, w,
-                                                                                           lay.plane_bytes[i] // (h * w))
+        return self.frames[:, lay.plane_off[i]:lay.plane_off[i] + lay.frame_bytes[i]].view(-1, h, w, lay.channels[i])
 
     def nbytes(self):
         return self.frames.numel()

@@ -267,24 +267,42 @@ STORE_ALIGN = 128   # plane offsets and the per-state pitch are multiples of one
 
 @dataclass
 class StoreLayout:
+    """``plane_bytes`` is what the kernels copy per plane: the frame (``frame_bytes`` = H * W * C) rounded up to
+    a whole number of 16-byte units.  84 x 84 frames need no rounding; the reference's native 174 x 174 frames
+    (GraphResize default, graph/core.py:43-49: 90,828 B rgb, 30,276 B depth) get 4 / 12 bytes of zero padding,
+    in the store records and in the rows of the observation batch alike."""
     planes: Tuple[str, ...]
     plane_bytes: Tuple[int, ...]
     plane_off: Tuple[int, ...]
     state_pitch: int
     frame_hw: Tuple[int, int]
+    frame_bytes: Tuple[int, ...] = ()
+    channels: Tuple[int, ...] = ()
 
     @staticmethod
     def make(planes, frame_hw):
         from .scenes import PLANE_CHANNELS
-        off, offs, sizes = 0, [], []
+        off, offs, sizes, exact, chans = 0, [], [], [], []
         for p in planes:
             nb = frame_hw[0] * frame_hw[1] * PLANE_CHANNELS[p]
-            if nb % 16:
-                raise ValueError("plane %s: %d bytes is not a multiple of 16" % (p, nb))
+            exact.append(nb)
+            chans.append(PLANE_CHANNELS[p])
+            nb = -(-nb // 16) * 16
             offs.append(off)
             sizes.append(nb)
             off += -(-nb // STORE_ALIGN) * STORE_ALIGN
-        return StoreLayout(tuple(planes), tuple(sizes), tuple(offs), off, tuple(frame_hw))
+        return StoreLayout(tuple(planes), tuple(sizes), tuple(offs), off, tuple(frame_hw), tuple(exact), tuple(chans))
+
+    def batch(self, plane, n, device):
+        """uint8 ``[n, H, W, C]`` observation batch of ``plane`` whose rows are ``plane_bytes`` apart (what the
+        gather kernels write): contiguous when the frame is a whole number of 16-byte units, else a strided view
+        of a padded allocation."""
+        import torch
+        i = self.planes.index(plane)
+        h, w = self.frame_hw
+        c, pitch = self.channels[i], self.plane_bytes[i]
+        raw = torch.zeros((max(n, 1), pitch), dtype=torch.uint8, device=device)
+        return raw.as_strided((n, h, w, c), (pitch, w * c, c, 1))
 
 
 @dataclass

@@ -192,10 +192,8 @@ class GraphVecEnv:
             self.actions_dev = i32()
             self._sched = torch.zeros(4, dtype=torch.int32, device=self.device)     # scheduler / completion counters
             self._gather_desc = torch.zeros((2, max(n, 1), 2), dtype=torch.int32, device=self.device)
-            self.obs_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
-                                           dtype=torch.uint8, device=self.device) for p in self.obs_planes}
-            self.goal_buf = {p: torch.zeros((n, h, w, lay.plane_bytes[lay.planes.index(p)] // (h * w)),
-                                            dtype=torch.uint8, device=self.device) for p in self.goal_planes}
+            self.obs_buf = {p: lay.batch(p, n, self.device) for p in self.obs_planes}
+            self.goal_buf = {p: lay.batch(p, n, self.device) for p in self.goal_planes}
             self._pack_host = torch.zeros(n * 20, dtype=torch.uint8).pin_memory()
             self._actions_host = torch.zeros(n, dtype=torch.int32).pin_memory()
         self._inject_keep = None
@@ -249,7 +247,7 @@ class GraphVecEnv:
 
         def frame(leaf):
             p = leaf[5:] if leaf.startswith("goal_") else leaf
-            c = lay.plane_bytes[lay.planes.index(p)] // (h * w)
+            c = lay.channels[lay.planes.index(p)]
             if scaled_float:
                 return spaces.Box(0.0, 1.0, (c, h, w), np.float32)
             return spaces.Box(0, 255, (h, w, c), np.uint8)
@@ -564,7 +562,9 @@ def gather_plane(dw: DeviceWorld, plane, idx, out=None, variant=L.GATHER_AUTO):
     idx = idx.to(device=dw.device, dtype=torch.int32).contiguous()
     n = idx.numel()
     if out is None:
-        out = torch.empty((n, h, w, lay.plane_bytes[pi] // (h * w)), dtype=torch.uint8, device=dw.device)
+        out = lay.batch(plane, n, dw.device)
+    elif n > 1 and out.stride(0) != lay.plane_bytes[pi]:
+        raise ValueError("gather_plane: rows of `out` must be %d bytes apart (StoreLayout.batch)" % lay.plane_bytes[pi])
     with torch.cuda.device(dw.device):
         L.check(dw.lib.vn_gather_plane(C.byref(dw.store), pi, idx.data_ptr(), n, out.data_ptr(), variant,
                                        torch.cuda.current_stream(dw.device).cuda_stream))

@@ -82,7 +82,9 @@ extern "C" {
 /* The cached-observation store resident in HBM.  Replaces the numpy arrays
  * ThorGridWorld._observations/_depths/_segmentations [X,Y,4,H,W,C] (graph/multi_graph_no_tp.py:6-25,
  * 141-144) and the h5 'observation' dataset (graph/util.py:224): one record per state holding all
- * planes, record pitch and plane offsets multiples of 128 B, plane sizes multiples of 16 B. */
+ * planes, record pitch and plane offsets multiples of 128 B, plane sizes multiples of 16 B: plane_bytes is
+ * H * W * C rounded up to 16 (84 x 84 frames need no rounding, the reference's native 174 x 174 ones get 4 / 12
+ * padding bytes), and the rows of an observation batch are plane_bytes apart as well. */
 typedef struct vn_store {
     const uint8_t *base;               /* [n_states][state_pitch] */
     int64_t state_pitch;
@@ -141,7 +143,7 @@ typedef struct vn_inject {
 
 /* Outputs of one vectorised step.  Any pointer may be NULL to skip that output. */
 typedef struct vn_step_out {
-    uint8_t *obs[VN_MAX_PLANES];      /* [n_envs][plane_bytes[p]] observation batch, contiguous */
+    uint8_t *obs[VN_MAX_PLANES];      /* [n_envs][plane_bytes[p]] observation batch, rows plane_bytes[p] apart */
     uint8_t *goal_obs[VN_MAX_PLANES]; /* persistent goal batch: rows rewritten only for envs that reset */
     float *reward;                    /* [n_envs] */
     uint8_t *done;                    /* [n_envs] env done OR time-limit */

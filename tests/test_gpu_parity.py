@@ -814,3 +814,43 @@ def test_outputs_stay_inside_their_buffers():
         assert torch.equal(env.obs_buf["segmentation"], env.dw.plane_view("segmentation")[s])
         assert torch.equal(env.goal_buf["rgb"], env.dw.plane_view("rgb")[env.goal.long()])
         assert env.episode_stats()["resets"] > N
+
+
+@pytest.mark.parametrize("hw,cell,out", [((174, 174), 4, (42, 42)), ((18, 22), 2, (8, 10))])
+def test_frames_that_are_not_a_multiple_of_16_bytes(hw, cell, out):
+    """The reference's native frame size is 174 x 174 (GraphResize default, graph/core.py:43-49; 90,828-byte
+    rgb frames, PC / deconv targets 42 x 42 - models/goal.py:151-156): records and batch rows are padded to 16
+    bytes, every gather variant and every target builder must still return the exact frames."""
+    import torch
+    from oracle import rollout as orl
+    planes = ("rgb", "depth", "segmentation")
+    scene = H.scenes.make_maze_scene((7, 7), 0.2, 3, n_goals=2, planes=planes, frame_hw=hw)
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    dw = vn.DeviceWorld(world)
+    for p in planes:
+        assert np.array_equal(dw.plane_view(p).cpu().numpy(), scene.plane_frames(p)), p
+    for N, gather in ((12, "auto"), (300, "bulk"), (300, "ldg")):
+        env = vn.GraphVecEnv(world, N, seed=2, max_episode_steps=6, obs_layout="aux5", gather=gather, device_world=dw)
+        env.set_complexity(0.4)
+        (obs, lar) = env.reset()
+        rng = np.random.RandomState(4)
+        for t in range(25):
+            (obs, lar), r, d, infos = env.step(rng.randint(0, 4, N))
+        s, g = env.state.cpu().numpy(), env.goal.cpu().numpy()
+        want = (scene.plane_frames("rgb", s), scene.plane_frames("rgb", g), scene.plane_frames("depth", s),
+                scene.plane_frames("segmentation", s), scene.plane_frames("segmentation", g))
+        for leaf, w in zip(obs, want):
+            assert leaf.shape == w.shape and np.array_equal(leaf.cpu().numpy(), w), (N, gather)
+        assert env.episode_stats()["resets"] > N
+    # target builders and the float policy input on padded records
+    st = torch.randint(0, world.n_states, (3, 5), dtype=torch.int32)
+    fr = scene.plane_frames("rgb", st.numpy().reshape(-1)).reshape(3, 5, hw[0], hw[1], 3)
+    pc = vn.rollout.pixel_control_reward(dw, st, cell, out)
+    np.testing.assert_allclose(pc.cpu().numpy(), orl.pixel_control_reward(orl.u8_to_policy_input(fr), cell, out),
+                               rtol=1e-5, atol=1e-7)
+    x = vn.rollout.policy_input(dw, st, "rgb").cpu().numpy()
+    assert np.array_equal(x, orl.u8_to_policy_input(fr))
+    dep = scene.plane_frames("depth", st.numpy().reshape(-1)).reshape(3, 5, hw[0], hw[1], 1)
+    aux = vn.rollout.auxiliary_target(dw, st, "depth", cell, out)
+    np.testing.assert_allclose(aux.cpu().numpy(), orl.aux_target(orl.u8_to_policy_input(dep), cell, out),
+                               rtol=1e-5, atol=1e-7)

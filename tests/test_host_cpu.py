@@ -112,8 +112,16 @@ def test_world_concatenation_and_layout():
     lay = w.layout
     assert lay.plane_bytes == (21168, 7056, 21168) and lay.state_pitch % 128 == 0
     assert all(o % 128 == 0 for o in lay.plane_off)
-    with pytest.raises(ValueError):
-        T.StoreLayout.make(("rgb",), (10, 10))        # 300 bytes is not a multiple of 16
+    # frames that are not a whole number of 16-byte units are padded (records and batch rows alike): the
+    # reference's native 174 x 174 (graph/core.py:43-49)
+    big = T.StoreLayout.make(("rgb", "depth", "segmentation"), (174, 174))
+    assert big.frame_bytes == (90828, 30276, 90828) and big.plane_bytes == (90832, 30288, 90832)
+    assert big.channels == (3, 1, 3) and all(o % 128 == 0 for o in big.plane_off) and big.state_pitch % 128 == 0
+    small = T.StoreLayout.make(("rgb",), (10, 10))
+    assert small.frame_bytes == (300,) and small.plane_bytes == (304,)
+    assert H.scenes.frame_bytes(1, 2, np.arange(3), 0, 300).shape == (3, 300)
+    assert np.array_equal(H.scenes.frame_bytes(1, 2, np.arange(3), 0, 300),
+                          H.scenes.frame_bytes(1, 2, np.arange(3), 0, 304)[:, :300])
 
 
 def test_frame_hash_is_stable():
