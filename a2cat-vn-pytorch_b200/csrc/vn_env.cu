@@ -439,9 +439,10 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     uint32_t parity = 0;
     BulkHints hints;
-    hints.mode = hint_mode;
-    hints.load_policy = (hint_mode & 1) ? l2_policy_evict_last() : 0;
-    hints.store_policy = (hint_mode & 2) ? l2_policy_evict_first() : 0;
+    // bits: 1 loads evict_last, 2 stores evict_first, 4 loads evict_first, 8 stores evict_last
+    hints.load_policy = (hint_mode & 1) ? l2_policy_evict_last() : (hint_mode & 4) ? l2_policy_evict_first() : 0;
+    hints.store_policy = (hint_mode & 2) ? l2_policy_evict_first() : (hint_mode & 8) ? l2_policy_evict_last() : 0;
+    hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
     const int units = p.n * split;
     const bool dynamic = sched != nullptr;
     int u = dynamic ? (int)atomicAdd(&sched[0], 1u) : (int)blockIdx.x;
