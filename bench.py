@@ -425,7 +425,10 @@ def run_cuda(args):
     kname = "vn_step_fused_kernel" if launches_per_step == 1 else \
         "vn_gather_%s_kernel" % ("ldg" if args.gather == "ldg" else "bulk")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(), "kernel": kname,
+                # the committed ncu capture is of the C2 bulk gather; other workloads / variants have none
+                "traffic": profiled_traffic() if (args.workload == "c2" and launches_per_step == 2 and
+                                                  args.gather in ("auto", "bulk") and hardness is None) else None,
+                "kernel": kname,
                 "kernel_ms": situ_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "how": "in situ: CUDA events around the K timed steps / K launches (the scalar kernel overlaps the "
                        "previous gather, so this is the gather's launch-to-launch period on this rank)",
@@ -511,13 +514,13 @@ def run_cuda(args):
 
     cpu_baseline = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline and args.workload == "c2":
-        # bounded sample (~15 s of CPU work): 32 envs x 4,000 vector steps cross the 900-step TimeLimit about four
+        # bounded sample (10-30 s of CPU work): 32 envs x 8,000 vector steps cross the 900-step TimeLimit about nine
         # times per env, so the reference's per-reset candidate enumeration (~0.1 s each here) is included
-        v, nres, cdt = cpu_run(32, 4000, 3, 1)
+        v, nres, cdt = cpu_run(32, 8000, 3, 1)
         cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": 1, "kind": "port",
-                        "sample": "32 envs x 4000 vector steps, one process, sequential + np.stack (DummyVecEnv "
+                        "sample": "32 envs x 8000 vector steps, one process, sequential + np.stack (DummyVecEnv "
                                   "equivalent), episode phases randomised, %.1f s, p_reset=%.5f"
-                                  % (cdt, nres / (32 * 4000.0))}
+                                  % (cdt, nres / (32 * 8000.0))}
 
     if rank == 0:
         line = {
