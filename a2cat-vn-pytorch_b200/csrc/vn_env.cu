@@ -10,6 +10,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 #include "vn_common.cuh"
@@ -1029,6 +1030,21 @@ int32_t vn_host_wait_seq(const uint32_t *host_seq, int32_t words, uint32_t seq, 
             return VN_ECUDA;
         }
     }
+}
+
+int32_t vn_env_step_host_sync(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
+                              const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
+                              int32_t *dev_actions_copy, const vn_step_out_t *out, uint8_t *pack_copy,
+                              int32_t seq_words, int32_t gather_variant, void *stream, int64_t timeout_us) {
+    VN_REQUIRE(out && out->host_pack && out->host_seq, "step_host_sync: out->host_pack and out->host_seq are required");
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    int32_t rc = vn_env_step_host(store, tables, envs, rules, inject, host_actions, dev_actions_copy, out, nullptr,
+                                  gather_variant, stream);
+    if (rc || envs->n_envs == 0) return rc;
+    rc = vn_host_wait_seq(out->host_seq, seq_words, out->seq, stream, timeout_us);
+    if (rc) return rc;
+    if (pack_copy) memcpy(pack_copy, out->host_pack, (size_t)20 * envs->n_envs);
+    return VN_OK;
 }
 
 int32_t vn_event_create(void **event) {

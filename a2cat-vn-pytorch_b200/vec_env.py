@@ -240,6 +240,7 @@ class GraphVecEnv:
         out_h.host_seq = self._seq_host.data_ptr()
         self._c_out_host = out_h
         self._seq = 0
+        self._actions_ptr, self._actions_dev_ptr = self._actions_host.data_ptr(), self.actions_dev.data_ptr()
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         # constant arguments of the per-step C calls, converted once
         self._ref = dict(store=C.byref(self.dw.store), tables=C.byref(self.dw.tables), envs=C.byref(self._c_envs),
@@ -465,6 +466,27 @@ class GraphVecEnv:
         return self._obs(), self.reward, self.done.bool(), LazyInfos(self, fetch, noop)
 
     def step(self, actions):
+        if self.host_outputs and type(actions) is np.ndarray and not self._pending and not self.closed \
+                and actions.size == self.num_envs and self.num_envs:
+            # the reference-facing call, numpy in / numpy out, as ONE C call: stage the actions, enqueue both
+            # kernels, spin until the scalars are in pinned memory, copy them out (vn_env_step_host_sync)
+            n = self.num_envs
+            np.copyto(self._actions_np, actions.reshape(-1), casting="same_kind")
+            out = self._c_out_host
+            self._calls += 1
+            out.parity = self._calls & 1
+            out.flags = L.STEP_ACTIONS_READY | self._step_flags
+            self._seq = (self._seq % 0x7FFFFFFF) + 1
+            out.seq = self._seq
+            h = np.empty(20 * n, np.uint8)
+            r = self._ref
+            self._call(self.lib.vn_env_step_host_sync, r["store"], r["tables"], r["envs"], r["rules"],
+                       C.byref(self._c_inject) if self._c_inject is not None else None,
+                       self._actions_ptr, self._actions_dev_ptr, r["out_host"], h.__array_interface__["data"][0],
+                       self._seq_words, self.gather, _raw_stream(self._dev_index), 60_000_000)
+            noop = (self._actions_np < 0) if self.family.noop_action else None
+            return (self._obs(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
+                    LazyInfos(self, h, noop))
         self.step_async(actions)
         return self.step_wait()
 
