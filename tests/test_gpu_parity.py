@@ -854,3 +854,44 @@ def test_frames_that_are_not_a_multiple_of_16_bytes(hw, cell, out):
     aux = vn.rollout.auxiliary_target(dw, st, "depth", cell, out)
     np.testing.assert_allclose(aux.cpu().numpy(), orl.aux_target(orl.u8_to_policy_input(dep), cell, out),
                                rtol=1e-5, atol=1e-7)
+
+
+def test_philox_reset_path_thor_cached_task_list():
+    """THORCachedEnv's intent (gym_thor_cached.py:45-53: a task list, start with dist[start][goal] > 0, dict
+    observation) on the device's own Philox reset path, against the oracle env driven by the oracle restatement
+    of that sampling built from the h5 'shortest_path_distance' table - not from the product's compiled tables."""
+    seed, N, Tn, limit = 77, 10, 250, 9
+    scene = H.scenes.make_maze_scene((8, 8), 0.2, 6, n_goals=1, planes=("rgb",))
+    osc = oenvs.OracleScene(scene)
+    _, graph, spd = gu.h5_tables(scene.maze, osc.graph)
+    goals = [3, 41, 90, 17]
+    world = T.compile_world([scene], T.THOR_CACHED, tasks=[(0, g) for g in goals])
+    assert np.array_equal(world.adj, graph)
+    env_tasks = np.tile(np.array([[0, len(goals)]], np.int32), (N, 1))
+    env = vn.GraphVecEnv(world, N, seed=seed, max_episode_steps=limit, obs_layout="dict", unreal_wrapper=False,
+                         env_tasks=env_tasks)
+    frames = scene.plane_frames("rgb")
+    oes = []
+    for i in range(N):
+        e = oenvs.ThorCachedEnv(graph, frames, spd, tasks=goals, dict_obs=True)
+        cands = [(list(np.nonzero(spd[:, g] > 0)[0]), spd[np.nonzero(spd[:, g] > 0)[0], g]) for g in goals]
+        e.reset_source = ovec.PhiloxResetSource(seed, i, cands, lambda t: None, False)
+        oes.append(ovec.TimeLimit(e, limit))
+    obs = env.reset()
+    oobs = [e.reset() for e in oes]
+    rng = np.random.RandomState(8)
+    n_done = 0
+    for t in range(Tn):
+        a = rng.randint(0, 4, N)
+        obs, rew, done, infos = env.step(a)
+        img, goal = obs["image"].cpu().numpy(), obs["goal"].cpu().numpy()
+        for i, e in enumerate(oes):
+            o, r, d, info = e.step(int(a[i]))
+            if d:
+                o = e.reset()                       # the VecEnv worker's auto-reset
+            assert bool(done[i]) == bool(d) and f32bits(rew[i]) == f32bits(np.float32(r)), (t, i)
+            assert int(env.state[i]) == e.env._current_state_idx and int(env.goal[i]) == e.env._current_goal_idx, (t, i)
+            assert np.array_equal(img[i], o["image"]) and np.array_equal(goal[i], o["goal"]), (t, i)
+            assert infos[i].get("TimeLimit.truncated") == info.get("TimeLimit.truncated"), (t, i)
+        n_done += int(done.sum())
+    assert n_done > N
