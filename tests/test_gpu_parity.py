@@ -895,3 +895,24 @@ def test_philox_reset_path_thor_cached_task_list():
             assert infos[i].get("TimeLimit.truncated") == info.get("TimeLimit.truncated"), (t, i)
         n_done += int(done.sum())
     assert n_done > N
+
+
+def test_evaluation_service_success_rate_and_spl():
+    """trainer.test()-style evaluation roll-outs: the shortest-path policy scores success 1 and SPL 1; a random
+    policy under a short time limit scores less on both; the hardness schedule is the reference's LinearSchedule."""
+    import torch
+    E = vn.evaluation
+    scene = H.scenes.make_thor_scene(200, (20, 25), seed=3, n_goals=3, planes=("rgb",))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    env = vn.GraphVecEnv(world, 256, seed=5, max_episode_steps=60, obs_layout="frame", host_outputs=False)
+    res = E.evaluate(env, lambda obs: env.optimal_actions()[0], episodes=1000)
+    assert res["episodes"] == 1000 and res["success_rate"] == 1.0 and abs(res["spl"] - 1.0) < 1e-12
+    assert res["truncated_rate"] == 0.0 and res["reward"] == 1.0
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    rnd = E.evaluate(env, lambda obs: torch.randint(0, 4, (256,), device="cuda", generator=gen, dtype=torch.int32),
+                     episodes=1000)
+    assert rnd["episodes"] == 1000 and rnd["success_rate"] < 0.9 and rnd["spl"] < rnd["success_rate"] + 1e-12
+    assert rnd["truncated_rate"] > 0 and abs(rnd["success_rate"] + rnd["truncated_rate"] - 1.0) < 1e-12
+    sched = E.LinearSchedule(0.3, 1.0, 200000)                       # thor_cached_auxiliary.py:45
+    assert sched(0) == 0.3 and abs(sched(100000) - 0.65) < 1e-12 and sched(10 ** 7) == 1.0
+    assert E.apply_hardness_schedule(env, sched, 50000) == sched(50000) and env.dw.complexity == sched(50000)
