@@ -285,6 +285,64 @@ __global__ void __launch_bounds__(256) vn_gather_f32_chw_kernel(const vn_store_t
     }
 }
 
+// float(v) / 255.0f, correctly rounded, without a division or a table: q = v * r with r = fl(1 / 255), one Newton
+// step on the exact residual e = fma(-q, 255, v), q' = fma(e, r, q).  Equal to __fdiv_rn(v, 255) for all 256 byte
+// values (checked exhaustively on the host and, bit for bit, by the policy_input parity tests).
+__device__ __forceinline__ float u8_over_255(uint32_t v) {
+    const float x = (float)v, r = 1.0f / 255.0f;
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q, 255.0f, x);
+    return __fmaf_rn(e, r, q);
+}
+
+// Vectorised form of the same conversion for frames whose pixel count is a multiple of 4 (84 x 84, 174 x 174):
+// one thread per GROUP of 4 pixels.  It reads the group's 4 * C bytes as C aligned 32-bit words straight from the
+// store (no staging, no shared memory, no block barrier), scales every byte with u8_over_255 and writes one
+// 16-byte vector per channel plane - a warp writes 512 contiguous bytes of each plane.  Grid-stride over
+// (frame, group), 4 groups per thread in flight.
+template <int C>
+__global__ void __launch_bounds__(256) vn_gather_f32_chw_vec_kernel(const uint8_t *__restrict__ pbase, int64_t pitch,
+                                                                    const int32_t *__restrict__ idx, int n, int hw,
+                                                                    float *__restrict__ out) {
+    const int groups = hw >> 2;
+    const int64_t total = (int64_t)n * groups;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int kUnroll = 4;  // groups per thread and iteration: 4 * C independent loads in flight
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < total; g0 += kUnroll * stride) {
+        uint32_t w[kUnroll][C];
+        float *o[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t g = g0 + u * stride;
+            o[u] = nullptr;
+            if (g < total) {
+                const int f = (int)(g / groups), q = (int)(g - (int64_t)f * groups);
+                const uint32_t *src =
+                    reinterpret_cast<const uint32_t *>(pbase + (size_t)__ldg(idx + f) * pitch) + (size_t)q * C;
+#pragma unroll
+                for (int j = 0; j < C; ++j) w[u][j] = __ldg(src + j);
+                o[u] = out + ((int64_t)f * C) * hw + 4 * q;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!o[u]) continue;
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) {
+                float v[4];
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                    const int b = px * C + ch;  // byte of the group: pixel-major, channel-minor (HWC)
+                    v[px] = u8_over_255((w[u][b >> 2] >> (8 * (b & 3))) & 255u);
+                }
+                asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o[u] + (int64_t)ch * hw), "f"(v[0]),
+                             "f"(v[1]), "f"(v[2]), "f"(v[3])
+                             : "memory");
+            }
+        }
+    }
+}
+
 // =====================================================================================================
 // reward-prediction labels + order-preserving compaction of zero / non-zero positions
 // =====================================================================================================
@@ -641,6 +699,22 @@ int32_t vn_gather_plane_f32_chw(const vn_store_t *store, int32_t plane, const in
     if (rc) return rc;
     VN_REQUIRE(idx && out && n >= 0, "gather_plane_f32_chw: bad arguments");
     if (n == 0) return VN_OK;
+    if ((h * w) % 4 == 0 && (c == 1 || c == 3) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        // whole 4-pixel groups: the vectorised kernel (0.36 -> see DESIGN.md of the copy peak for the staged one)
+        const int64_t total = (int64_t)n * (h * w / 4);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        const int64_t want = (total + 4 * 256 - 1) / (4 * 256), cap = (int64_t)sms * 16;
+        const int grid = (int)(want < cap ? want : cap);
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const uint8_t *pbase = store->base + store->plane_off[plane];
+        if (c == 1)
+            vn::vn_gather_f32_chw_vec_kernel<1><<<grid, 256, 0, st>>>(pbase, store->state_pitch, idx, n, h * w, out);
+        else
+            vn::vn_gather_f32_chw_vec_kernel<3><<<grid, 256, 0, st>>>(pbase, store->state_pitch, idx, n, h * w, out);
+        return vn::check_launch("vn_gather_f32_chw_vec_kernel");
+    }
     const int smem = (h * w * c + 15) & ~15;
     VN_REQUIRE(smem <= 220 * 1024, "gather_plane_f32_chw: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_gather_f32_chw_kernel, smem);
