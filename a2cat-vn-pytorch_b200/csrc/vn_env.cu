@@ -503,6 +503,9 @@ __global__ void __launch_bounds__(kFusedWarps * 32) vn_step_fused_kernel(const S
         int rec, grec;
         step_env<kReset>(sp, env, st, rec, grec);
         if (sp.out.stats) add_stats(sp.out.stats, st);
+        if (sp.out.gather_desc)  // for consumers after this launch (float batches, vn_gather_plane_f32_chw_rows)
+            reinterpret_cast<int2 *>(sp.out.gather_desc)[(size_t)(sp.out.parity & 1) * sp.env.n_envs + env] =
+                make_int2(rec, grec);
         s_rec = rec;
         s_grec = gp.goal ? grec : -1;
     }
@@ -896,6 +899,7 @@ int32_t vn_abi_struct_size(int32_t which) {
         case 4: return (int32_t)sizeof(vn_inject_t);
         case 5: return (int32_t)sizeof(vn_step_out_t);
         case 6: return (int32_t)sizeof(vn_replay_t);
+        case 7: return (int32_t)sizeof(vn_float_leaf_t);
         default: return -1;
     }
 }

@@ -268,14 +268,16 @@ __global__ void __launch_bounds__(256) vn_aux_target_kernel(const vn_store_t sto
 
 // gather + TransposeImage + ScaledFloatFrame: out[i][c][h][w] = float(frame[h][w][c]) / 255
 __global__ void __launch_bounds__(256) vn_gather_f32_chw_kernel(const vn_store_t store, int plane,
-                                                                const int32_t *__restrict__ idx, int n, int h, int w,
-                                                                int c, float *__restrict__ out) {
+                                                                const int32_t *__restrict__ idx, int idx_stride, int n,
+                                                                int h, int w, int c, float *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int fbytes = h * w * c;
     const int hw = h * w;
     for (int f = blockIdx.x; f < n; f += gridDim.x) {
+        const int rec = idx[(int64_t)f * idx_stride];
+        if (rec < 0) continue;  // uniform over the block: row f keeps its content
         __syncthreads();
-        load_frame(smem_raw, store.base + store.plane_off[plane] + (size_t)idx[f] * store.state_pitch, fbytes);
+        load_frame(smem_raw, store.base + store.plane_off[plane] + (size_t)rec * store.state_pitch, fbytes);
         __syncthreads();
         float *o = out + (int64_t)f * fbytes;
         for (int k = threadIdx.x; k < fbytes; k += blockDim.x) {  // k indexes the CHW output: coalesced stores
@@ -302,8 +304,8 @@ __device__ __forceinline__ float u8_over_255(uint32_t v) {
 // (frame, group), 4 groups per thread in flight.
 template <int C>
 __global__ void __launch_bounds__(256) vn_gather_f32_chw_vec_kernel(const uint8_t *__restrict__ pbase, int64_t pitch,
-                                                                    const int32_t *__restrict__ idx, int n, int hw,
-                                                                    float *__restrict__ out) {
+                                                                    const int32_t *__restrict__ idx, int idx_stride,
+                                                                    int n, int hw, float *__restrict__ out) {
     const int groups = hw >> 2;
     const int64_t total = (int64_t)n * groups;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -317,11 +319,13 @@ __global__ void __launch_bounds__(256) vn_gather_f32_chw_vec_kernel(const uint8_
             o[u] = nullptr;
             if (g < total) {
                 const int f = (int)(g / groups), q = (int)(g - (int64_t)f * groups);
-                const uint32_t *src =
-                    reinterpret_cast<const uint32_t *>(pbase + (size_t)__ldg(idx + f) * pitch) + (size_t)q * C;
+                const int rec = __ldg(idx + (int64_t)f * idx_stride);
+                if (rec >= 0) {  // negative: row f keeps its content
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(pbase + (size_t)rec * pitch) + (size_t)q * C;
 #pragma unroll
-                for (int j = 0; j < C; ++j) w[u][j] = __ldg(src + j);
-                o[u] = out + ((int64_t)f * C) * hw + 4 * q;
+                    for (int j = 0; j < C; ++j) w[u][j] = __ldg(src + j);
+                    o[u] = out + ((int64_t)f * C) * hw + 4 * q;
+                }
             }
         }
 #pragma unroll
@@ -338,6 +342,86 @@ __global__ void __launch_bounds__(256) vn_gather_f32_chw_vec_kernel(const uint8_
                 asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o[u] + (int64_t)ch * hw), "f"(v[0]),
                              "f"(v[1]), "f"(v[2]), "f"(v[3])
                              : "memory");
+            }
+        }
+    }
+}
+
+// All float leaves of one step in ONE launch: thread per (env, group of 4 pixels); for every leaf the record comes
+// from the step's gather descriptor (x = observation record or -1, y = goal record or -1).  The loads of all
+// leaves are issued before the first conversion, so one thread keeps up to 18 independent 4-byte loads in flight.
+constexpr int kMaxFloatLeaves = 6;
+struct FloatLeaves {
+    const uint8_t *pbase[kMaxFloatLeaves];  // store base + plane offset
+    float *out[kMaxFloatLeaves];
+    int32_t c[kMaxFloatLeaves];             // 1 or 3
+    int32_t goal[kMaxFloatLeaves];          // 0: descriptor x, 1: descriptor y
+    int32_t n_leaves;
+};
+
+__device__ __forceinline__ void store_group(float *o, const uint32_t *w, int c, int hw) {
+    for (int ch = 0; ch < c; ++ch) {
+        float v[4];
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+            const int b = px * c + ch;
+            // w[] is indexed with compile-time constants once c is known (c == 1 or c == 3 below)
+            v[px] = u8_over_255((w[b >> 2] >> (8 * (b & 3))) & 255u);
+        }
+        asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + (int64_t)ch * hw), "f"(v[0]), "f"(v[1]),
+                     "f"(v[2]), "f"(v[3])
+                     : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256) vn_gather_leaves_f32_kernel(const FloatLeaves L, int64_t pitch,
+                                                                   const int2 *__restrict__ desc, int n, int hw) {
+    const int groups = hw >> 2;
+    const int64_t total = (int64_t)n * groups;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // groups per thread and iteration: 1 (with 2 the kernel needs 71 registers and runs 40 % slower, measured)
+    constexpr int kUnroll = 1;
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < total; g0 += kUnroll * stride) {
+        uint32_t w[kUnroll][kMaxFloatLeaves][3];
+        bool live[kUnroll][kMaxFloatLeaves];
+        int fq[kUnroll][2];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t g = g0 + u * stride;
+            const bool in = g < total;
+            const int f = in ? (int)(g / groups) : 0, q = in ? (int)(g - (int64_t)f * groups) : 0;
+            fq[u][0] = f;
+            fq[u][1] = q;
+            int2 d = make_int2(-1, -1);
+            if (in) d = __ldg(desc + f);
+#pragma unroll
+            for (int l = 0; l < kMaxFloatLeaves; ++l) {
+                live[u][l] = false;
+                if (l < L.n_leaves) {
+                    const int rec = L.goal[l] ? d.y : d.x;
+                    if (rec >= 0) {
+                        live[u][l] = true;
+                        const uint32_t *src =
+                            reinterpret_cast<const uint32_t *>(L.pbase[l] + (size_t)rec * pitch) + (size_t)q * L.c[l];
+                        w[u][l][0] = __ldg(src);
+                        if (L.c[l] == 3) {
+                            w[u][l][1] = __ldg(src + 1);
+                            w[u][l][2] = __ldg(src + 2);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+            for (int l = 0; l < kMaxFloatLeaves; ++l) {
+                if (!live[u][l]) continue;
+                float *o = L.out[l] + ((int64_t)fq[u][0] * L.c[l]) * hw + 4 * fq[u][1];
+                if (L.c[l] == 3)
+                    store_group(o, w[u][l], 3, hw);
+                else
+                    store_group(o, w[u][l], 1, hw);
             }
         }
     }
@@ -695,9 +779,14 @@ int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx
 
 int32_t vn_gather_plane_f32_chw(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, int32_t h,
                                 int32_t w, int32_t c, float *out, void *stream) {
+    return vn_gather_plane_f32_chw_rows(store, plane, idx, 1, n, h, w, c, out, stream);
+}
+
+int32_t vn_gather_plane_f32_chw_rows(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t idx_stride,
+                                     int32_t n, int32_t h, int32_t w, int32_t c, float *out, void *stream) {
     int32_t rc = check_plane(store, plane, h, w, c, "gather_plane_f32_chw");
     if (rc) return rc;
-    VN_REQUIRE(idx && out && n >= 0, "gather_plane_f32_chw: bad arguments");
+    VN_REQUIRE(idx && out && n >= 0 && idx_stride >= 1, "gather_plane_f32_chw: bad arguments");
     if (n == 0) return VN_OK;
     if ((h * w) % 4 == 0 && (c == 1 || c == 3) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         // whole 4-pixel groups: the vectorised kernel (0.36 -> see DESIGN.md of the copy peak for the staged one)
@@ -710,18 +799,63 @@ int32_t vn_gather_plane_f32_chw(const vn_store_t *store, int32_t plane, const in
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         const uint8_t *pbase = store->base + store->plane_off[plane];
         if (c == 1)
-            vn::vn_gather_f32_chw_vec_kernel<1><<<grid, 256, 0, st>>>(pbase, store->state_pitch, idx, n, h * w, out);
+            vn::vn_gather_f32_chw_vec_kernel<1><<<grid, 256, 0, st>>>(pbase, store->state_pitch, idx, idx_stride, n, h * w,
+                                                                      out);
         else
-            vn::vn_gather_f32_chw_vec_kernel<3><<<grid, 256, 0, st>>>(pbase, store->state_pitch, idx, n, h * w, out);
+            vn::vn_gather_f32_chw_vec_kernel<3><<<grid, 256, 0, st>>>(pbase, store->state_pitch, idx, idx_stride, n, h * w,
+                                                                      out);
         return vn::check_launch("vn_gather_f32_chw_vec_kernel");
     }
     const int smem = (h * w * c + 15) & ~15;
     VN_REQUIRE(smem <= 220 * 1024, "gather_plane_f32_chw: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_gather_f32_chw_kernel, smem);
     const int grid = n < 148 * 8 ? n : 148 * 8;
-    vn::vn_gather_f32_chw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, n, h, w,
-                                                                                        c, out);
+    vn::vn_gather_f32_chw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, idx_stride,
+                                                                                        n, h, w, c, out);
     return vn::check_launch("vn_gather_f32_chw_kernel");
+}
+
+int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t *leaves, int32_t n_leaves,
+                                 const int32_t *desc, int32_t n, int32_t h, int32_t w, void *stream) {
+    VN_REQUIRE(store && store->base && leaves && desc && n >= 0, "gather_leaves_f32_chw: null pointer");
+    VN_REQUIRE(n_leaves >= 1 && n_leaves <= vn::kMaxFloatLeaves, "gather_leaves_f32_chw: n_leaves=%d (max %d)", n_leaves,
+               vn::kMaxFloatLeaves);
+    if ((h * w) % 4 != 0) {
+        vn::set_error("gather_leaves_f32_chw: %d x %d pixels are not whole groups of 4 (use the per-leaf call)", h, w);
+        return VN_EUNSUPPORTED;
+    }
+    vn::FloatLeaves L;
+    L.n_leaves = n_leaves;
+    for (int l = 0; l < vn::kMaxFloatLeaves; ++l) {
+        L.pbase[l] = nullptr;
+        L.out[l] = nullptr;
+        L.c[l] = 1;
+        L.goal[l] = 0;
+    }
+    for (int l = 0; l < n_leaves; ++l) {
+        int32_t rc = check_plane(store, leaves[l].plane, h, w, leaves[l].channels, "gather_leaves_f32_chw");
+        if (rc) return rc;
+        if (leaves[l].channels != 1 && leaves[l].channels != 3) {
+            vn::set_error("gather_leaves_f32_chw: %d channels (use the per-leaf call)", leaves[l].channels);
+            return VN_EUNSUPPORTED;
+        }
+        VN_REQUIRE(leaves[l].out && (reinterpret_cast<uintptr_t>(leaves[l].out) & 15) == 0,
+                   "gather_leaves_f32_chw: out[%d] must be 16-byte aligned", l);
+        VN_REQUIRE(leaves[l].source == 0 || leaves[l].source == 1, "gather_leaves_f32_chw: source=%d", leaves[l].source);
+        L.pbase[l] = store->base + store->plane_off[leaves[l].plane];
+        L.out[l] = leaves[l].out;
+        L.c[l] = leaves[l].channels;
+        L.goal[l] = leaves[l].source;
+    }
+    if (n == 0) return VN_OK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    const int64_t total = (int64_t)n * (h * w / 4);
+    const int64_t want = (total + 255) / 256, cap = (int64_t)sms * 16;
+    vn::vn_gather_leaves_f32_kernel<<<(int)(want < cap ? want : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        L, store->state_pitch, reinterpret_cast<const int2 *>(desc), n, h * w);
+    return vn::check_launch("vn_gather_leaves_f32_kernel");
 }
 
 int32_t vn_rp_labels(const float *reward, int32_t n, int8_t *labels, int32_t *zero_idx, int32_t *nonzero_idx,

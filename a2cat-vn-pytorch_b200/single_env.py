@@ -64,7 +64,8 @@ class GraphEnv:
     def render(self, mode="rgbarray"):
         if mode != "rgbarray":
             raise Exception("Render mode %s is not supported" % mode)     # gym_graph/graph.py:93
-        return self._vec.obs_buf["rgb"][0].cpu().numpy()
+        from .vec_env import gather_plane
+        return gather_plane(self._vec.dw, "rgb", self._vec.obs_state)[0].cpu().numpy()
 
     def close(self):
         self._vec.close()

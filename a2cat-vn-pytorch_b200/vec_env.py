@@ -120,8 +120,9 @@ class GraphVecEnv:
         inject           optional (task [n_local, R] int32, start [n_local, R] int32 GLOBAL states) reset stream
         host_outputs     rewards / dones as numpy (reference behaviour) or as CUDA tensors
         scaled_float     observation leaves as float32 CHW in [0, 1] - what TransposeImage + ScaledFloatFrame
-                         (experiments/thor_cached_auxiliary.py:61-62) hand to the model - produced by one fused
-                         gather/convert kernel per leaf instead of the uint8 HWC batch
+                         (experiments/thor_cached_auxiliary.py:61-62) hand to the model - in persistent batches filled
+                         by one fused gather/convert kernel per leaf straight from the store (no uint8 batch is
+                         written; rows that did not change / goal rows of envs that did not reset are skipped)
         gather           "auto" | "ldg" | "bulk" | "fused" (include/vn_b200.h VN_GATHER_*); "auto" runs the whole step
                          as ONE fused launch for batches of at most one env per SM and as scalar kernel + bulk-copy
                          gather otherwise
@@ -192,8 +193,17 @@ class GraphVecEnv:
             self.actions_dev = i32()
             self._sched = torch.zeros(4, dtype=torch.int32, device=self.device)     # scheduler / completion counters
             self._gather_desc = torch.zeros((2, max(n, 1), 2), dtype=torch.int32, device=self.device)
-            self.obs_buf = {p: lay.batch(p, n, self.device) for p in self.obs_planes}
-            self.goal_buf = {p: lay.batch(p, n, self.device) for p in self.goal_planes}
+            if scaled_float:
+                # float mode: no uint8 batch at all - persistent float32 CHW batches, one per leaf, converted straight
+                # from the store after every step (only rows that changed; goal leaves only for envs that reset)
+                self.obs_buf, self.goal_buf = {}, {}
+                chw = lambda p: (n, lay.channels[lay.planes.index(p)], h, w)
+                self.float_buf = {("goal_" + p if g else p): torch.zeros(chw(p), dtype=torch.float32, device=self.device)
+                                  for g, ps in ((False, self.obs_planes), (True, self.goal_planes)) for p in ps}
+            else:
+                self.obs_buf = {p: lay.batch(p, n, self.device) for p in self.obs_planes}
+                self.goal_buf = {p: lay.batch(p, n, self.device) for p in self.goal_planes}
+                self.float_buf = {}
             self._pack_host = torch.zeros(n * 20, dtype=torch.uint8).pin_memory()
             self._actions_host = torch.zeros(n, dtype=torch.int32).pin_memory()
         self._inject_keep = None
@@ -263,6 +273,13 @@ class GraphVecEnv:
             if unreal_wrapper else inner
         self.action_space = spaces.Discrete(self.n_actions)
         self.set_hardness = self.set_complexity     # experiments/thor_cached_auxiliary.py:68
+        self._float_leaves = None
+        if self.float_buf and (h * w) % 4 == 0 and len(self.float_buf) <= 6 and \
+                all(b.shape[1] in (1, 3) for b in self.float_buf.values()):
+            self._float_leaves = (L.FloatLeaf * len(self.float_buf))(*[
+                L.FloatLeaf(lay.planes.index(name[5:] if name.startswith("goal_") else name),
+                            1 if name.startswith("goal_") else 0, buf.shape[1], 0, buf.data_ptr())
+                for name, buf in self.float_buf.items()])
         self._pending = False
         self._obs_cache = None
         self.closed = False
@@ -311,18 +328,39 @@ class GraphVecEnv:
 
     def _leaf(self, name):
         if self.scaled_float:
-            from . import rollout
-            if name.startswith("goal_"):
-                return rollout.policy_input(self.dw, self.goal, name[5:])
-            return rollout.policy_input(self.dw, self.obs_state, name)
+            return self.float_buf[name]
         return self.goal_buf[name[5:]] if name.startswith("goal_") else self.obs_buf[name]
 
     def _obs(self):
-        if not self.scaled_float:       # the leaves are the persistent batch buffers: build the structure once
-            if self._obs_cache is None:
-                self._obs_cache = self._build_obs()
-            return self._obs_cache
-        return self._build_obs()
+        if self._obs_cache is None:     # the leaves are persistent batch buffers: build the structure once
+            self._obs_cache = self._build_obs()
+        return self._obs_cache
+
+    def _convert_float_leaves(self, all_rows=False):
+        """Float mode: TransposeImage + ScaledFloatFrame (thor_cached_auxiliary.py:61-62) of the step just enqueued,
+        one launch per leaf, reading the step's gather descriptors (record or -1 = row unchanged; goal record or
+        -1 = no reset): rows that did not change are not converted again."""
+        if self.num_envs == 0:
+            return
+        lay = self.world.layout
+        h, w = lay.frame_hw
+        desc = self._gather_desc[self._calls & 1]
+        stream = self._stream()
+        if not all_rows and self._float_leaves is not None:
+            # one launch for every leaf (whole 4-pixel groups, 1- or 3-channel planes)
+            arr = self._float_leaves
+            self._call(self.lib.vn_gather_leaves_f32_chw, self._ref["store"], arr, len(arr), desc.data_ptr(),
+                       self.num_envs, h, w, stream)
+            return
+        for name, buf in self.float_buf.items():
+            goal = name.startswith("goal_")
+            pi = lay.planes.index(name[5:] if goal else name)
+            if all_rows:
+                idx, stride = (self.goal if goal else self.obs_state).data_ptr(), 1
+            else:
+                idx, stride = desc.data_ptr() + (4 if goal else 0), 2
+            self._call(self.lib.vn_gather_plane_f32_chw_rows, self._ref["store"], pi, idx, stride, self.num_envs, h, w,
+                       lay.channels[pi], buf.data_ptr(), stream)
 
     def _build_obs(self):
         lv = self.leaves
@@ -345,6 +383,8 @@ class GraphVecEnv:
         self._call(self.lib.vn_env_reset, r["store"], r["tables"], r["envs"], r["rules"],
                    C.byref(self._c_inject) if self._c_inject is not None else None,
                    L.ptr(m), r["out"], self.gather, self._stream())
+        if self.scaled_float:
+            self._convert_float_leaves()
         return self._obs()
 
     def _tick(self, out, flags):
@@ -375,6 +415,8 @@ class GraphVecEnv:
             self._call(self.lib.vn_env_step_host, r["store"], r["tables"], r["envs"], r["rules"], inj,
                        self._actions_host.data_ptr(), self.actions_dev.data_ptr(), r["out_host"], None,
                        self.gather, self._stream())
+            if self.scaled_float:
+                self._convert_float_leaves()
             self._pending = "host"
             return
         if torch.is_tensor(actions) and actions.is_cuda:
@@ -392,6 +434,8 @@ class GraphVecEnv:
         r = self._ref
         self._call(self.lib.vn_env_step, r["store"], r["tables"], r["envs"], r["rules"], inj, a.data_ptr(), r["out"],
                    self.gather, self._stream())
+        if self.scaled_float:
+            self._convert_float_leaves()
         self._pending = "device"
 
     def step_enqueue(self, actions, actions_ready=False):
@@ -467,7 +511,7 @@ class GraphVecEnv:
 
     def step(self, actions):
         if self.host_outputs and type(actions) is np.ndarray and not self._pending and not self.closed \
-                and actions.size == self.num_envs and self.num_envs:
+                and actions.size == self.num_envs and self.num_envs and not self.scaled_float:
             # the reference-facing call, numpy in / numpy out, as ONE C call: stage the actions, enqueue both
             # kernels, spin until the scalars are in pinned memory, copy them out (vn_env_step_host_sync)
             n = self.num_envs
@@ -572,6 +616,8 @@ class GraphVecEnv:
         for p, buf in self.goal_buf.items():
             gather_plane(self.dw, p, self.goal, out=buf, variant=self.gather)
         self.obs_state.copy_(self.state)       # the rows now hold the frames of `state` (skip_unchanged compares to it)
+        if self.scaled_float:
+            self._convert_float_leaves(all_rows=True)
         return self._obs()
 
 

@@ -465,6 +465,37 @@ def run_cuda(args):
                                  "ms_per_step": ms_r / Kr2, "algorithmic_bytes_per_env_step": 2 * F_RGB,
                                  "frac_if_every_row_were_copied": N * 2 * F_RGB / (ms_r * 1e-3 / Kr2) / 1e9 / peak}
         del env_r
+        # secondary line: float32 CHW observations in [0, 1] - what the reference's wrappers hand to its model
+        # (TransposeImage + ScaledFloatFrame, thor_cached_auxiliary.py:61-62) - converted straight from the store
+        # into persistent batches (no uint8 batch in this mode): 4 bytes written per byte read
+        env_f = vn.GraphVecEnv(world, n_total, device=dev, seed=4, max_episode_steps=MAX_EPISODE_STEPS,
+                               obs_layout=layout, unreal_wrapper=True, rank=rank, world_size=world_size,
+                               gather=args.gather, host_outputs=False, device_world=env.dw, scaled_float=True)
+        env_f.reset()
+        Kf = min(K, 2000)
+        for i in range(300 + W):
+            env_f.step_enqueue(actions[i % n_rows], actions_ready=True)
+        env_f.stats.zero_()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(Kf):
+            env_f.step_enqueue(actions[i % n_rows], actions_ready=True)
+        f1.record()
+        barrier()
+        ms_f = f0.elapsed_time(f1)
+        if world_size > 1:
+            t = torch.tensor([ms_f], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_f = float(t.item())
+        fs = env_f.episode_stats()
+        skip_f, reset_f = fs["rows_skipped"] / max(1.0, fs["steps"]), fs["resets"] / max(1.0, fs["steps"])
+        bytes_f = N * 5 * ((1 - skip_f) * F_OBS + reset_f * F_GOAL)
+        secondary["float_chw"] = {"value": n_total * Kf / (ms_f * 1e-3), "unit": "env-steps/s", "steps": Kf,
+                                  "ms_per_step": ms_f / Kf, "algorithmic_bytes_per_step": bytes_f,
+                                  "frac": bytes_f / (ms_f * 1e-3 / Kf) / 1e9 / peak,
+                                  "note": "float32 CHW leaves (rgb, goal, depth) / 255 in persistent batches"}
+        del env_f
 
     if args.quick:
         if rank == 0:

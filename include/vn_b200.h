@@ -188,7 +188,7 @@ typedef struct vn_step_out {
 
 int32_t vn_abi_version(void);
 /* sizeof of the descriptor structs as compiled into the library (0 store, 1 tables, 2 envs, 3 rules, 4 inject,
- * 5 step_out, 6 replay; -1 otherwise): a binding checks its mirrors against these at load time. */
+ * 5 step_out, 6 replay, 7 float_leaf; -1 otherwise): a binding checks its mirrors against these at load time. */
 int32_t vn_abi_struct_size(int32_t which);
 const char *vn_last_error(void);
 /* Kernels enqueued by the library so far (process-wide, monotonically increasing; statistics only). */
@@ -267,6 +267,27 @@ int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *i
  * fused with the gather: out[i] = float32 CHW of plane / 255. */
 int32_t vn_gather_plane_f32_chw(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, int32_t h,
                                 int32_t w, int32_t c, float *out, void *stream);
+/* The same into a PERSISTENT float batch: row i is rewritten from record idx[i * idx_stride] unless that entry is
+ * negative.  With idx = gather_desc of the step just enqueued (stride 2; + 1 for the goal record) only the rows
+ * whose observation changed - and only the goal rows of envs that reset - are converted again. */
+int32_t vn_gather_plane_f32_chw_rows(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t idx_stride,
+                                     int32_t n, int32_t h, int32_t w, int32_t c, float *out, void *stream);
+
+/* All float leaves of one step in ONE launch (the observation tuple the reference's wrappers produce,
+ * thor_cached_auxiliary.py:59-64): leaf l is plane leaves[l].plane of the observation record (source 0) or of the
+ * goal record (source 1) named by desc[i] = (record or -1, goal record or -1) - the gather_desc half of the step
+ * just enqueued - written as float32 CHW / 255 into row i of the persistent batch leaves[l].out; negative records
+ * leave the row untouched.  VN_EUNSUPPORTED when H * W is not a multiple of 4 or a plane has neither 1 nor 3
+ * channels (use vn_gather_plane_f32_chw_rows per leaf then).  At most 6 leaves. */
+typedef struct vn_float_leaf {
+    int32_t plane;
+    int32_t source;   /* 0 observation record, 1 goal record */
+    int32_t channels; /* 1 or 3 */
+    int32_t reserved;
+    float *out;       /* [n][channels][h][w] */
+} vn_float_leaf_t;
+int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t *leaves /* [host] */, int32_t n_leaves,
+                                 const int32_t *desc /* [n][2] */, int32_t n, int32_t h, int32_t w, void *stream);
 
 /* A2C n-step returns (deep_rl RolloutStorage.batch):
  *   R_T = (1 - done[T-1]) * last_value;  R_t = reward[t] + gamma * (1 - done[t]) * R_{t+1}.

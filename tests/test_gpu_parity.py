@@ -465,18 +465,22 @@ def test_thor_cached_single_env_returns_previous_obs_on_terminal():
     assert np.array_equal(ob[0], frames[s0])             # previous observation, not the goal frame
 
 
-def test_scaled_float_observation_mode():
-    """scaled_float=True: leaves are what TransposeImage + ScaledFloatFrame produce (float32 CHW / 255)."""
+@pytest.mark.parametrize("N", [8, 300])
+def test_scaled_float_observation_mode(N):
+    """scaled_float=True: leaves are what TransposeImage + ScaledFloatFrame produce (float32 CHW / 255), kept in
+    persistent batches that are filled straight from the store (rows that did not change are skipped, goal leaves
+    are converted only for envs that reset; no uint8 batch exists in this mode)."""
     import torch
     scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2)
     world = T.compile_world([scene], T.GYM_GRAPH)
-    a = vn.GraphVecEnv(world, 8, seed=1, max_episode_steps=9)
-    b = vn.GraphVecEnv(world, 8, seed=1, max_episode_steps=9, scaled_float=True, device_world=a.dw)
+    a = vn.GraphVecEnv(world, N, seed=1, max_episode_steps=9)
+    b = vn.GraphVecEnv(world, N, seed=1, max_episode_steps=9, scaled_float=True, device_world=a.dw)
     assert b.observation_space.spaces[0].spaces[0].shape == (3, 84, 84)       # thor_cached_auxiliary.py:55
+    assert not b.obs_buf and not b.goal_buf and len(b.float_buf) == 5
     (oa, _), (ob, _) = a.reset(), b.reset()
     rng = np.random.RandomState(0)
     for _ in range(25):
-        act = rng.randint(0, 4, 8)
+        act = rng.randint(0, 4, N)
         (oa, _), _, _, _ = a.step(act)
         (ob, _), _, _, _ = b.step(act)
         for x, y in zip(oa, ob):
@@ -484,6 +488,14 @@ def test_scaled_float_observation_mode():
             # by a rounded reciprocal and differs in the last bit for 126 of the 256 byte values)
             want = np.stack([ovec.transpose_scale(f) for f in x.cpu().numpy()])
             assert y.dtype == torch.float32 and np.array_equal(y.cpu().numpy(), want)
+    assert b.episode_stats() == a.episode_stats() and b.episode_stats()["rows_skipped"] > 0
+    # a checkpoint round trip refreshes the float batches
+    sd = b.state_dict()
+    for buf in b.float_buf.values():
+        buf.zero_()
+    b.load_state_dict(sd)
+    for x, y in zip(oa, b._obs()[0]):
+        assert np.array_equal(y.cpu().numpy(), np.stack([ovec.transpose_scale(f) for f in x.cpu().numpy()]))
 
 
 def test_edge_cases_empty_ragged_and_errors():
