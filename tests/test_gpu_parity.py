@@ -928,3 +928,71 @@ def test_evaluation_service_success_rate_and_spl():
     sched = E.LinearSchedule(0.3, 1.0, 200000)                       # thor_cached_auxiliary.py:45
     assert sched(0) == 0.3 and abs(sched(100000) - 0.65) < 1e-12 and sched(10 ** 7) == 1.0
     assert E.apply_hardness_schedule(env, sched, 50000) == sched(50000) and env.dw.complexity == sched(50000)
+
+
+@pytest.mark.parametrize("case", range(10))
+def test_randomised_configurations_against_oracle(case):
+    """Differential fuzz: random maze, family, goals, batch size, time limit, reward triple, curriculum schedule,
+    launch mode and row skipping - every step compared with the oracle envs driven by the same Philox reset
+    stream (states, float bits of rewards and last_action_reward, dones, observation bytes, info keys)."""
+    rng = np.random.RandomState(1000 + case)
+    oriented = bool(rng.randint(2))
+    shape = (int(rng.randint(4, 12)), int(rng.randint(4, 12)))
+    n_goals = int(rng.randint(1, 4))
+    planes = ("rgb", "depth", "segmentation") if oriented else ("rgb",)
+    scene = H.scenes.make_maze_scene(shape, float(rng.uniform(0.05, 0.35)), int(rng.randint(1 << 20)), n_goals=n_goals,
+                                     oriented=oriented, planes=planes)
+    if scene.n_cells < 3:
+        pytest.skip("degenerate maze")
+    fam = T.GYM_GRAPH if oriented else T.SIMPLE_GRAPH
+    world = T.compile_world([scene], fam)
+    osc = oenvs.OracleScene(scene)
+    N = int(rng.choice([1, 2, 7, 33, 150, 260]))
+    limit = int(rng.randint(2, 40))
+    rewards = tuple(float(x) for x in rng.choice([1.0, 0.0, -0.01, 0.5, -1.0, 2.0], 3))
+    seed = int(rng.randint(1 << 30))
+    gather = str(rng.choice(["auto", "bulk", "ldg", "fused"] if N <= 148 else ["auto", "bulk", "ldg"]))
+    skip = bool(rng.randint(2))
+    goals = list(scene.goals)
+    env_tasks = np.tile(np.array([[0, len(goals)]], np.int32), (N, 1)) if oriented else None
+    env = vn.GraphVecEnv(world, N, seed=seed, max_episode_steps=limit, rewards=rewards, gather=gather,
+                         skip_unchanged=skip, obs_layout="aux5" if oriented else "frame", env_tasks=env_tasks)
+    oes = []
+    for i in range(N):
+        if oriented:
+            e = oenvs.GymGraphAuxiliaryEnv(osc, goals=goals, rewards=rewards)
+            cands = [gu.initial_state_candidates(scene.maze, osc.graph, osc.optimal_actions, gl) for gl in goals]
+            e.reset_source = ovec.PhiloxResetSource(seed, i, cands, lambda t, e=e: e.optimal_distance(), False)
+        else:
+            gl = goals[i % len(goals)]                    # default env_tasks: one task per env, round-robin
+            e = oenvs.SimpleGraphEnv(osc, goal=gl, rewards=rewards)
+            cands = [gu.initial_position_candidates(scene.maze, osc.graph, gl)]
+            e.reset_source = ovec.PhiloxResetSource(seed, i, cands, lambda t, e=e: e.optimal_distance(), True)
+        oes.append(ovec.RewardCollector(ovec.TimeLimit(e, limit)))
+    ov = ovec.VecEnv(oes)
+    c0 = None if rng.randint(3) == 0 else float(rng.uniform(0.0, 1.0))
+    env.set_complexity(c0)
+    [e.set_complexity(c0) for e in oes]
+    (obs, lar), (oobs, olar) = env.reset(), ov.reset()
+    for t in range(120):
+        if t and t % 37 == 0:                             # the curriculum moves while episodes are running
+            c = None if rng.randint(4) == 0 else float(rng.uniform(0.0, 1.0))
+            env.set_complexity(c)
+            [e.set_complexity(c) for e in oes]
+        a = rng.randint(0 if oriented else -1, 4, size=N)
+        (obs, lar), rew, done, infos = env.step(a)
+        (oobs, olar), orew, odone, oinfos = ov.step(a)
+        assert np.array_equal(done, odone), (case, t)
+        assert np.array_equal(f32bits(rew), f32bits(orew)), (case, t)
+        assert np.array_equal(f32bits(lar.cpu().numpy()), f32bits(olar)), (case, t)
+        assert [oe.state for oe in oes] == env.states(), (case, t)
+        leaves = obs if isinstance(obs, tuple) else (obs,)
+        oleaves = oobs if isinstance(oobs, tuple) else (oobs,)
+        for x, y in zip(leaves, oleaves):
+            y = y if y.dtype == np.uint8 else np.rint(y * 255).astype(np.uint8)
+            assert np.array_equal(x.cpu().numpy(), y), (case, t)
+        for i in (0, N // 2, N - 1):
+            info, oinfo = infos[i], oinfos[i]
+            assert info.get("episode") == oinfo.get("episode"), (case, t, i)
+            assert info.get("TimeLimit.truncated") == oinfo.get("TimeLimit.truncated"), (case, t, i)
+            assert info.get("state") == oinfo.get("state") and info.get("win") == oinfo.get("win"), (case, t, i)
