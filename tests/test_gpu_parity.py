@@ -996,3 +996,39 @@ def test_randomised_configurations_against_oracle(case):
             assert info.get("episode") == oinfo.get("episode"), (case, t, i)
             assert info.get("TimeLimit.truncated") == oinfo.get("TimeLimit.truncated"), (case, t, i)
             assert info.get("state") == oinfo.get("state") and info.get("win") == oinfo.get("win"), (case, t, i)
+
+
+def test_host_facing_c_abi_failure_paths():
+    """vn_env_step_host / vn_host_wait_seq fail loudly instead of hanging or faulting: pageable host buffers are
+    refused, a sequence word that never arrives ends the wait once the stream has drained, and the explicit FUSED
+    variant refuses records that do not fit in shared memory."""
+    import ctypes as C
+    import torch
+    L = vn.lib
+    lib = L.load()
+    scene = H.scenes.make_maze_scene((6, 6), 0.1, 1, n_goals=1, planes=("rgb",))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    env = vn.GraphVecEnv(world, 5, seed=1, obs_layout="frame")
+    env.reset()
+    stream = torch.cuda.current_stream().cuda_stream
+    pageable = np.zeros(5, np.int32)
+    rc = lib.vn_env_step_host(C.byref(env.dw.store), C.byref(env.dw.tables), C.byref(env._c_envs), C.byref(env._c_rules),
+                              None, pageable.ctypes.data, None, C.byref(env._c_out_host), None, env.gather, stream)
+    assert rc == -1 and b"pinned" in lib.vn_last_error()
+    # nothing was enqueued: the env still steps normally afterwards
+    _, r, d, _ = env.step(np.zeros(5, np.int32))
+    assert r.shape == (5,)
+    # a word nobody will ever publish: the wait notices that the stream is idle and returns an error
+    torch.cuda.synchronize()
+    never = (env._seq + 12345) & 0x7FFFFFFF
+    rc = lib.vn_host_wait_seq(env._seq_host.data_ptr(), env._seq_words, never, stream, 5_000_000)
+    assert rc == -2 and b"drained" in lib.vn_last_error()
+    # 174 x 174 x (rgb + depth + segmentation) = 212 KB per record: too large for the fused launch when asked explicitly
+    big = H.scenes.make_maze_scene((5, 5), 0.0, 1, n_goals=1, frame_hw=(174, 174))
+    wbig = T.compile_world([big], T.GYM_GRAPH)
+    with pytest.raises(L.VnError, match="fused"):
+        vn.GraphVecEnv(wbig, 4, obs_layout="aux5", gather="fused")
+    ok = vn.GraphVecEnv(wbig, 4, obs_layout="aux5", gather="auto")       # AUTO falls back to two launches
+    ok.reset()
+    ok.step(np.zeros(4, np.int32))
+    assert ok.kernel_launches == 4
