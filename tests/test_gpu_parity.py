@@ -1032,3 +1032,39 @@ def test_host_facing_c_abi_failure_paths():
     ok.reset()
     ok.step(np.zeros(4, np.int32))
     assert ok.kernel_launches == 4
+
+
+def test_cuda_graph_replays_with_an_odd_number_of_steps():
+    """Back-to-back replays of a graph with an ODD number of steps, and eager pipelined steps right after a replay:
+    the descriptor parity of the last captured step then equals that of the next first step, so that step must not
+    overlap the previous gather (it runs in serial mode).  Large batch so that a gather is long enough to race."""
+    import torch
+    scene = H.scenes.make_thor_scene(150, (16, 20), seed=1, n_goals=3, planes=("rgb", "depth"))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    N, S = 4096, 5
+    a = vn.GraphVecEnv(world, N, seed=2, max_episode_steps=6, host_outputs=False, obs_layout="rgbd_goal")
+    b = vn.GraphVecEnv(world, N, seed=2, max_episode_steps=6, host_outputs=False, obs_layout="rgbd_goal",
+                       device_world=a.dw)
+    a.reset()
+    b.reset()
+    acts = torch.randint(0, 4, (S, N), device="cuda", dtype=torch.int32)
+    extra = torch.randint(0, 4, (3, N), device="cuda", dtype=torch.int32)
+    cap = b.capture_steps(acts)
+    for rep in range(12):
+        for t in range(S):
+            a.step_enqueue(acts[t])
+        cap.replay()
+        if rep % 3 == 2:                      # eager pipelined steps straight after a replay
+            for t in range(3):
+                a.step_enqueue(extra[t])
+                b.step_enqueue(extra[t], actions_ready=True)
+        if rep % 4 == 3:
+            torch.cuda.synchronize()
+            assert torch.equal(a.state, b.state) and torch.equal(a._pack, b._pack)
+            for x, y in zip(list(a.obs_buf.values()) + list(a.goal_buf.values()),
+                            list(b.obs_buf.values()) + list(b.goal_buf.values())):
+                assert torch.equal(x, y)
+            s = b.state.long()
+            assert torch.equal(b.obs_buf["rgb"], b.dw.plane_view("rgb")[s])
+            assert torch.equal(b.goal_buf["rgb"], b.dw.plane_view("rgb")[b.goal.long()])
+    assert a.episode_stats() == b.episode_stats()
