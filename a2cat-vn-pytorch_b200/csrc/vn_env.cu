@@ -132,6 +132,9 @@ __device__ __forceinline__ void step_env(const StepParams &p, const int i, EnvSt
         const uint8_t trunc_code = at_limit ? (trunc ? 1 : 2) : 0;
         if (p.out.reward) p.out.reward[i] = r;
         if (p.out.done) p.out.done[i] = done;
+        if (p.out.rec_action) p.out.rec_action[i] = a;
+        if (p.out.rec_reward) p.out.rec_reward[i] = r;
+        if (p.out.rec_done) p.out.rec_done[i] = done;
         if (p.out.truncated) p.out.truncated[i] = trunc_code;
         if (p.out.win) p.out.win[i] = terminal;
         if (p.out.info_state) p.out.info_state[i] = s;
@@ -216,6 +219,10 @@ __device__ __forceinline__ void step_env(const StepParams &p, const int i, EnvSt
     p.env.ep_length[i] = ep_len;
     p.out.obs_state[i] = obs_s;
     if (p.out.did_reset) p.out.did_reset[i] = do_reset;
+    if (!kReset) {  // rollout record of this step (RolloutStorage.insert without copy kernels)
+        if (p.out.rec_state) p.out.rec_state[i] = obs_s;
+        if (p.out.rec_goal) p.out.rec_goal[i] = g;
+    }
     // the batch row of an env whose record did not change (collision, no-op) already holds the right frames
     const bool same = may_skip && obs_s == prev_obs;
     st.skipped = same;

@@ -60,7 +60,8 @@ class StepOut(C.Structure):
                 ("truncated", _P), ("win", _P), ("did_reset", _P), ("last_action_reward", _P),
                 ("episode_return", _P), ("episode_length", _P), ("info_state", _P), ("obs_state", _P), ("stats", _P),
                 ("gather_desc", _P), ("parity", C.c_int32), ("flags", C.c_int32), ("sched", _P), ("host_pack", _P),
-                ("host_seq", _P), ("seq", C.c_uint32), ("reserved", C.c_uint32)]
+                ("host_seq", _P), ("seq", C.c_uint32), ("reserved", C.c_uint32),
+                ("rec_action", _P), ("rec_reward", _P), ("rec_done", _P), ("rec_state", _P), ("rec_goal", _P)]
 
 
 class Replay(C.Structure):

@@ -255,6 +255,16 @@ class RolloutBuffer:
         self.goals[t + 1].copy_(env.goal)
         self.t = t + 1
 
+    def step(self, env, actions, actions_ready=False):
+        """``env.step_enqueue(actions)`` + ``insert`` in one: the step kernel writes (action, reward, done, next
+        state, next goal) straight into row ``t`` of this buffer (vn_step_out_t.rec_*), no copy kernels."""
+        t = self.t
+        if not (torch.is_tensor(actions) and actions.is_cuda and actions.dtype == torch.int32):
+            raise ValueError("RolloutBuffer.step needs CUDA int32 actions")
+        env.step_enqueue(actions, actions_ready,
+                         record=(self.actions[t], self.rewards[t], self.dones[t], self.states[t + 1], self.goals[t + 1]))
+        self.t = t + 1
+
     def returns(self, last_values, gamma):
         """[B, T] n-step returns."""
         return nstep_returns(self.rewards, self.dones, last_values, gamma, time_major=True).t().contiguous()

@@ -456,11 +456,22 @@ class GraphVecEnv:
             self._convert_float_leaves()
         self._pending = "device"
 
-    def step_enqueue(self, actions, actions_ready=False):
+    def step_enqueue(self, actions, actions_ready=False, record=None):
         """Device-resident loops: enqueue one vectorised step for CUDA int32 ``actions`` and return at once.
         Nothing is copied to the host; ``env.reward`` / ``env.done`` / the observation buffers hold the
-        results in stream order.  See step_async for ``actions_ready``."""
-        self.step_async(actions, actions_ready)
+        results in stream order.  See step_async for ``actions_ready``.  ``record`` = (actions, rewards, dones,
+        next_states, next_goals) CUDA tensors of ``num_envs`` elements (int32, float32, uint8, int32, int32; any may
+        be None) that the step kernel fills as well - a rollout storage row written without copy kernels
+        (``RolloutBuffer.step``)."""
+        if record is not None:
+            o = self._c_out
+            o.rec_action, o.rec_reward, o.rec_done, o.rec_state, o.rec_goal = (L.ptr(t) for t in record)
+            try:
+                self.step_async(actions, actions_ready)
+            finally:
+                o.rec_action = o.rec_reward = o.rec_done = o.rec_state = o.rec_goal = None
+        else:
+            self.step_async(actions, actions_ready)
         self._pending = False
 
     def capture_steps(self, actions, after_step=None):

@@ -3,7 +3,7 @@
 public API only, as a trainer in the style of deep_rl's A2C loop would use it:
 
     env.reset() / env.step(actions)          GraphVecEnv (device-resident: host_outputs=False)
-    RolloutBuffer.start / insert / returns    n-step discounted returns on the device
+    RolloutBuffer.start / step / returns      the step writes the rollout row; n-step returns on the device
     rollout.policy_input                      gather + TransposeImage + ScaledFloatFrame in one kernel
     env.set_hardness                          the reference's curriculum (thor_cached_auxiliary.py:68-70)
     env.episode_stats                         RewardCollector-style statistics, accumulated on the device
@@ -72,8 +72,7 @@ def train(updates=400, num_envs=16, n_step=5, gamma=0.99, lr=7e-4, seed=0, hardn
             for _ in range(n_step):
                 logits, _ = model(vn.rollout.policy_input(env.dw, env.obs_state))
                 a = torch.distributions.Categorical(logits=logits).sample().to(torch.int32)
-                env.step_enqueue(a)
-                buf.insert(env, a)
+                buf.step(env, a)                # env step + rollout row in the same launch
             _, last_v = model(vn.rollout.policy_input(env.dw, env.obs_state))
         returns = buf.returns(last_v, gamma)                                # [B, T]
         x = vn.rollout.policy_input(env.dw, buf.states[:-1].t().contiguous())      # [B, T, 3, 84, 84]

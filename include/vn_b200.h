@@ -176,6 +176,13 @@ typedef struct vn_step_out {
                                          the two halves, so the gather stays programmatically chained to the scalar half */
     uint32_t seq;                     /* value to store; the caller changes it every call */
     uint32_t reserved;
+    /* Optional rollout record of this step, [n_envs] each, typically row t of a caller-owned [T, n_envs] rollout
+     * storage (deep_rl RolloutStorage.insert): written by the step itself instead of by copy kernels afterwards. */
+    int32_t *rec_action;              /* the action taken */
+    float *rec_reward;                /* = reward */
+    uint8_t *rec_done;                /* = done */
+    int32_t *rec_state;               /* state whose frames the NEXT observation shows (= obs_state, post auto-reset) */
+    int32_t *rec_goal;                /* goal state of the next observation's episode */
 } vn_step_out_t;
 
 /* gather kernel variants (all bit-identical) */

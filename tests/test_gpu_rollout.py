@@ -228,3 +228,32 @@ def test_replay_ring_sampling(dw):
     assert torch.equal(fr[3, 2], dw.plane_view("rgb")[int(smp["states"][3, 2])])
     ff = ring.frames(smp, "rgb", scaled_float=True)
     assert ff.shape == (N, 7, 3, 84, 84)
+
+
+@pytest.mark.parametrize("N", [16, 600])
+def test_rollout_buffer_step_records_without_copy_kernels(dw, N):
+    """RolloutBuffer.step: the step kernel writes the rollout row itself (vn_step_out_t.rec_*); identical to
+    step_enqueue + insert, with one launch pair per step and no copy kernels."""
+    import torch
+    Tn = 9
+    a = vn.GraphVecEnv(dw.world, N, seed=5, max_episode_steps=7, device_world=dw, host_outputs=False)
+    b = vn.GraphVecEnv(dw.world, N, seed=5, max_episode_steps=7, device_world=dw, host_outputs=False)
+    a.reset()
+    b.reset()
+    ba, bb = vn.rollout.RolloutBuffer(dw, N, Tn), vn.rollout.RolloutBuffer(dw, N, Tn)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for rollout in range(3):
+        ba.start(a)
+        bb.start(b)
+        launched = 0
+        for _ in range(Tn):
+            act = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+            a.step_enqueue(act)
+            ba.insert(a, act)
+            l0 = b.kernel_launches              # process-wide counter: look at b's call only
+            bb.step(b, act)
+            launched += b.kernel_launches - l0
+        assert launched == Tn * (1 if N <= 148 else 2)
+        for name in ("states", "goals", "rewards", "dones", "actions"):
+            assert torch.equal(getattr(ba, name), getattr(bb, name)), name
+    assert ba.dones.sum() > 0

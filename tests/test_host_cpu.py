@@ -160,7 +160,7 @@ def test_library_exports_every_declared_symbol():
     # struct sizes agree with the header (guards the ctypes mirrors)
     assert ctypes.sizeof(L.Store) == 8 + 8 + 4 + 4 + 24 + 24
     assert ctypes.sizeof(L.Rules) == 40 and ctypes.sizeof(L.Inject) == 24
-    assert ctypes.sizeof(L.StepOut) == 8 * (6 + 6 + 15 + 2)
+    assert ctypes.sizeof(L.StepOut) == 8 * (6 + 6 + 15 + 2 + 5)
 
 
 def test_product_never_imports_the_oracle():
