@@ -318,6 +318,30 @@ class ReplayRing:
         self.head = (h + 1) % self.cap
         self.count = min(self.count + 1, self.cap)
 
+    def extend(self, buf):
+        """Appends the ``buf.t`` steps of a RolloutBuffer in bulk (same result as ``insert`` after every step of that
+        rollout): at most two copies per array and rollout instead of seven copy kernels per step."""
+        T = buf.t
+        if T == 0:
+            return
+        if T > self.cap:
+            raise ValueError("rollout of %d steps does not fit a replay ring of %d" % (T, self.cap))
+        src = dict(before=buf.states[:T], after=buf.states[1:T + 1], goal=buf.goals[1:T + 1], action=buf.actions[:T],
+                   reward=buf.rewards[:T], done=buf.dones[:T])
+        h = self.head
+        first = min(T, self.cap - h)
+        for name, rows in src.items():
+            dst = getattr(self, name)
+            dst[h:h + first].copy_(rows[:first])
+            if first < T:
+                dst[:T - first].copy_(rows[first:])
+        if self._prev is None:
+            self._prev = buf.states[T].clone()
+        else:
+            self._prev.copy_(buf.states[T])
+        self.head = (h + T) % self.cap
+        self.count = min(self.count + T, self.cap)
+
     def _sample(self, length, mode):
         lib = L.load()
         Lw = 4 if mode == 1 else length

@@ -257,3 +257,28 @@ def test_rollout_buffer_step_records_without_copy_kernels(dw, N):
         for name in ("states", "goals", "rewards", "dones", "actions"):
             assert torch.equal(getattr(ba, name), getattr(bb, name)), name
     assert ba.dones.sum() > 0
+
+
+def test_replay_ring_bulk_extend_equals_per_step_insert(dw):
+    """ReplayRing.extend(rollout_buffer) == insert() after every step, across the ring's wrap-around."""
+    import torch
+    N, Tn, cap = 24, 7, 20
+    env = vn.GraphVecEnv(dw.world, N, seed=9, max_episode_steps=5, device_world=dw, host_outputs=False)
+    env.reset()
+    buf = vn.rollout.RolloutBuffer(dw, N, Tn)
+    r1 = vn.rollout.ReplayRing(dw, N, capacity=cap, seed=3)
+    r2 = vn.rollout.ReplayRing(dw, N, capacity=cap, seed=3)
+    r1.start(env)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for rollout in range(5):                      # 35 steps through a ring of 20: wraps twice
+        buf.start(env)
+        for _ in range(Tn):
+            act = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
+            buf.step(env, act)
+            r1.insert(env, act)
+        r2.extend(buf)
+        assert (r1.head, r1.count) == (r2.head, r2.count)
+        for name in ("before", "after", "goal", "action", "reward", "done"):
+            assert torch.equal(getattr(r1, name), getattr(r2, name)), (rollout, name)
+    s1, s2 = r1.sample_rp_sequence(), r2.sample_rp_sequence()
+    assert all(torch.equal(s1[k], s2[k]) for k in s1)
