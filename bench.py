@@ -496,6 +496,44 @@ def run_cuda(args):
                                   "frac": bytes_f / (ms_f * 1e-3 / Kf) / 1e9 / peak,
                                   "note": "float32 CHW leaves (rgb, goal, depth) / 255 in persistent batches"}
         del env_f
+        # secondary line: one whole A2C / UNREAL data pass as the trainer sees it (thor_cached_auxiliary.py:30-42:
+        # num_steps = 20): 20 vectorised steps that write their rollout rows themselves, then n-step returns,
+        # pixel-control rewards + their back-up and reward-prediction labels, all on the device
+        R = vn.rollout
+        T_roll = 20
+        rb = R.RolloutBuffer(env.dw, N, T_roll)
+        v_last = torch.randn(N, device=dev)
+        q_last = torch.rand(N, 400, device=dev)
+        R.target_tables(env.dw, 4, (20, 20))                # per-world pixel-control table, built once
+
+        def a2c_pass(i0):
+            rb.start(env)
+            for t in range(T_roll):
+                rb.step(env, actions[(i0 + t) % n_rows], actions_ready=True)
+            ret = rb.returns(v_last, 0.99)
+            pc = rb.pixel_control(4, (20, 20))
+            pcr = R.discounted_backup(pc.view(N, T_roll, 400), rb.dones.t().contiguous(), q_last, 0.9)
+            return ret, pcr, rb.reward_prediction()
+
+        for i in range(5):
+            a2c_pass(i * T_roll)
+        Kp = 100
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(Kp):
+            a2c_pass(i * T_roll)
+        p1.record()
+        barrier()
+        ms_p = p0.elapsed_time(p1)
+        if world_size > 1:
+            t = torch.tensor([ms_p], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_p = float(t.item())
+        secondary["a2c_pass"] = {"value": n_total * T_roll * Kp / (ms_p * 1e-3), "unit": "env-steps/s",
+                                 "ms_per_pass": ms_p / Kp, "num_steps": T_roll,
+                                 "note": "20 env steps (rollout rows written by the step kernel) + n-step returns + "
+                                         "pixel-control rewards and back-up + RP labels, per pass"}
 
     if args.quick:
         if rank == 0:
