@@ -840,7 +840,7 @@ static int32_t run_fused(const vn_store_t *store, const vn_tables_t *tab, const 
 
 // -1: error already set; 0: two launches; > 0: fused, shared memory bytes
 static int32_t choose_fused(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant) {
-    if (variant != VN_GATHER_FUSED && !(variant == VN_GATHER_AUTO && envs->n_envs <= sm_count())) return 0;
+    if (variant != VN_GATHER_FUSED && variant != VN_GATHER_AUTO) return 0;
     static const bool off = getenv("VN_NO_FUSED") && atoi(getenv("VN_NO_FUSED"));
     if (off && variant == VN_GATHER_AUTO) return 0;
     if (!out) return 0;  // reported by the parameter checks
@@ -850,6 +850,13 @@ static int32_t choose_fused(const vn_store_t *store, const vn_envs_t *envs, cons
         set_error("gather(fused): a %lld-byte record (x2 with goal planes) exceeds shared memory",
                   (long long)store->state_pitch);
         return -1;
+    }
+    if (variant == VN_GATHER_AUTO) {
+        // one wave of CTAs: as many envs as fit at once (shared memory bound), at most 4 per SM - beyond that the
+        // step is no longer bound by launch latency and the two-kernel path (pipelined, bandwidth-tuned) wins
+        static const int env_waves = getenv("VN_FUSED_PER_SM") ? atoi(getenv("VN_FUSED_PER_SM")) : 4;
+        const int per_sm = max(1, min(env_waves, (220 * 1024) / (smem + 1024)));
+        if (envs->n_envs > sm_count() * per_sm) return 0;
     }
     return smem;
 }

@@ -190,8 +190,9 @@ typedef struct vn_step_out {
 #define VN_GATHER_LDG 1      /* 16-byte vector loads/stores through registers */
 #define VN_GATHER_BULK 2     /* cp.async.bulk (TMA engine) global->shared->global, mbarrier-tracked */
 #define VN_GATHER_FUSED 3    /* vn_env_reset / vn_env_step / vn_env_step_host as ONE launch (CTA per env: scalar half, then
-                                bulk copies); what VN_GATHER_AUTO picks for batches of at most one env per SM, where the
-                                step is bound by launch latency.  Elsewhere it means VN_GATHER_BULK. */
+                                bulk copies); what VN_GATHER_AUTO picks for batches that fit in one wave of CTAs (as many
+                                envs per SM as shared memory holds records, at most 4), where the step is bound by launch
+                                latency.  Elsewhere it means VN_GATHER_BULK. */
 
 int32_t vn_abi_version(void);
 /* sizeof of the descriptor structs as compiled into the library (0 store, 1 tables, 2 envs, 3 rules, 4 inject,
