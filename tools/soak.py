@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Long device-resident runs with invariant checks (development aid; needs a B200): after every block of steps the
+observation / goal batches must equal the store rows of the env states, in uint8 and float mode, pipelined, with row
+skipping, across CUDA-graph replays.  Prints one line per configuration."""
+import importlib
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(steps=200000, block=5000):
+    import torch
+    vn = importlib.import_module("a2cat-vn-pytorch_b200")
+    scene = vn.scenes.make_thor_scene(400, (30, 30), seed=3, n_goals=4, planes=("rgb", "depth", "segmentation"))
+    world = vn.compile_world([scene], vn.GYM_GRAPH)
+    dw = vn.DeviceWorld(world)
+    for name, n, kw in (("uint8 aux5 pipelined", 2048, dict(obs_layout="aux5")),
+                        ("float rgbd_goal", 1024, dict(obs_layout="rgbd_goal", scaled_float=True)),
+                        ("fused 200 envs", 200, dict(obs_layout="aux5")),
+                        ("hardness 0.01 (reset-heavy)", 4096, dict(obs_layout="rgbd_goal"))):
+        env = vn.GraphVecEnv(world, n, seed=11, max_episode_steps=37, host_outputs=False, device_world=dw, **kw)
+        if "hardness" in name:
+            env.set_hardness(0.01)
+        env.reset()
+        acts = torch.randint(0, 4, (1024, n), device="cuda", dtype=torch.int32)
+        t0 = time.perf_counter()
+        for b0 in range(0, steps, block):
+            for i in range(block):
+                env.step_enqueue(acts[(b0 + i) % 1024], actions_ready=True)
+            torch.cuda.synchronize()
+            s, g = env.state.long(), env.goal.long()
+            if env.scaled_float:
+                want = vn.rollout.policy_input(dw, env.state, "rgb")
+                assert torch.equal(env.float_buf["rgb"], want)
+                assert torch.equal(env.float_buf["goal_rgb"], vn.rollout.policy_input(dw, env.goal, "rgb"))
+            else:
+                for p, buf in env.obs_buf.items():
+                    assert torch.equal(buf, dw.plane_view(p)[s]), (name, p, b0)
+                for p, buf in env.goal_buf.items():
+                    assert torch.equal(buf, dw.plane_view(p)[g]), (name, p, b0)
+            assert torch.equal(env.goal, dw.task_goal[env.task.long()])
+        st = env.episode_stats()
+        assert st["steps"] == steps * n and st["episodes"] == st["resets"] - n
+        print("%-28s %d envs x %d steps ok: %.0f episodes, %.1f %% rows skipped, %.1f M env-steps/s incl. checks"
+              % (name, n, steps, st["episodes"], 100 * st["rows_skipped"] / st["steps"],
+                 steps * n / (time.perf_counter() - t0) / 1e6))
+
+
+if __name__ == "__main__":
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 200000)
