@@ -123,7 +123,7 @@ class GraphVecEnv:
     def __init__(self, world, num_envs, *, device="cuda", seed=0, max_episode_steps=900, rewards=(1.0, 0.0, 0.0),
                  obs_layout="aux5", unreal_wrapper=True, env_tasks=None, auto_reset=True, rank=0, world_size=1,
                  gather="auto", inject=None, host_outputs=True, device_world=None, scaled_float=False,
-                 episode_info=True, skip_unchanged=True):
+                 episode_info=True, skip_unchanged=True, numpy_obs=False):
         """
         world            tables.World (compiled scenes) - or pass a ready ``device_world``
         num_envs         TOTAL number of envs of the job; this process owns shard_range(num_envs, rank, world_size)
@@ -138,6 +138,9 @@ class GraphVecEnv:
         gather           "auto" | "ldg" | "bulk" | "fused" (include/vn_b200.h VN_GATHER_*); "auto" runs the whole step
                          as ONE fused launch for batches of at most one env per SM and as scalar kernel + bulk-copy
                          gather otherwise
+        numpy_obs        return the observation leaves (and last_action_reward) as fresh numpy arrays, like the
+                         reference's SubprocVecEnv, for a trainer that cannot take CUDA tensors: one device-to-host
+                         copy of the whole batch per step (PCIe-bound - C2: ~1.9 M instead of ~110 M env-steps/s)
         skip_unchanged   the observation leaves are views of persistent batch buffers owned by this object, so the
                          row of an env whose state did not change (collision, no-op) is not copied again
                          (VN_STEP_SKIP_UNCHANGED).  Pass False if the returned observation tensors are modified in
@@ -158,6 +161,8 @@ class GraphVecEnv:
         self.unreal_wrapper = unreal_wrapper
         self.host_outputs = host_outputs
         self.scaled_float = scaled_float
+        self.numpy_obs = numpy_obs
+        self._host_stage = {}
         self.episode_info = episode_info     # RewardCollector's info['episode'] (create_envs wraps with it, :60)
         self.n_actions = 4
         self.gather = {"auto": L.GATHER_AUTO, "ldg": L.GATHER_LDG, "bulk": L.GATHER_BULK,
@@ -349,6 +354,41 @@ class GraphVecEnv:
             self._obs_cache = self._build_obs()
         return self._obs_cache
 
+    def _obs_out(self):
+        """What reset() / step() hand back: the persistent CUDA batches, or (numpy_obs) fresh host copies of them."""
+        obs = self._obs()
+        if not self.numpy_obs:
+            return obs
+        leaves = []
+
+        def walk(x):
+            if isinstance(x, tuple):
+                return tuple(walk(v) for v in x)
+            if isinstance(x, dict):
+                return {k: walk(v) for k, v in x.items()}
+            leaves.append(x)
+            return len(leaves) - 1
+
+        shape = walk(obs)
+        staged = []
+        for i, t in enumerate(leaves):
+            buf = self._host_stage.get(i)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = self._host_stage[i] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            buf.copy_(t, non_blocking=True)
+            staged.append(buf)
+        torch.cuda.current_stream(self.device).synchronize()
+        host = [b.numpy().copy() for b in staged]
+
+        def build(x):
+            if isinstance(x, tuple):
+                return tuple(build(v) for v in x)
+            if isinstance(x, dict):
+                return {k: build(v) for k, v in x.items()}
+            return host[x]
+
+        return build(shape)
+
     def _convert_float_leaves(self, all_rows=False):
         """Float mode: TransposeImage + ScaledFloatFrame (thor_cached_auxiliary.py:61-62) of the step just enqueued,
         one launch per leaf, reading the step's gather descriptors (record or -1 = row unchanged; goal record or
@@ -398,7 +438,7 @@ class GraphVecEnv:
                    L.ptr(m), r["out"], self.gather, self._stream())
         if self.scaled_float:
             self._convert_float_leaves()
-        return self._obs()
+        return self._obs_out()
 
     def _tick(self, out, flags):
         self._calls += 1
@@ -531,15 +571,15 @@ class GraphVecEnv:
                 L.check(self.lib.vn_host_wait_seq(self._seq_host.data_ptr(), self._seq_words, self._seq, self._stream(),
                                                   60_000_000))
             h = self._pack_np.copy()
-            return (self._obs(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
+            return (self._obs_out(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
                     LazyInfos(self, h, noop))
         if self.host_outputs:
             self._pack_host.copy_(self._pack, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             h = self._unpack(self._pack_np.copy())
-            return self._obs(), h["reward"], h["done"].view(np.bool_), LazyInfos(self, h, noop)
+            return self._obs_out(), h["reward"], h["done"].view(np.bool_), LazyInfos(self, h, noop)
         fetch = lambda: self._unpack(self._pack.cpu().numpy())
-        return self._obs(), self.reward, self.done.bool(), LazyInfos(self, fetch, noop)
+        return self._obs_out(), self.reward, self.done.bool(), LazyInfos(self, fetch, noop)
 
     def step(self, actions):
         if self.host_outputs and type(actions) is np.ndarray and not self._pending and not self.closed \
@@ -559,7 +599,7 @@ class GraphVecEnv:
                        self._actions_ptr, self._actions_dev_ptr, r["out_host"], h.__array_interface__["data"][0],
                        self._seq_words, self.gather, _raw_stream(self._dev_index), 60_000_000)
             noop = (self._actions_np < 0) if self.family.noop_action else None
-            return (self._obs(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
+            return (self._obs_out(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
                     LazyInfos(self, h, noop))
         self.step_async(actions)
         return self.step_wait()
