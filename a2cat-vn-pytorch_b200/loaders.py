@@ -63,3 +63,86 @@ def scene_from_h5_arrays(graph, observation, shortest_path_distance=None, locati
     # start-state candidates of a goal g are {s : shortest_path_distance[s][g] > 0} (cached.py:41-44)
     sc.h5_spd = None if shortest_path_distance is None else np.asarray(shortest_path_distance)
     return sc
+
+
+# --------------------------------------------------------------------------- scene pickles without the reference tree
+class _Bag:
+    """Stand-in for the reference classes inside a scene pickle (graph.*.ThorGridWorld and friends are plain
+    objects whose state is their ``__dict__``)."""
+
+    def __setstate__(self, state):
+        if isinstance(state, dict):
+            self.__dict__.update(state)
+
+    @property
+    def maze(self):                                  # GridWorldScene.maze, graph/core.py
+        return self._maze
+
+
+def load_scene_pickle(path_or_file):
+    """``graph.util.load_graph`` (graph/util.py:69-79) for a box that does not have the reference package: classes
+    of the ``graph`` / ``environments`` packages found in the pickle are replaced by attribute bags, everything
+    else (numpy arrays, tuples) unpickles normally.  Returns an object with the ThorGridWorld attributes
+    (``_maze``, ``_observations``, ``_depths``, ``_segmentations``, optionally ``_tp_*``, ``goals``).  The cached
+    ``graph`` / ``optimal_actions`` tables of dump_graph are ignored: tables.compile_world recomputes them (BFS)."""
+    import pickle
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            root = module.split(".")[0]
+            if root in ("graph", "environments", "environment"):
+                return _Bag
+            return super().find_class(module, name)
+
+    if isinstance(path_or_file, (str, bytes)) or hasattr(path_or_file, "__fspath__"):
+        with open(path_or_file, "rb") as f:
+            return _Unpickler(f).load()
+    return _Unpickler(path_or_file).load()
+
+
+#: scene name -> goals, environments/gym_graph/download.py:21-29 (the -174 variants share the goals)
+THOR_CACHED_GOALS = {
+    "thor-cached-212": [(3, 1, 2), (13, 21, 3), (10, 2, 1), (10, 14, 0)],
+    "thor-cached-208": [(6, 3, 1), (13, 3, 0), (7, 18, 2), (6, 25, 1)],
+    "thor-cached-218": [(6, 22, 1), (7, 0, 0), (18, 18, 3), (13, 31, 3)],
+    "thor-cached-225": [(3, 17, 2), (12, 17, 3), (15, 10, 0), (14, 8, 3)],
+}
+
+#: gym ids of environments/gym_graph/__init__.py:8-28 -> (observation layout, max_episode_steps)
+GYM_IDS = {"OrientedGraph-v0": ("frame", 900), "AuxiliaryGraph-v0": ("aux5", 900)}
+
+
+def scene_file(graph_name):
+    """Where the reference caches its scene pickles: ~/.visual_navigation/scenes/<name>.pkl (download.py:38-43)."""
+    import os
+    return os.path.join(os.path.expanduser("~"), ".visual_navigation", "scenes", "%s.pkl" % graph_name)
+
+
+def make_vec(id, tasks, num_envs=None, screen_size=None, graph_files=None, **env_kwargs):
+    """``create_envs`` of the experiments in one call (thor_cached_auxiliary.py:58-71): ``id`` is a gym id of
+    environments/gym_graph/__init__.py ('AuxiliaryGraph-v0', 'OrientedGraph-v0', 'Graph<Scene>-v0'), ``tasks`` the
+    experiment's ``[(scene_name, [goal, ...]), ...]`` list (``None`` goals = the table of download.py:21-29).  One env
+    per (scene, goal) unless ``num_envs`` says otherwise; scene pickles come from ``graph_files[scene_name]`` or the
+    reference's cache directory.  Returns a GraphVecEnv (extra keyword arguments are passed on)."""
+    from .tables import GYM_GRAPH, compile_world
+    from .vec_env import GraphVecEnv
+    if id in GYM_IDS:
+        layout, limit = GYM_IDS[id]
+    elif id.startswith("Graph") and id.endswith("-v0"):
+        layout, limit = "frame", 100                    # gym_graph/__init__.py:8-17
+    else:
+        raise ValueError("unknown environment id %r" % (id,))
+    scenes, task_list = [], []
+    for k, (name, goals) in enumerate(tasks):
+        if goals is None:
+            goals = THOR_CACHED_GOALS[name[:-4] if name.endswith("-174") else name]
+        path = (graph_files or {}).get(name) or scene_file(name)
+        graph = load_scene_pickle(path)
+        planes = ("rgb", "depth", "segmentation") if layout == "aux5" else ("rgb",)
+        scenes.append(scene_from_thor_grid_world(graph, goals, screen_size=screen_size, planes=planes, scene_id=k,
+                                                 name=name))
+        task_list += [(k, tuple(g)) for g in goals]
+    world = compile_world(scenes, GYM_GRAPH, tasks=task_list)
+    env_kwargs.setdefault("max_episode_steps", limit)
+    env_kwargs.setdefault("obs_layout", layout)
+    return GraphVecEnv(world, num_envs or len(task_list), **env_kwargs)

@@ -109,3 +109,40 @@ def assert_record_equal(rec, g, obs=True):
     if obs:
         assert np.array_equal(rec["obs_crc"], g["obs_crc"]), "obs_crc"
         assert np.array_equal(rec["reset_obs_crc"], g["reset_obs_crc"]), "reset_obs_crc"
+
+
+def write_reference_style_pickle(scene, path, frame=12):
+    """Pickles ``scene`` the way the reference stores its scenes: an object of class
+    graph.multi_graph_no_tp.ThorGridWorld whose state is its __dict__ (dense [X,Y,4,H,W,C] arrays).  The class is
+    faked in a throw-away module, so this works on boxes without the reference tree."""
+    import pickle
+    import sys
+    import types
+    X, Y = scene.maze.shape
+    h, w = scene.frame_hw
+    pkg, mod = types.ModuleType("graph"), types.ModuleType("graph.multi_graph_no_tp")
+
+    class ThorGridWorld:
+        pass
+
+    ThorGridWorld.__module__, ThorGridWorld.__qualname__ = "graph.multi_graph_no_tp", "ThorGridWorld"
+    mod.ThorGridWorld = ThorGridWorld
+    saved = {k: sys.modules.get(k) for k in ("graph", "graph.multi_graph_no_tp")}
+    sys.modules["graph"], sys.modules["graph.multi_graph_no_tp"] = pkg, mod
+    try:
+        wld = ThorGridWorld()
+        wld._maze = scene.maze.copy()
+        for attr, plane, c in (("_observations", "rgb", 3), ("_depths", "depth", 1), ("_segmentations", "segmentation", 3)):
+            a = np.zeros((X, Y, 4, h, w, c), np.uint8)
+            a[scene.cells[:, 0], scene.cells[:, 1]] = scene.plane_frames(plane).reshape(scene.n_cells, 4, h, w, c)
+            setattr(wld, attr, a)
+        wld.goals = list(scene.goals)
+        wld.graph = "stale tables are ignored"
+        with open(path, "wb") as f:
+            pickle.dump(wld, f)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v

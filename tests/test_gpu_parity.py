@@ -1092,3 +1092,30 @@ def test_numpy_observation_mode_for_host_trainers():
                 kept = (ob[0], ob[0].copy())
         assert np.array_equal(*kept)              # arrays handed out earlier are not overwritten by later steps
         assert ob[0].dtype == (np.float32 if flt else np.uint8)
+
+
+def test_make_vec_from_scene_pickles(tmp_path):
+    """loaders.make_vec: the experiments' create_envs in one call - gym id, [(scene, goals)] task list, scene pickles
+    in the reference's format (read without the reference package) -> a stepping GraphVecEnv."""
+    scs = [H.scenes.make_maze_scene((7, 6), 0.2, 40 + k, n_goals=2, frame_hw=(84, 84), scene_id=k) for k in range(2)]
+    files = {}
+    for k, sc in enumerate(scs):
+        files["scene-%d" % k] = str(tmp_path / ("scene-%d.pkl" % k))
+        H.write_reference_style_pickle(sc, files["scene-%d" % k])
+    tasks = [("scene-%d" % k, list(sc.goals)) for k, sc in enumerate(scs)]
+    env = vn.loaders.make_vec("AuxiliaryGraph-v0", tasks, graph_files=files, scaled_float=True, seed=3)
+    assert env.num_envs == 4 and env.max_episode_steps == 900                 # one env per (scene, goal), :66
+    assert env.observation_space.spaces[0].spaces[0].shape == (3, 84, 84)
+    env.set_hardness(0.01)
+    (obs, lar) = env.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(30):
+        (obs, lar), r, d, infos = env.step(rng.randint(0, 4, 4))
+    st = env.state.cpu().numpy()
+    for i in range(4):
+        k = i // 2                                                             # envs 0,1 -> scene 0; 2,3 -> scene 1
+        local = int(st[i] - env.world.scene_base[k])
+        want = ovec.transpose_scale(scs[k].plane_frames("rgb", [local])[0])
+        assert np.array_equal(obs[0][i].cpu().numpy(), want)
+    small = vn.loaders.make_vec("OrientedGraph-v0", tasks[:1], graph_files=files, screen_size=(42, 42), num_envs=8)
+    assert small.reset()[0].shape == (8, 42, 42, 3) and small.max_episode_steps == 900

@@ -266,3 +266,24 @@ def test_loader_third_person_planes():
     for p in scene.planes:
         assert np.array_equal(loaded.plane_frames(p), scene.plane_frames(p))
     assert not np.array_equal(scene.plane_frames("rgb"), scene.plane_frames("tp_rgb"))
+
+
+def test_scene_pickle_loads_without_the_reference_package(tmp_path):
+    """loaders.load_scene_pickle: a ThorGridWorld pickle (class path graph.multi_graph_no_tp.ThorGridWorld) unpickles on
+    a box that has no `graph` package, and compiles into the same world as the scene it was exported from."""
+    import pickle
+    scene = H.scenes.make_maze_scene((6, 7), 0.2, 5, n_goals=2, planes=("rgb", "depth", "segmentation"), frame_hw=(12, 12))
+    path = tmp_path / "scene.pkl"
+    H.write_reference_style_pickle(scene, path)
+    with pytest.raises(ModuleNotFoundError):
+        pickle.load(open(path, "rb"))                # the stock unpickler needs the reference package
+    g = vn.loaders.load_scene_pickle(str(path))
+    assert g.goals == list(scene.goals) and np.array_equal(g.maze, scene.maze)
+    loaded = vn.loaders.scene_from_thor_grid_world(g, g.goals)
+    w0, w1 = T.compile_world([scene], T.GYM_GRAPH), T.compile_world([loaded], T.GYM_GRAPH)
+    assert np.array_equal(w0.adj, w1.adj) and np.array_equal(w0.cand_state, w1.cand_state)
+    for p in ("rgb", "depth", "segmentation"):
+        assert np.array_equal(loaded.plane_frames(p), scene.plane_frames(p))
+    assert vn.loaders.THOR_CACHED_GOALS["thor-cached-225"][0] == (3, 17, 2)
+    with pytest.raises(ValueError):
+        vn.loaders.make_vec("NoSuchEnv-v0", [])
