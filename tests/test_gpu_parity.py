@@ -1119,3 +1119,53 @@ def test_make_vec_from_scene_pickles(tmp_path):
         assert np.array_equal(obs[0][i].cpu().numpy(), want)
     small = vn.loaders.make_vec("OrientedGraph-v0", tasks[:1], graph_files=files, screen_size=(42, 42), num_envs=8)
     assert small.reset()[0].shape == (8, 42, 42, 3) and small.max_episode_steps == 900
+
+
+@pytest.mark.parametrize("oriented", [True, False])
+def test_reset_sampling_distribution_matches_the_reference_weights(oriented):
+    """The reference draws start states with np.random.choice(p=weights) (graph/util.py:132-142 oriented: uniform over
+    the eligible set; :103-116 un-oriented: 0.9 / 0.1 over the near / far buckets) and goals with random.choice.  The
+    device's Philox draws must follow the same distribution: chi-square of ~260k resets against the oracle's weights,
+    and never a state outside the candidate set."""
+    import torch
+    from scipy import stats
+    scene = H.scenes.make_maze_scene((9, 9), 0.2, 12, n_goals=2, oriented=oriented,
+                                     planes=("rgb",))
+    osc = oenvs.OracleScene(scene)
+    fam = T.GYM_GRAPH if oriented else T.SIMPLE_GRAPH
+    world = T.compile_world([scene], fam)
+    N, rounds = 8192, 32
+    goals = list(scene.goals)
+    env_tasks = np.tile(np.array([[0, len(goals)]], np.int32), (N, 1))
+    env = vn.GraphVecEnv(world, N, seed=2024, max_episode_steps=1, obs_layout="frame", env_tasks=env_tasks,
+                         host_outputs=False)
+    c = 0.35
+    env.set_complexity(c)
+    env.reset()
+    counts = torch.zeros((len(goals), world.n_states), dtype=torch.int64, device="cuda")
+    zeros = torch.zeros(N, dtype=torch.int32, device="cuda")
+    for _ in range(rounds):                                   # TimeLimit 1: every step ends the episode and resets
+        env.step_enqueue(zeros)
+        counts.index_put_((env.task.long(), env.state.long()), torch.ones(N, dtype=torch.int64, device="cuda"),
+                          accumulate=True)
+    counts = counts.cpu().numpy()
+    total = N * rounds
+    # goals: uniform (random.choice, gym_graph/graph.py:47)
+    per_goal = counts.sum(1)
+    assert stats.chisquare(per_goal).pvalue > 1e-4, per_goal
+    for t, goal in enumerate(goals):
+        if oriented:
+            pots, dists = gu.initial_state_candidates(scene.maze, osc.graph, osc.optimal_actions, goal)
+            od = c * (int(np.max(osc.graph)) + 4 - 1) + 1    # gym_graph/graph.py:49-51
+            w = gu.initial_state_weights(dists, od)
+        else:
+            pots, dists = gu.initial_position_candidates(scene.maze, osc.graph, goal)
+            od = c * (int(np.max(osc.graph)) - 1) + 1        # graph/env.py:103-105
+            w = gu.initial_position_weights(dists, od)
+        idx = np.array([scene.state_index(p) for p in pots])
+        assert counts[t].sum() == counts[t][idx].sum()        # nothing outside the candidate set
+        live = w > 0
+        assert counts[t][idx[~live]].sum() == 0               # nothing the reference gives zero weight
+        obs, exp = counts[t][idx[live]], w[live] / w[live].sum() * per_goal[t]
+        assert stats.chisquare(obs, exp).pvalue > 1e-4, (t, obs[:8], exp[:8])
+    assert total == counts.sum()
