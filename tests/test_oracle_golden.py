@@ -125,3 +125,36 @@ def test_aux_target_matches_reference_function():
     np.testing.assert_allclose(orl.aux_target(x, 4, None), g["y21"], rtol=1e-6, atol=1e-7)
     d = rng.randint(0, 256, size=(2, 3, 1, 84, 84)).astype(np.float32) / np.float32(255.0)
     np.testing.assert_allclose(orl.aux_target(d, 4, (20, 20)), g["yd"], rtol=1e-6, atol=1e-7)
+
+
+def test_rollout_oracle_agrees_with_the_torch_formulation():
+    """The D5 / A15 restatements (numpy, explicit summation order) against the same computation written with the
+    torch ops deep_rl uses (autocrop -> abs diff -> F.avg_pool2d -> channel mean; F.avg_pool2d for the aux targets).
+    torch's CPU pooling sums in its own order, hence the 1e-6 tolerance - the north-star bound is 1e-5."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import rollout as orl
+    rng = np.random.RandomState(0)
+    obs = (rng.randint(0, 256, size=(3, 6, 3, 84, 84)).astype(np.float32) / np.float32(255.0)).astype(np.float32)
+    for cell, out in ((4, (20, 20)), (4, None), (3, (27, 26))):
+        x = torch.from_numpy(obs)
+        h, w = x.shape[3:]
+        nh, nw = ((h // cell) * cell, (w // cell) * cell) if out is None else (out[0] * cell, out[1] * cell)
+        top, left = (h - nh) // 2, (w - nw) // 2
+        xc = x[:, :, :, top:top + nh, left:left + nw]
+        d = (xc[:, 1:] - xc[:, :-1]).abs()
+        p = F.avg_pool2d(d.reshape(-1, *d.shape[2:]), cell, stride=cell).mean(1, keepdim=True)
+        want = p.view(d.shape[0], d.shape[1], 1, nh // cell, nw // cell).numpy()
+        np.testing.assert_allclose(orl.pixel_control_reward(obs, cell, out), want, rtol=1e-6, atol=1e-7)
+        a = F.avg_pool2d(xc.reshape(-1, *xc.shape[2:]), cell, stride=cell).view(3, 6, 3, nh // cell, nw // cell).numpy()
+        np.testing.assert_allclose(orl.aux_target(obs, cell, out), a, rtol=1e-6, atol=1e-7)
+    # n-step returns: the recurrence written with torch tensors step by step
+    r = torch.from_numpy(rng.rand(5, 9).astype(np.float32))
+    dn = torch.from_numpy((rng.rand(5, 9) < 0.2))
+    v = torch.from_numpy(rng.randn(5).astype(np.float32))
+    ret = torch.zeros(5, 10)
+    ret[:, -1] = v * (1.0 - dn[:, -1].float())
+    for t in reversed(range(9)):
+        ret[:, t] = r[:, t] + 0.99 * ret[:, t + 1] * (1.0 - dn[:, t].float())
+    got = orl.nstep_returns(r.numpy(), dn.numpy(), v.numpy(), 0.99)
+    np.testing.assert_allclose(got, ret[:, :-1].numpy(), rtol=1e-6, atol=1e-7)
