@@ -488,8 +488,9 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
 }
 
 // ---- fused single launch for small batches ----------------------------------------------------------
-// A batch of at most one env per SM (C1: 16 envs) is bound by launch latency and by the chain of dependent
-// memory round trips, not by bandwidth, so ONE kernel does both halves: one CTA per env, thread 0 steps the
+// A batch that fits in one wave of CTAs (C1: 16 envs; up to 444 envs for C2's records, see choose_fused) is bound
+// by launch latency and by the chain of dependent memory round trips, not by bandwidth, so ONE kernel does both
+// halves: one CTA per env, thread 0 steps the
 // env, then lane 0 of warp w moves slice w of every plane - the observation record and, after a reset, the goal
 // record, both in flight at once - with bulk async copies through a record-shaped region of shared memory.
 constexpr int kFusedWarps = 4;
