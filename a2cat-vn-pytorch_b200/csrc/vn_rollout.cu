@@ -61,11 +61,14 @@ __global__ void __launch_bounds__(256) vn_backup_kernel(const float *__restrict_
 // =====================================================================================================
 // pixel-control reward and auxiliary targets from the store
 // =====================================================================================================
-// lut[v] = float32(v) / 255.0f with IEEE division: exactly what ScaledFloatFrame produces per pixel.  The
-// table is replicated once per shared-memory bank (index v * 32 + lane) so that the 32 lanes of a warp,
-// each looking up a different byte value, never conflict.
-__device__ __forceinline__ void build_lut(float *lut) {
-    for (int k = threadIdx.x; k < 256 * 32; k += blockDim.x) lut[k] = __fdiv_rn((float)(k >> 5), 255.0f);
+// float(v) / 255.0f, correctly rounded, without a division or a table: q = v * r with r = fl(1 / 255), one Newton
+// step on the exact residual e = fma(-q, 255, v), q' = fma(e, r, q).  Equal to __fdiv_rn(v, 255) for all 256 byte
+// values (checked exhaustively on the host and, bit for bit, by the policy_input parity tests).
+__device__ __forceinline__ float u8_over_255(uint32_t v) {
+    const float x = (float)v, r = 1.0f / 255.0f;
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q, 255.0f, x);
+    return __fmaf_rn(e, r, q);
 }
 
 __device__ __forceinline__ void load_frame(uint8_t *dst_smem, const uint8_t *src, int nbytes) {
@@ -80,9 +83,8 @@ struct PoolGeom {
 };
 
 // out[cell] = mean_c avg_pool_cell(|nxt/255 - cur/255|) for one transition; frames and LUT in shared memory
-__device__ __forceinline__ void pc_cells(const uint8_t *cur, const uint8_t *nxt, const float *lut, const PoolGeom &g,
+__device__ __forceinline__ void pc_cells(const uint8_t *cur, const uint8_t *nxt, const PoolGeom &g,
                                          float *__restrict__ out_row) {
-    const int lane = threadIdx.x & 31;
     const int cells = g.out_h * g.out_w;
     const int row_bytes = g.w * g.c;
     for (int cidx = threadIdx.x; cidx < cells; cidx += blockDim.x) {
@@ -93,8 +95,8 @@ __device__ __forceinline__ void pc_cells(const uint8_t *cur, const uint8_t *nxt,
             for (int dy = 0; dy < g.cell; ++dy) {
                 const int rowoff = (g.top + oi * g.cell + dy) * row_bytes + (g.left + oj * g.cell) * g.c + ch;
                 for (int dx = 0; dx < g.cell; ++dx) {
-                    const float a = lut[(int)nxt[rowoff + dx * g.c] * 32 + lane];
-                    const float b = lut[(int)cur[rowoff + dx * g.c] * 32 + lane];
+                    const float a = u8_over_255(nxt[rowoff + dx * g.c]);
+                    const float b = u8_over_255(cur[rowoff + dx * g.c]);
                     acc = __fadd_rn(acc, fabsf(__fsub_rn(a, b)));
                 }
             }
@@ -112,8 +114,7 @@ __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t 
                                                                PoolGeom g, float *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int fbytes = g.h * g.w * g.c;
-    float *lut = reinterpret_cast<float *>(smem_raw);
-    uint8_t *frame0 = smem_raw + 256 * 32 * sizeof(float);
+    uint8_t *frame0 = smem_raw;
     uint8_t *frame1 = frame0 + ((fbytes + 15) & ~15);
     const int chunks = (t + kChunk - 1) / kChunk;
     const int env = blockIdx.x / chunks;
@@ -122,14 +123,13 @@ __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t 
     const int32_t *srow = states + (int64_t)env * (t + 1);
     const uint8_t *pbase = store.base + store.plane_off[plane];
 
-    build_lut(lut);
     load_frame(frame0, pbase + (size_t)srow[k0] * store.state_pitch, fbytes);
     uint8_t *cur = frame0, *nxt = frame1;
     const int cells = g.out_h * g.out_w;
     for (int k = k0; k < k1; ++k) {
         load_frame(nxt, pbase + (size_t)srow[k + 1] * store.state_pitch, fbytes);
         __syncthreads();
-        pc_cells(cur, nxt, lut, g, out + ((int64_t)env * t + k) * cells);
+        pc_cells(cur, nxt, g, out + ((int64_t)env * t + k) * cells);
         __syncthreads();
         uint8_t *tmp = cur;
         cur = nxt;
@@ -147,12 +147,10 @@ __global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_sto
                                                                     float *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int fbytes = g.h * g.w * g.c;
-    float *lut = reinterpret_cast<float *>(smem_raw);
-    uint8_t *frame0 = smem_raw + 256 * 32 * sizeof(float);
+    uint8_t *frame0 = smem_raw;
     uint8_t *frame1 = frame0 + ((fbytes + 15) & ~15);
     const int m_total = min(*count, max_count);
     if ((int)blockIdx.x >= m_total) return;
-    build_lut(lut);
     const uint8_t *pbase = store.base + store.plane_off[plane];
     const int cells = g.out_h * g.out_w;
     for (int m = blockIdx.x; m < m_total; m += gridDim.x) {
@@ -163,7 +161,7 @@ __global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_sto
         load_frame(frame0, pbase + (size_t)srow[k] * store.state_pitch, fbytes);
         load_frame(frame1, pbase + (size_t)srow[k + 1] * store.state_pitch, fbytes);
         __syncthreads();
-        pc_cells(frame0, frame1, lut, g, out + (int64_t)p * cells);
+        pc_cells(frame0, frame1, g, out + (int64_t)p * cells);
     }
 }
 
@@ -243,10 +241,7 @@ __global__ void __launch_bounds__(256) vn_aux_target_kernel(const vn_store_t sto
                                                             float *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int fbytes = g.h * g.w * g.c;
-    float *lut = reinterpret_cast<float *>(smem_raw);
-    uint8_t *frame = smem_raw + 256 * 32 * sizeof(float);
-    const int lane = threadIdx.x & 31;
-    build_lut(lut);
+    uint8_t *frame = smem_raw;
     const int cells = g.out_h * g.out_w;
     const int row_bytes = g.w * g.c;
     for (int f = blockIdx.x; f < m; f += gridDim.x) {
@@ -259,7 +254,7 @@ __global__ void __launch_bounds__(256) vn_aux_target_kernel(const vn_store_t sto
             float acc = 0.f;
             for (int dy = 0; dy < g.cell; ++dy) {
                 const int rowoff = (g.top + oi * g.cell + dy) * row_bytes + (g.left + oj * g.cell) * g.c + ch;
-                for (int dx = 0; dx < g.cell; ++dx) acc = __fadd_rn(acc, lut[(int)frame[rowoff + dx * g.c] * 32 + lane]);
+                for (int dx = 0; dx < g.cell; ++dx) acc = __fadd_rn(acc, u8_over_255(frame[rowoff + dx * g.c]));
             }
             out[(int64_t)f * cells * g.c + o] = __fdiv_rn(acc, (float)(g.cell * g.cell));
         }
@@ -285,16 +280,6 @@ __global__ void __launch_bounds__(256) vn_gather_f32_chw_kernel(const vn_store_t
             o[k] = __fdiv_rn((float)smem_raw[px * c + ch], 255.0f);
         }
     }
-}
-
-// float(v) / 255.0f, correctly rounded, without a division or a table: q = v * r with r = fl(1 / 255), one Newton
-// step on the exact residual e = fma(-q, 255, v), q' = fma(e, r, q).  Equal to __fdiv_rn(v, 255) for all 256 byte
-// values (checked exhaustively on the host and, bit for bit, by the policy_input parity tests).
-__device__ __forceinline__ float u8_over_255(uint32_t v) {
-    const float x = (float)v, r = 1.0f / 255.0f;
-    const float q = __fmul_rn(x, r);
-    const float e = __fmaf_rn(-q, 255.0f, x);
-    return __fmaf_rn(e, r, q);
 }
 
 // Vectorised form of the same conversion for frames whose pixel count is a multiple of 4 (84 x 84, 174 x 174):
@@ -662,7 +647,7 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
     if (n == 0) return VN_OK;
     constexpr int kChunk = 16;
     const int fb = (h * w * c + 15) & ~15;
-    const int smem = 256 * 32 * 4 + 2 * fb;
+    const int smem = 2 * fb;
     VN_REQUIRE(smem <= 220 * 1024, "pixel_control: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_pixel_control_kernel<kChunk>, smem);
     const int64_t blocks = (int64_t)n * ((t + kChunk - 1) / kChunk);
@@ -710,10 +695,11 @@ int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int3
     if (rc) return rc;
     if (n == 0 || max_count == 0) return VN_OK;
     const int fb = (h * w * c + 15) & ~15;
-    const int smem = 256 * 32 * 4 + 2 * fb;
+    const int smem = 2 * fb;
     VN_REQUIRE(smem <= 220 * 1024, "pixel_control_list: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_pixel_control_list_kernel, smem);
-    const int grid = max_count < 148 * 3 ? max_count : 148 * 3;
+    const int per_sm = (220 * 1024) / (smem + 1024) < 8 ? ((220 * 1024) / (smem + 1024) < 1 ? 1 : (220 * 1024) / (smem + 1024)) : 8;
+    const int grid = max_count < 148 * per_sm ? max_count : 148 * per_sm;
     vn::vn_pixel_control_list_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         *store, plane, states, t, g, pos, count, max_count, out);
     return vn::check_launch("vn_pixel_control_list_kernel");
@@ -767,7 +753,7 @@ int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx
     rc = vn::pool_geom(h, w, c, cell, out_h, out_w, &g);
     if (rc) return rc;
     if (m == 0) return VN_OK;
-    const int smem = 256 * 32 * 4 + ((h * w * c + 15) & ~15);
+    const int smem = (h * w * c + 15) & ~15;
     VN_REQUIRE(smem <= 220 * 1024, "aux_target: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_aux_target_kernel, smem);
     const int grid = m < 148 * 8 ? m : 148 * 8;
