@@ -41,6 +41,44 @@ __global__ void __launch_bounds__(256) vn_nstep_returns_kernel(const float *__re
     }
 }
 
+// The same recurrence as a warp-level scan: one warp per env, 32 time steps per pass.  Step t is the affine map
+// f_t(x) = b_t + a_t x with a_t = gamma (1 - done_t), b_t = r_t; R_t = (f_t o f_{t+1} o ... o f_{T-1})(R_T).  An
+// inclusive SUFFIX scan of the maps under composition (5 shuffle rounds) gives every R_t of the chunk from the carry
+// R_{chunk end + 1}.  Re-associates the float operations: equal to the serial kernel within ~1e-6 relative, not bit
+// for bit - which is why the serial kernel stays the default (the north-star bound is 1e-5).
+__global__ void __launch_bounds__(128) vn_nstep_returns_scan_kernel(const float *__restrict__ reward,
+                                                                    const uint8_t *__restrict__ done,
+                                                                    const float *__restrict__ last_value, float gamma,
+                                                                    int n, int t, int64_t stride_n, int64_t stride_t,
+                                                                    float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const int64_t base = (int64_t)i * stride_n;
+        float carry = (1.0f - (float)done[base + (int64_t)(t - 1) * stride_t]) * last_value[i];
+        for (int hi = t; hi > 0; hi -= 32) {          // chunk [hi - 32, hi), lane L <-> step hi - 32 + L
+            const int k = hi - 32 + lane;
+            float a = 1.0f, b = 0.0f;                 // identity map for lanes before step 0
+            if (k >= 0) {
+                const int64_t at = base + (int64_t)k * stride_t;
+                a = gamma * (1.0f - (float)done[at]);
+                b = reward[at];
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float a2 = __shfl_down_sync(0xffffffffu, a, o), b2 = __shfl_down_sync(0xffffffffu, b, o);
+                if (lane + o < 32) {                  // f <- f o g with g the composed map of the lanes after this one
+                    b = fmaf(a, b2, b);
+                    a = a * a2;
+                }
+            }
+            const float r = fmaf(a, carry, b);
+            if (k >= 0) out[base + (int64_t)k * stride_t] = r;
+            carry = __shfl_sync(0xffffffffu, r, hi >= 32 ? 0 : 32 - hi);   // R at the first real step of the chunk
+        }
+    }
+}
+
 // [n][t][d] with trailing feature axis: one thread per (env, feature), coalesced over d
 __global__ void __launch_bounds__(256) vn_backup_kernel(const float *__restrict__ reward,
                                                         const uint8_t *__restrict__ done,
@@ -610,6 +648,17 @@ int32_t vn_nstep_returns(const float *reward, const uint8_t *done, const float *
     vn::vn_nstep_returns_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reward, done, last_value, gamma, n, t, stride_n, stride_t, out);
     return vn::check_launch("vn_nstep_returns_kernel");
+}
+
+int32_t vn_nstep_returns_scan(const float *reward, const uint8_t *done, const float *last_value, float gamma,
+                              int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream) {
+    VN_REQUIRE(reward && done && last_value && out, "nstep_returns_scan: null pointer");
+    VN_REQUIRE(n >= 0 && t >= 1, "nstep_returns_scan: n=%d t=%d", n, t);
+    if (n == 0) return VN_OK;
+    const int64_t want = ((int64_t)n * 32 + 127) / 128, cap = 148 * 16;
+    vn::vn_nstep_returns_scan_kernel<<<(int)(want < cap ? want : cap), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reward, done, last_value, gamma, n, t, stride_n, stride_t, out);
+    return vn::check_launch("vn_nstep_returns_scan_kernel");
 }
 
 int32_t vn_discounted_backup(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,

@@ -83,7 +83,7 @@ _lib = None
 #: every symbol include/vn_b200.h declares
 EXPORTS = ("vn_abi_version", "vn_abi_struct_size", "vn_last_error", "vn_launch_count", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
            "vn_env_gather", "vn_env_step_host", "vn_env_step_host_sync", "vn_env_host_seq_words", "vn_host_wait_seq", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
-           "vn_gather_plane_f32_chw", "vn_gather_plane_f32_chw_rows", "vn_gather_leaves_f32_chw", "vn_nstep_returns", "vn_discounted_backup", "vn_pixel_control",
+           "vn_gather_plane_f32_chw", "vn_gather_plane_f32_chw_rows", "vn_gather_leaves_f32_chw", "vn_nstep_returns", "vn_nstep_returns_scan", "vn_discounted_backup", "vn_pixel_control",
            "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_replay_sample",
            "vn_aux_target", "vn_rp_labels")
 
@@ -131,6 +131,7 @@ def load(build_if_missing=True):
         "vn_gather_plane_f32_chw_rows": (i32, [S, i32, _P, i32, i32, i32, i32, i32, _P, _P]),
         "vn_gather_leaves_f32_chw": (i32, [S, C.POINTER(FloatLeaf), i32, _P, i32, i32, i32, _P]),
         "vn_nstep_returns": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, _P]),
+        "vn_nstep_returns_scan": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, _P]),
         "vn_discounted_backup": (i32, [_P, _P, _P, f32, i32, i32, i32, _P, _P]),
         "vn_pixel_control": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, i32, _P, _P]),
         "vn_transition_rows": (i32, [_P, _P, i32, i32, _P, _P, _P, _P]),

@@ -20,10 +20,14 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def nstep_returns(rewards, dones, last_values, gamma, time_major=False):
+def nstep_returns(rewards, dones, last_values, gamma, time_major=False, method="serial"):
     """A2C n-step returns (deep_rl RolloutStorage.batch).
-    rewards float32, dones uint8/bool: [B, T] (or [T, B] with time_major=True); last_values [B]."""
+    rewards float32, dones uint8/bool: [B, T] (or [T, B] with time_major=True); last_values [B].
+    method="serial" (default): thread per env, the reference's loop order, bit-identical to it.
+    method="scan": warp per env, 32 steps per pass composed with shuffles - for few envs and long rollouts; equal
+    within ~1e-6 relative (float re-association), not bit for bit."""
     lib = L.load()
+    fn = {"serial": lib.vn_nstep_returns, "scan": lib.vn_nstep_returns_scan}[method]
     rewards = rewards.contiguous().float()
     dones = dones.contiguous().to(torch.uint8)
     last_values = last_values.contiguous().float()
@@ -35,8 +39,8 @@ def nstep_returns(rewards, dones, last_values, gamma, time_major=False):
         sn, st = t, 1
     out = torch.empty_like(rewards)
     with torch.cuda.device(rewards.device):
-        L.check(lib.vn_nstep_returns(rewards.data_ptr(), dones.data_ptr(), last_values.data_ptr(), float(gamma), n, t,
-                                     sn, st, out.data_ptr(), _stream(rewards)))
+        L.check(fn(rewards.data_ptr(), dones.data_ptr(), last_values.data_ptr(), float(gamma), n, t, sn, st,
+                   out.data_ptr(), _stream(rewards)))
     return out
 
 

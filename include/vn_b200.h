@@ -303,6 +303,12 @@ int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t 
 int32_t vn_nstep_returns(const float *reward, const uint8_t *done, const float *last_value, float gamma, int32_t n,
                          int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream);
 
+/* The same returns by a warp-level scan (one warp per env, 32 steps per pass, affine maps composed with shuffles):
+ * for few envs and long rollouts.  Re-associates the float operations: within ~1e-6 relative of vn_nstep_returns,
+ * not bit-identical. */
+int32_t vn_nstep_returns_scan(const float *reward, const uint8_t *done, const float *last_value, float gamma,
+                              int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream);
+
 /* Backward discounted scan with a trailing feature axis of width d (pixel-control returns):
  *   R_T = bootstrap;  R_t = reward[t] + gamma * (1 - done[t]) * R_{t+1};  arrays are [n][t][d]. */
 int32_t vn_discounted_backup(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,

@@ -282,3 +282,26 @@ def test_replay_ring_bulk_extend_equals_per_step_insert(dw):
             assert torch.equal(getattr(r1, name), getattr(r2, name)), (rollout, name)
     s1, s2 = r1.sample_rp_sequence(), r2.sample_rp_sequence()
     assert all(torch.equal(s1[k], s2[k]) for k in s1)
+
+
+@pytest.mark.parametrize("n,t,time_major", [(16, 5, False), (3, 128, True), (8192, 128, True), (37, 33, False), (1, 1, False)])
+def test_nstep_returns_warp_scan_variant(n, t, time_major):
+    """method="scan": the backward discounted-return recurrence as a warp-level scan of affine maps.  Within 1e-5
+    relative of the reference loop (north_star tolerance; the serial default is bit-exact), episode ends included."""
+    import torch
+    rng = np.random.RandomState(n * 131 + t)
+    r = rng.randn(n, t).astype(np.float32)
+    d = rng.rand(n, t) < 0.15
+    v = rng.randn(n).astype(np.float32)
+    want = orl.nstep_returns(r, d, v, 0.99)
+    rt, dt = torch.from_numpy(r).cuda(), torch.from_numpy(d).cuda()
+    if time_major:
+        rt, dt = rt.t().contiguous(), dt.t().contiguous()
+    got = vn.rollout.nstep_returns(rt, dt, torch.from_numpy(v).cuda(), 0.99, time_major=time_major, method="scan")
+    got = got.t() if time_major else got
+    # 1e-5 relative to the scale of the returns (signed random rewards cancel, so single values can be ~0)
+    scale = float(np.abs(want).max())
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5 * max(scale, 1.0))
+    exact = vn.rollout.nstep_returns(rt, dt, torch.from_numpy(v).cuda(), 0.99, time_major=time_major)
+    exact = exact.t() if time_major else exact
+    assert np.array_equal(exact.cpu().numpy().view(np.uint32), want.view(np.uint32))
