@@ -453,7 +453,9 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
     const int units = p.n * split;
     const bool dynamic = sched != nullptr;
-    int u = dynamic ? (int)atomicAdd(&sched[0], 1u) : (int)blockIdx.x;
+    // the first unit of every CTA is its block index (no atomic round trip before the first copy); the units
+    // beyond the grid are handed out by the ticket counter
+    int u = (int)blockIdx.x;
     while (u < units) {
         const int env = u / split, slice = u - env * split;
         int rec, grec = -1;
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
             const uint8_t *gsrc = p.store.base + (size_t)grec * p.store.state_pitch;
             bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints);
         }
-        u = dynamic ? (int)atomicAdd(&sched[0], 1u) : u + (int)gridDim.x;
+        u = dynamic ? (int)gridDim.x + (int)atomicAdd(&sched[0], 1u) : u + (int)gridDim.x;
     }
     bulk_wait_read<0>();
     if (dynamic) {
