@@ -102,12 +102,20 @@ __global__ void __launch_bounds__(256) vn_backup_kernel(const float *__restrict_
 // float(v) / 255.0f, correctly rounded, without a division or a table: q = v * r with r = fl(1 / 255), one Newton
 // step on the exact residual e = fma(-q, 255, v), q' = fma(e, r, q).  Equal to __fdiv_rn(v, 255) for all 256 byte
 // values (checked exhaustively on the host and, bit for bit, by the policy_input parity tests).
-__device__ __forceinline__ float u8_over_255(uint32_t v) {
-    const float x = (float)v, r = 1.0f / 255.0f;
+__device__ __forceinline__ float u8_over_255_f(float x) {
+    const float r = 1.0f / 255.0f;
     const float q = __fmul_rn(x, r);
     const float e = __fmaf_rn(-q, 255.0f, x);
     return __fmaf_rn(e, r, q);
 }
+
+// Byte k of word w as a float without the (quarter-rate) integer-to-float conversion: one byte permute builds
+// 0x4B0000vv = 2^23 + v, one exact subtraction removes the 2^23.
+__device__ __forceinline__ float byte_as_float(uint32_t w, uint32_t k) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | k)) - 8388608.0f;
+}
+
+__device__ __forceinline__ float u8_over_255(uint32_t v) { return u8_over_255_f(byte_as_float(v, 0)); }
 
 __device__ __forceinline__ void load_frame(uint8_t *dst_smem, const uint8_t *src, int nbytes) {
     const int4 *s = reinterpret_cast<const int4 *>(src);
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(256) vn_gather_f32_chw_vec_kernel(const uint8_
 #pragma unroll
                 for (int px = 0; px < 4; ++px) {
                     const int b = px * C + ch;  // byte of the group: pixel-major, channel-minor (HWC)
-                    v[px] = u8_over_255((w[u][b >> 2] >> (8 * (b & 3))) & 255u);
+                    v[px] = u8_over_255_f(byte_as_float(w[u][b >> 2], b & 3));
                 }
                 asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o[u] + (int64_t)ch * hw), "f"(v[0]),
                              "f"(v[1]), "f"(v[2]), "f"(v[3])
@@ -389,7 +397,7 @@ __device__ __forceinline__ void store_group(float *o, const uint32_t *w, int c, 
         for (int px = 0; px < 4; ++px) {
             const int b = px * c + ch;
             // w[] is indexed with compile-time constants once c is known (c == 1 or c == 3 below)
-            v[px] = u8_over_255((w[b >> 2] >> (8 * (b & 3))) & 255u);
+            v[px] = u8_over_255_f(byte_as_float(w[b >> 2], b & 3));
         }
         asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + (int64_t)ch * hw), "f"(v[0]), "f"(v[1]),
                      "f"(v[2]), "f"(v[3])
