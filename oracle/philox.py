@@ -5,7 +5,7 @@ The reference draws resets from unseeded global Mersenne-Twister streams
 only defined under injected reset streams.  The device path's own per-env counter-based RNG is
 Philox4x32-10 keyed by ``seed`` with counter ``(global_env_id, reset_epoch, 0, 0)``; this file is
 its independent CPU restatement, checked against the Random123 known-answer vectors in
-tests/test_oracle_cpu.py.
+tests/test_oracle_golden.py (test_philox_known_answers).
 """
 import numpy as np
 
