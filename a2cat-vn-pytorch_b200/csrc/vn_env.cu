@@ -884,7 +884,9 @@ static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const v
 }
 
 // Pinned + device-mapped?  The answer for the last few pointers is remembered per thread: the query costs about
-// a microsecond and the host-facing step asks about the same three buffers every call.
+// a microsecond and the host-facing step asks about the same three buffers every call.  (A buffer that is freed and
+// whose address comes back as pageable memory would pass from the cache; the kernel then faults on the unmapped
+// address - a loud failure, and only for callers that free the staging buffers of a live env.)
 static bool is_mapped_host(const void *p) {
     constexpr int kSlots = 8;
     static thread_local const void *known[kSlots] = {nullptr};
