@@ -32,18 +32,36 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    cmd = [nvcc_path()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + \
-        ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libvn_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
-    return LIB
+    """Compiles into a temporary file and renames it over libvn_b200.so under an exclusive file lock: ranks of one
+    torchrun job that all find the library missing build one after the other (the later ones find it fresh and
+    return), and no process can ever CDLL a half-written file."""
+    import fcntl
+    import tempfile
+    with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            fd, tmp = tempfile.mkstemp(prefix=".libvn_b200.", suffix=".so.tmp", dir=PKG)
+            os.close(fd)
+            cmd = [nvcc_path()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + \
+                ["-I", os.path.join(ROOT, "include"), "-I", CSRC] + (["-Xptxas", "-v"] if verbose else []) + \
+                [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+            try:
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if res.returncode != 0:
+                    sys.stderr.write(res.stdout + res.stderr)
+                    raise RuntimeError("nvcc failed building libvn_b200.so")
+                os.chmod(tmp, 0o755)
+                os.replace(tmp, LIB)
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+            if verbose:
+                sys.stderr.write(res.stderr)
+            return LIB
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

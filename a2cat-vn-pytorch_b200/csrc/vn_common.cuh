@@ -16,6 +16,7 @@ namespace vn {
 
 void set_error(const char *fmt, ...);
 int32_t check_launch(const char *what);
+int sm_count();  // multiprocessors of the current device (cached per device)
 
 #define VN_REQUIRE(cond, ...)            \
     do {                                 \

@@ -311,6 +311,11 @@ struct GatherParams {
     uint8_t *goal_obs[VN_MAX_PLANES];
     unsigned int *sched;  // optional ticket counters (dynamic scheduling), see vn_gather_bulk_kernel
     int32_t n;
+    // 1: let the next kernel in the stream be scheduled while this one runs (the step path, where the successor is the
+    // next scalar kernel and never writes what this gather reads).  0 (vn_gather_plane): the index list is caller
+    // memory - often env.state / obs_state / goal themselves - that a following step kernel REWRITES, so the successor
+    // must not start before this grid has completed.
+    int32_t early_release;
 };
 
 // ---- variant A: 16-byte vector loads / stores through registers -------------------------------------
@@ -340,7 +345,7 @@ __device__ __forceinline__ void copy_segment16(const uint8_t *__restrict__ src, 
 template <int kThreads, int kUnroll>
 __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherParams p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.early_release) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (int env = blockIdx.x; env < p.n; env += gridDim.x) {
         int rec, grec = -1;
         if (p.desc) {
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the prologue above overlapped the scalar kernel; its results are needed from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (p.early_release) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     uint32_t parity = 0;
     BulkHints hints;
     // bits: 1 loads evict_last, 2 stores evict_first, 4 loads evict_first, 8 stores evict_last
@@ -641,7 +646,7 @@ static int current_device() {
     cudaGetDevice(&dev);
     return dev >= 0 && dev < kMaxDevices ? dev : 0;
 }
-static int sm_count() {
+int sm_count() {
     static int cached[kMaxDevices] = {0};
     const int dev = current_device();
     if (!cached[dev]) {
@@ -781,6 +786,7 @@ static int32_t make_gather_params(GatherParams &gp, const vn_store_t *store, con
     gp.goal = any_goal ? envs->goal : nullptr;
     gp.did_reset = out->did_reset;
     gp.sched = out->sched;
+    gp.early_release = 1;
     gp.desc = out->gather_desc
                   ? reinterpret_cast<const int2 *>(out->gather_desc) + (size_t)(out->parity & 1) * envs->n_envs
                   : nullptr;
@@ -1114,6 +1120,7 @@ int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *i
     gp.did_reset = nullptr;
     gp.desc = nullptr;
     gp.sched = nullptr;  // static unit assignment: no scratch in this signature
+    gp.early_release = 0;  // idx is caller memory a following step may rewrite: no early start of the successor
     gp.n = n;
     for (int pl = 0; pl < VN_MAX_PLANES; ++pl) {
         gp.obs[pl] = (pl == plane) ? out : nullptr;

@@ -25,10 +25,11 @@ __global__ void __launch_bounds__(256) vn_nstep_returns_kernel(const float *__re
                                                                const uint8_t *__restrict__ done,
                                                                const float *__restrict__ last_value, float gamma, int n,
                                                                int t, int64_t stride_n, int64_t stride_t,
-                                                               float *__restrict__ out) {
+                                                               float *__restrict__ out, int64_t ostride_n,
+                                                               int64_t ostride_t) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int64_t base = (int64_t)i * stride_n;
+    const int64_t base = (int64_t)i * stride_n, obase = (int64_t)i * ostride_n;
     // R_T = (1 - done[T-1]) * V(s_T)
     float ret = (1.0f - (float)done[base + (int64_t)(t - 1) * stride_t]) * last_value[i];
     for (int k = t - 1; k >= 0; --k) {
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) vn_nstep_returns_kernel(const float *__re
         // r + (gamma * R) * nd, evaluated in this order without contraction (nd is 0 or 1, so the
         // product by nd is exact and an FMA could not change the result either)
         ret = __fadd_rn(reward[at], __fmul_rn(__fmul_rn(gamma, ret), nd));
-        out[at] = ret;
+        out[obase + (int64_t)k * ostride_t] = ret;
     }
 }
 
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(128) vn_nstep_returns_scan_kernel(const float 
                                                                     const uint8_t *__restrict__ done,
                                                                     const float *__restrict__ last_value, float gamma,
                                                                     int n, int t, int64_t stride_n, int64_t stride_t,
-                                                                    float *__restrict__ out) {
+                                                                    float *__restrict__ out, int64_t ostride_n,
+                                                                    int64_t ostride_t) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128) vn_nstep_returns_scan_kernel(const float 
                 }
             }
             const float r = fmaf(a, carry, b);
-            if (k >= 0) out[base + (int64_t)k * stride_t] = r;
+            if (k >= 0) out[(int64_t)i * ostride_n + (int64_t)k * ostride_t] = r;
             carry = __shfl_sync(0xffffffffu, r, hi >= 32 ? 0 : 32 - hi);   // R at the first real step of the chunk
         }
     }
@@ -83,14 +85,15 @@ __global__ void __launch_bounds__(128) vn_nstep_returns_scan_kernel(const float 
 __global__ void __launch_bounds__(256) vn_backup_kernel(const float *__restrict__ reward,
                                                         const uint8_t *__restrict__ done,
                                                         const float *__restrict__ bootstrap, float gamma, int n, int t,
-                                                        int d, float *__restrict__ out) {
+                                                        int d, int64_t dstride_n, int64_t dstride_t,
+                                                        float *__restrict__ out) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)n * d) return;
     const int i = (int)(gid / d), f = (int)(gid - (int64_t)i * d);
     float ret = bootstrap[(int64_t)i * d + f];
     for (int k = t - 1; k >= 0; --k) {
         const int64_t at = ((int64_t)i * t + k) * d + f;
-        const float nd = 1.0f - (float)done[(int64_t)i * t + k];
+        const float nd = 1.0f - (float)done[(int64_t)i * dstride_n + (int64_t)k * dstride_t];
         ret = __fadd_rn(reward[at], __fmul_rn(__fmul_rn(gamma, ret), nd));
         out[at] = ret;
     }
@@ -157,7 +160,8 @@ __device__ __forceinline__ void pc_cells(const uint8_t *cur, const uint8_t *nxt,
 template <int kChunk>
 __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t store, int plane,
                                                                const int32_t *__restrict__ states, int n, int t,
-                                                               PoolGeom g, float *__restrict__ out) {
+                                                               int64_t sn, int64_t st, PoolGeom g,
+                                                               float *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int fbytes = g.h * g.w * g.c;
     uint8_t *frame0 = smem_raw;
@@ -166,14 +170,14 @@ __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t 
     const int env = blockIdx.x / chunks;
     const int k0 = (blockIdx.x - env * chunks) * kChunk;
     const int k1 = min(t, k0 + kChunk);
-    const int32_t *srow = states + (int64_t)env * (t + 1);
+    const int32_t *srow = states + (int64_t)env * sn;   // observation k of this env lives at srow[k * st]
     const uint8_t *pbase = store.base + store.plane_off[plane];
 
-    load_frame(frame0, pbase + (size_t)srow[k0] * store.state_pitch, fbytes);
+    load_frame(frame0, pbase + (size_t)srow[(int64_t)k0 * st] * store.state_pitch, fbytes);
     uint8_t *cur = frame0, *nxt = frame1;
     const int cells = g.out_h * g.out_w;
     for (int k = k0; k < k1; ++k) {
-        load_frame(nxt, pbase + (size_t)srow[k + 1] * store.state_pitch, fbytes);
+        load_frame(nxt, pbase + (size_t)srow[(int64_t)(k + 1) * st] * store.state_pitch, fbytes);
         __syncthreads();
         pc_cells(cur, nxt, g, out + ((int64_t)env * t + k) * cells);
         __syncthreads();
@@ -188,9 +192,10 @@ __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t 
 // device memory, so no host synchronisation is needed between the lookup pass and this one.
 __global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_store_t store, int plane,
                                                                     const int32_t *__restrict__ states, int t,
-                                                                    PoolGeom g, const int32_t *__restrict__ pos,
+                                                                    int64_t sn, int64_t st, PoolGeom g,
+                                                                    const int32_t *__restrict__ pos,
                                                                     const int32_t *__restrict__ count, int max_count,
-                                                                    float *__restrict__ out) {
+                                                                    int compact, float *__restrict__ out) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int fbytes = g.h * g.w * g.c;
     uint8_t *frame0 = smem_raw;
@@ -202,19 +207,21 @@ __global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_sto
     for (int m = blockIdx.x; m < m_total; m += gridDim.x) {
         const int p = pos[m];
         const int env = p / t, k = p - env * t;
-        const int32_t *srow = states + (int64_t)env * (t + 1);
+        const int32_t *srow = states + (int64_t)env * sn;
         __syncthreads();
-        load_frame(frame0, pbase + (size_t)srow[k] * store.state_pitch, fbytes);
-        load_frame(frame1, pbase + (size_t)srow[k + 1] * store.state_pitch, fbytes);
+        load_frame(frame0, pbase + (size_t)srow[(int64_t)k * st] * store.state_pitch, fbytes);
+        load_frame(frame1, pbase + (size_t)srow[(int64_t)(k + 1) * st] * store.state_pitch, fbytes);
         __syncthreads();
-        pc_cells(frame0, frame1, g, out + (int64_t)p * cells);
+        // compact: row m of a side buffer (consumed by vn_pixel_control_returns); else row p of the [n][t] output
+        pc_cells(frame0, frame1, g, out + (int64_t)(compact ? m : p) * cells);
     }
 }
 
 // rows[n][k] = pixel-control table row of transition states[n][k] -> states[n][k+1]
-constexpr int kRowZero = -1, kRowMiss = -2;
+constexpr int kRowZero = -1, kRowMiss = -2;   // a miss is stored as -(2 + m), m = its index in the miss list
 __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *__restrict__ adj,
                                                                  const int32_t *__restrict__ states, int n, int t,
+                                                                 int64_t sn, int64_t st,
                                                                  int32_t *__restrict__ rows,
                                                                  int32_t *__restrict__ miss_pos,
                                                                  int32_t *__restrict__ miss_count) {
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *
     bool miss = false;
     if (p < (int64_t)n * t) {
         const int env = (int)(p / t), k = (int)(p - (int64_t)env * t);
-        const int s = states[(int64_t)env * (t + 1) + k], s2 = states[(int64_t)env * (t + 1) + k + 1];
+        const int s = states[(int64_t)env * sn + (int64_t)k * st], s2 = states[(int64_t)env * sn + (int64_t)(k + 1) * st];
         int row = kRowMiss;
         if (s2 == s) {
             row = kRowZero;  // collision / no-op: identical frames, |x - x| = 0 exactly
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *
             else if (nb.w == s2)
                 row = s * 4 + 3;
         }
-        rows[p] = row;
+        if (row != kRowMiss) rows[p] = row;
         miss = row == kRowMiss;
     }
     // warp-aggregated append of the misses (ballot + one atomic per warp)
@@ -247,7 +254,11 @@ __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *
         int base = 0;
         if (lane == __ffs(b) - 1) base = atomicAdd(miss_count, __popc(b));
         base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
-        if (miss) miss_pos[base + __popc(b & ((1u << lane) - 1u))] = (int32_t)p;
+        if (miss) {
+            const int m = base + __popc(b & ((1u << lane) - 1u));
+            miss_pos[m] = (int32_t)p;
+            rows[p] = kRowMiss - m;
+        }
     }
 }
 
@@ -255,13 +266,16 @@ __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *
 // untouched (kRowMiss: the list kernel fills it).  One warp per row, grid-stride.
 __global__ void __launch_bounds__(256) vn_gather_rows_kernel(const int4 *__restrict__ table, int row16,
                                                              const int32_t *__restrict__ idx, int64_t n,
+                                                             int idx_t, int64_t sn, int64_t st,
                                                              int4 *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t i = warp0; i < n; i += nwarps) {
-        const int r = __ldg(idx + i);
-        if (r == kRowMiss) continue;
+        // output row i = (a, k) of an [n / idx_t][idx_t] batch-major result reads idx[a * sn + k * st]
+        const int64_t a = i / idx_t, k = i - a * idx_t;
+        const int r = __ldg(idx + a * sn + k * st);
+        if (r <= kRowMiss) continue;
         int4 *dst = out + i * row16;
         if (r < 0) {
             for (int k = lane; k < row16; k += 32) st_stream16(dst + k, make_int4(0, 0, 0, 0));
@@ -456,17 +470,73 @@ __global__ void __launch_bounds__(256) vn_gather_leaves_f32_kernel(const FloatLe
     }
 }
 
+// Pixel-control returns in ONE pass over the table rows: thread per (env, group of 4 cells), backward over t,
+//   pc(n, k) = table[rows[n][k]] | 0 (rows == -1: identical frames) | miss_rows[m] (rows == -(2 + m): reset transition,
+//              computed directly by vn_pixel_control_list in compact mode)
+//   R_T = bootstrap;  R_k = pc(n, k) + gamma * (1 - done(n, k)) * R_{k+1}     (same operation order as vn_backup_kernel)
+// The rewards are never written to memory unless out_reward is given: 1,600 B read + 1,600 B written per transition
+// instead of twice that for gather + back-up.
+__global__ void __launch_bounds__(256) vn_pc_returns_kernel(const float4 *__restrict__ table,
+                                                            const int32_t *__restrict__ rows,
+                                                            const float4 *__restrict__ miss_rows,
+                                                            const uint8_t *__restrict__ done, int64_t dsn, int64_t dst,
+                                                            const float4 *__restrict__ bootstrap, float gamma, int n,
+                                                            int t, int d4, float4 *__restrict__ out,
+                                                            float4 *__restrict__ out_reward) {
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)n * d4) return;
+    const int i = (int)(gid / d4), f = (int)(gid - (int64_t)i * d4);
+    float4 ret = bootstrap[(int64_t)i * d4 + f];
+    constexpr int kAhead = 4;   // loads of kAhead steps are issued before the dependent chain consumes them
+    for (int hi = t; hi > 0; hi -= kAhead) {
+        float4 v[kAhead];
+        float nd[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int k = hi - 1 - u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            nd[u] = 0.f;
+            if (k >= 0) {
+                const int r = __ldg(rows + (int64_t)i * t + k);
+                if (r >= 0)
+                    v[u] = __ldg(table + (int64_t)r * d4 + f);
+                else if (r <= kRowMiss)
+                    v[u] = __ldg(miss_rows + (int64_t)(kRowMiss - r) * d4 + f);
+                nd[u] = 1.0f - (float)done[(int64_t)i * dsn + (int64_t)k * dst];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int k = hi - 1 - u;
+            if (k < 0) break;
+            ret.x = __fadd_rn(v[u].x, __fmul_rn(__fmul_rn(gamma, ret.x), nd[u]));
+            ret.y = __fadd_rn(v[u].y, __fmul_rn(__fmul_rn(gamma, ret.y), nd[u]));
+            ret.z = __fadd_rn(v[u].z, __fmul_rn(__fmul_rn(gamma, ret.z), nd[u]));
+            ret.w = __fadd_rn(v[u].w, __fmul_rn(__fmul_rn(gamma, ret.w), nd[u]));
+            const int64_t at = ((int64_t)i * t + k) * d4 + f;
+            __stcs(out + at, ret);
+            if (out_reward) __stcs(out_reward + at, v[u]);
+        }
+    }
+}
+
 // =====================================================================================================
 // reward-prediction labels + order-preserving compaction of zero / non-zero positions
 // =====================================================================================================
 constexpr int kRpBlock = 1024;
 
-__global__ void __launch_bounds__(kRpBlock) vn_rp_count_kernel(const float *__restrict__ reward, int n,
-                                                               int8_t *__restrict__ labels,
+// Position i = (a, k) of the batch-major [n / t][t] result reads reward[a * sn + k * st] (t = 1, sn = 1: flat input).
+__device__ __forceinline__ float rp_reward(const float *__restrict__ reward, int i, int t, int64_t sn, int64_t st) {
+    const int a = i / t, k = i - a * t;
+    return reward[(int64_t)a * sn + (int64_t)k * st];
+}
+
+__global__ void __launch_bounds__(kRpBlock) vn_rp_count_kernel(const float *__restrict__ reward, int n, int t,
+                                                               int64_t sn, int64_t st, int8_t *__restrict__ labels,
                                                                int32_t *__restrict__ block_counts) {
     __shared__ int warp_nz[kRpBlock / 32];
     const int i = blockIdx.x * kRpBlock + threadIdx.x;
-    const float r = i < n ? reward[i] : 0.f;
+    const float r = i < n ? rp_reward(reward, i, t, sn, st) : 0.f;
     const bool nz = i < n && r != 0.f;
     if (i < n && labels) labels[i] = r > 0.f ? 1 : (r < 0.f ? 2 : 0);
     const unsigned b = __ballot_sync(0xffffffffu, nz);
@@ -520,14 +590,15 @@ __global__ void __launch_bounds__(1024) vn_rp_scan_kernel(int32_t *__restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(kRpBlock) vn_rp_scatter_kernel(const float *__restrict__ reward, int n,
+__global__ void __launch_bounds__(kRpBlock) vn_rp_scatter_kernel(const float *__restrict__ reward, int n, int t,
+                                                                 int64_t sn, int64_t st,
                                                                  const int32_t *__restrict__ block_offsets,
                                                                  int32_t *__restrict__ zero_idx,
                                                                  int32_t *__restrict__ nonzero_idx) {
     __shared__ int warp_nz[kRpBlock / 32];
     const int i = blockIdx.x * kRpBlock + threadIdx.x;
     const bool valid = i < n;
-    const bool nz = valid && reward[i] != 0.f;
+    const bool nz = valid && rp_reward(reward, i, t, sn, st) != 0.f;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned b = __ballot_sync(0xffffffffu, nz);
     if (lane == 0) warp_nz[wid] = __popc(b);
@@ -547,7 +618,7 @@ __global__ void __launch_bounds__(kRpBlock) vn_rp_scatter_kernel(const float *__
 // device-side UNREAL replay ring: uniform sampling of valid windows, one thread per env
 // =====================================================================================================
 struct ReplayParams {
-    const int32_t *before, *after, *goal, *action;  // [cap][n] time-major ring
+    const int32_t *before, *after, *goal, *goal_before, *action;  // [cap][n] time-major ring
     const float *reward;
     const uint8_t *done;
     int32_t n, cap, head, count;                     // head = next slot to write, count = filled slots (<= cap)
@@ -614,7 +685,9 @@ __global__ void __launch_bounds__(128) vn_replay_sample_kernel(const ReplayParam
     for (int k = 0; k < L; ++k) {
         const size_t at = (size_t)((oldest + start + k) % p.cap) * p.n + e;
         p.o_states[(size_t)e * (L + 1) + k] = p.before[at];
-        p.o_goals[(size_t)e * (L + 1) + k] = p.goal[at];
+        // goal of the episode the BEFORE observation belongs to (ring.goal is the goal after the step, i.e. the next
+        // episode's goal when the step ended one and the env auto-reset)
+        p.o_goals[(size_t)e * (L + 1) + k] = p.goal_before[at];
         p.o_actions[(size_t)e * L + k] = p.action[at];
         p.o_rewards[(size_t)e * L + k] = p.reward[at];
         p.o_dones[(size_t)e * L + k] = p.done[at];
@@ -649,35 +722,59 @@ static int32_t pool_geom(int h, int w, int c, int cell, int out_h, int out_w, Po
 extern "C" {
 
 int32_t vn_nstep_returns(const float *reward, const uint8_t *done, const float *last_value, float gamma, int32_t n,
-                         int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream) {
+                         int32_t t, int64_t stride_n, int64_t stride_t, float *out, int64_t out_stride_n,
+                         int64_t out_stride_t, void *stream) {
     VN_REQUIRE(reward && done && last_value && out, "nstep_returns: null pointer");
     VN_REQUIRE(n >= 0 && t >= 1, "nstep_returns: n=%d t=%d", n, t);
     if (n == 0) return VN_OK;
     vn::vn_nstep_returns_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reward, done, last_value, gamma, n, t, stride_n, stride_t, out);
+        reward, done, last_value, gamma, n, t, stride_n, stride_t, out, out_stride_n, out_stride_t);
     return vn::check_launch("vn_nstep_returns_kernel");
 }
 
 int32_t vn_nstep_returns_scan(const float *reward, const uint8_t *done, const float *last_value, float gamma,
-                              int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream) {
+                              int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, float *out,
+                              int64_t out_stride_n, int64_t out_stride_t, void *stream) {
     VN_REQUIRE(reward && done && last_value && out, "nstep_returns_scan: null pointer");
     VN_REQUIRE(n >= 0 && t >= 1, "nstep_returns_scan: n=%d t=%d", n, t);
     if (n == 0) return VN_OK;
-    const int64_t want = ((int64_t)n * 32 + 127) / 128, cap = 148 * 16;
+    const int64_t want = ((int64_t)n * 32 + 127) / 128, cap = (int64_t)vn::sm_count() * 16;
     vn::vn_nstep_returns_scan_kernel<<<(int)(want < cap ? want : cap), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        reward, done, last_value, gamma, n, t, stride_n, stride_t, out);
+        reward, done, last_value, gamma, n, t, stride_n, stride_t, out, out_stride_n, out_stride_t);
     return vn::check_launch("vn_nstep_returns_scan_kernel");
 }
 
-int32_t vn_discounted_backup(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,
-                             int32_t n, int32_t t, int32_t d, float *out, void *stream) {
+int32_t vn_discounted_backup(const float *reward, const uint8_t *done, int64_t done_stride_n, int64_t done_stride_t,
+                             const float *bootstrap, float gamma, int32_t n, int32_t t, int32_t d, float *out,
+                             void *stream) {
     VN_REQUIRE(reward && done && bootstrap && out, "discounted_backup: null pointer");
     VN_REQUIRE(n >= 0 && t >= 1 && d >= 1, "discounted_backup: n=%d t=%d d=%d", n, t, d);
     if (n == 0) return VN_OK;
     const int64_t total = (int64_t)n * d;
     vn::vn_backup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reward, done, bootstrap, gamma, n, t, d, out);
+        reward, done, bootstrap, gamma, n, t, d, done_stride_n, done_stride_t, out);
     return vn::check_launch("vn_backup_kernel");
+}
+
+int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int32_t *rows, const float *miss_rows,
+                                 const uint8_t *done, int64_t done_stride_n, int64_t done_stride_t,
+                                 const float *bootstrap, float gamma, int32_t n, int32_t t, float *out_returns,
+                                 float *out_reward, void *stream) {
+    VN_REQUIRE(pc_table && rows && miss_rows && done && bootstrap && out_returns, "pixel_control_returns: null pointer");
+    VN_REQUIRE(n >= 0 && t >= 1 && cells >= 4 && (cells & 3) == 0, "pixel_control_returns: n=%d t=%d cells=%d", n, t,
+               cells);
+    VN_REQUIRE(((reinterpret_cast<uintptr_t>(pc_table) | reinterpret_cast<uintptr_t>(miss_rows) |
+                 reinterpret_cast<uintptr_t>(bootstrap) | reinterpret_cast<uintptr_t>(out_returns) |
+                 reinterpret_cast<uintptr_t>(out_reward)) & 15) == 0,
+               "pixel_control_returns: arrays must be 16-byte aligned");
+    if (n == 0) return VN_OK;
+    const int d4 = cells >> 2;
+    const int64_t total = (int64_t)n * d4;
+    vn::vn_pc_returns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4 *>(pc_table), rows, reinterpret_cast<const float4 *>(miss_rows), done,
+        done_stride_n, done_stride_t, reinterpret_cast<const float4 *>(bootstrap), gamma, n, t, d4,
+        reinterpret_cast<float4 *>(out_returns), reinterpret_cast<float4 *>(out_reward));
+    return vn::check_launch("vn_pc_returns_kernel");
 }
 
 static int32_t check_plane(const vn_store_t *store, int32_t plane, int h, int w, int c, const char *who) {
@@ -693,8 +790,8 @@ static int32_t check_plane(const vn_store_t *store, int32_t plane, int h, int w,
 }
 
 int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
-                         int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out,
-                         void *stream) {
+                         int64_t state_stride_n, int64_t state_stride_t, int32_t h, int32_t w, int32_t c, int32_t cell,
+                         int32_t out_h, int32_t out_w, float *out, void *stream) {
     int32_t rc = check_plane(store, plane, h, w, c, "pixel_control");
     if (rc) return rc;
     VN_REQUIRE(states && out && n >= 0 && t >= 1, "pixel_control: bad arguments");
@@ -710,12 +807,13 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
     const int64_t blocks = (int64_t)n * ((t + kChunk - 1) / kChunk);
     VN_REQUIRE(blocks < (1ll << 31), "pixel_control: too many blocks");
     vn::vn_pixel_control_kernel<kChunk><<<(unsigned)blocks, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        *store, plane, states, n, t, g, out);
+        *store, plane, states, n, t, state_stride_n, state_stride_t, g, out);
     return vn::check_launch("vn_pixel_control_kernel");
 }
 
-int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int32_t *rows,
-                           int32_t *miss_pos, int32_t *miss_count, void *stream) {
+int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int64_t state_stride_n,
+                           int64_t state_stride_t, int32_t *rows, int32_t *miss_pos, int32_t *miss_count,
+                           void *stream) {
     VN_REQUIRE(adj && states && rows && miss_pos && miss_count, "transition_rows: null pointer");
     VN_REQUIRE(n >= 0 && t >= 1, "transition_rows: n=%d t=%d", n, t);
     VN_REQUIRE((reinterpret_cast<uintptr_t>(adj) & 15) == 0, "transition_rows: adj must be 16-byte aligned");
@@ -723,27 +821,31 @@ int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaMemsetAsync(miss_count, 0, sizeof(int32_t), st);
     const int64_t total = (int64_t)n * t;
-    vn::vn_transition_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(adj, states, n, t, rows, miss_pos,
-                                                                                  miss_count);
+    vn::vn_transition_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        adj, states, n, t, state_stride_n, state_stride_t, rows, miss_pos, miss_count);
     return vn::check_launch("vn_transition_rows_kernel");
 }
 
-int32_t vn_gather_rows(const void *table, int64_t row_bytes, const int32_t *idx, int64_t n, void *out, void *stream) {
+int32_t vn_gather_rows(const void *table, int64_t row_bytes, const int32_t *idx, int64_t n, int32_t idx_t,
+                       int64_t idx_stride_n, int64_t idx_stride_t, void *out, void *stream) {
     VN_REQUIRE(table && idx && out, "gather_rows: null pointer");
+    VN_REQUIRE(idx_t >= 1 && n % idx_t == 0, "gather_rows: n=%lld is not a multiple of idx_t=%d", (long long)n, idx_t);
     VN_REQUIRE(row_bytes > 0 && (row_bytes & 15) == 0, "gather_rows: row_bytes=%lld must be a multiple of 16",
                (long long)row_bytes);
     VN_REQUIRE(((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                "gather_rows: table and out must be 16-byte aligned");
     if (n <= 0) return VN_OK;
-    const int64_t warps = n < 148 * 64 ? n : 148 * 64;
+    const int64_t cap = (int64_t)vn::sm_count() * 64, warps = n < cap ? n : cap;
     vn::vn_gather_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const int4 *>(table), (int)(row_bytes >> 4), idx, n, static_cast<int4 *>(out));
+        static_cast<const int4 *>(table), (int)(row_bytes >> 4), idx, n, idx_t, idx_stride_n, idx_stride_t,
+        static_cast<int4 *>(out));
     return vn::check_launch("vn_gather_rows_kernel");
 }
 
 int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
-                              int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w,
-                              const int32_t *pos, const int32_t *count, int32_t max_count, float *out, void *stream) {
+                              int64_t state_stride_n, int64_t state_stride_t, int32_t h, int32_t w, int32_t c,
+                              int32_t cell, int32_t out_h, int32_t out_w, const int32_t *pos, const int32_t *count,
+                              int32_t max_count, int32_t compact, float *out, void *stream) {
     int32_t rc = check_plane(store, plane, h, w, c, "pixel_control_list");
     if (rc) return rc;
     VN_REQUIRE(states && pos && count && out && n >= 0 && t >= 1 && max_count >= 0, "pixel_control_list: bad arguments");
@@ -756,16 +858,17 @@ int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int3
     VN_REQUIRE(smem <= 220 * 1024, "pixel_control_list: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_pixel_control_list_kernel, smem);
     const int per_sm = (220 * 1024) / (smem + 1024) < 8 ? ((220 * 1024) / (smem + 1024) < 1 ? 1 : (220 * 1024) / (smem + 1024)) : 8;
-    const int grid = max_count < 148 * per_sm ? max_count : 148 * per_sm;
+    const int grid = max_count < vn::sm_count() * per_sm ? max_count : vn::sm_count() * per_sm;
     vn::vn_pixel_control_list_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        *store, plane, states, t, g, pos, count, max_count, out);
+        *store, plane, states, t, state_stride_n, state_stride_t, g, pos, count, max_count, compact, out);
     return vn::check_launch("vn_pixel_control_list_kernel");
 }
 
 int32_t vn_replay_sample(const vn_replay_t *ring, int32_t length, int32_t mode, uint64_t seed, uint32_t call,
                          int32_t env_id_base, int32_t *o_states, int32_t *o_goals, int32_t *o_actions,
                          float *o_rewards, uint8_t *o_dones, int32_t *o_start, int8_t *o_label, void *stream) {
-    VN_REQUIRE(ring && ring->before && ring->after && ring->goal && ring->action && ring->reward && ring->done,
+    VN_REQUIRE(ring && ring->before && ring->after && ring->goal && ring->goal_before && ring->action && ring->reward &&
+                   ring->done,
                "replay_sample: null ring pointer");
     VN_REQUIRE(ring->n >= 0 && ring->cap > 0 && ring->count >= 0 && ring->count <= ring->cap && ring->head >= 0 &&
                    ring->head < ring->cap,
@@ -778,6 +881,7 @@ int32_t vn_replay_sample(const vn_replay_t *ring, int32_t length, int32_t mode, 
     p.before = ring->before;
     p.after = ring->after;
     p.goal = ring->goal;
+    p.goal_before = ring->goal_before;
     p.action = ring->action;
     p.reward = ring->reward;
     p.done = ring->done;
@@ -813,7 +917,7 @@ int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx
     const int smem = (h * w * c + 15) & ~15;
     VN_REQUIRE(smem <= 220 * 1024, "aux_target: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_aux_target_kernel, smem);
-    const int grid = m < 148 * 8 ? m : 148 * 8;
+    const int grid = m < vn::sm_count() * 8 ? m : vn::sm_count() * 8;
     vn::vn_aux_target_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, m, g, out);
     return vn::check_launch("vn_aux_target_kernel");
 }
@@ -832,10 +936,7 @@ int32_t vn_gather_plane_f32_chw_rows(const vn_store_t *store, int32_t plane, con
     if ((h * w) % 4 == 0 && (c == 1 || c == 3) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         // whole 4-pixel groups: the vectorised kernel (0.36 -> see DESIGN.md of the copy peak for the staged one)
         const int64_t total = (int64_t)n * (h * w / 4);
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        const int64_t want = (total + 4 * 256 - 1) / (4 * 256), cap = (int64_t)sms * 16;
+        const int64_t want = (total + 4 * 256 - 1) / (4 * 256), cap = (int64_t)vn::sm_count() * 16;
         const int grid = (int)(want < cap ? want : cap);
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         const uint8_t *pbase = store->base + store->plane_off[plane];
@@ -850,7 +951,7 @@ int32_t vn_gather_plane_f32_chw_rows(const vn_store_t *store, int32_t plane, con
     const int smem = (h * w * c + 15) & ~15;
     VN_REQUIRE(smem <= 220 * 1024, "gather_plane_f32_chw: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_gather_f32_chw_kernel, smem);
-    const int grid = n < 148 * 8 ? n : 148 * 8;
+    const int grid = n < vn::sm_count() * 8 ? n : vn::sm_count() * 8;
     vn::vn_gather_f32_chw_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*store, plane, idx, idx_stride,
                                                                                         n, h, w, c, out);
     return vn::check_launch("vn_gather_f32_chw_kernel");
@@ -889,12 +990,9 @@ int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t 
         L.goal[l] = leaves[l].source;
     }
     if (n == 0) return VN_OK;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     const int64_t total = (int64_t)n * (h * w / 4);
     const int unroll = n_leaves == 1 ? 4 : (n_leaves <= 3 ? 2 : 1);
-    const int64_t want = (total + unroll * 256 - 1) / (unroll * 256), cap = (int64_t)sms * 16;
+    const int64_t want = (total + unroll * 256 - 1) / (unroll * 256), cap = (int64_t)vn::sm_count() * 16;
     const int grid = (int)(want < cap ? want : cap);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int2 *d2 = reinterpret_cast<const int2 *>(desc);
@@ -910,17 +1008,21 @@ int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t 
     return vn::check_launch("vn_gather_leaves_f32_kernel");
 }
 
-int32_t vn_rp_labels(const float *reward, int32_t n, int8_t *labels, int32_t *zero_idx, int32_t *nonzero_idx,
-                     int32_t *counts, int32_t *scratch, void *stream) {
+int32_t vn_rp_labels(const float *reward, int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, int8_t *labels,
+                     int32_t *zero_idx, int32_t *nonzero_idx, int32_t *counts, int32_t *scratch, void *stream) {
     VN_REQUIRE(reward && scratch, "rp_labels: reward and scratch are required");
     VN_REQUIRE(n >= 0 && n <= (1 << 24), "rp_labels: n=%d (max 2^24 per call)", n);
+    VN_REQUIRE(t >= 1 && n % t == 0, "rp_labels: n=%d is not a multiple of t=%d", n, t);
     if (n == 0) return VN_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int blocks = (n + vn::kRpBlock - 1) / vn::kRpBlock;
-    vn::vn_rp_count_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, labels, scratch);
+    vn::vn_rp_count_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, t, stride_n, stride_t, labels, scratch);
+    vn::check_launch("vn_rp_count_kernel");
     vn::vn_rp_scan_kernel<<<1, 1024, 0, st>>>(scratch, blocks, n, counts);
+    vn::check_launch("vn_rp_scan_kernel");
     if (zero_idx || nonzero_idx)
-        vn::vn_rp_scatter_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, scratch, zero_idx, nonzero_idx);
+        vn::vn_rp_scatter_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, t, stride_n, stride_t, scratch, zero_idx,
+                                                                  nonzero_idx);
     return vn::check_launch("vn_rp_labels");
 }
 

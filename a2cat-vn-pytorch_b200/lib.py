@@ -22,7 +22,7 @@ RULE_AUTO_RESET = 0x40
 GATHER_AUTO, GATHER_LDG, GATHER_BULK, GATHER_FUSED = 0, 1, 2, 3
 STEP_ACTIONS_READY = 0x01
 STEP_SKIP_UNCHANGED = 0x02
-ABI_VERSION = 2
+ABI_VERSION = 3
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "steps", "truncations", "resets",
               "rows_skipped")
 
@@ -65,7 +65,8 @@ class StepOut(C.Structure):
 
 
 class Replay(C.Structure):
-    _fields_ = [("before", _P), ("after", _P), ("goal", _P), ("action", _P), ("reward", _P), ("done", _P),
+    _fields_ = [("before", _P), ("after", _P), ("goal", _P), ("goal_before", _P), ("action", _P), ("reward", _P),
+                ("done", _P),
                 ("n", C.c_int32), ("cap", C.c_int32), ("head", C.c_int32), ("count", C.c_int32)]
 
 
@@ -84,7 +85,7 @@ _lib = None
 EXPORTS = ("vn_abi_version", "vn_abi_struct_size", "vn_last_error", "vn_launch_count", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
            "vn_env_gather", "vn_env_step_host", "vn_env_step_host_sync", "vn_env_host_seq_words", "vn_host_wait_seq", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_gather_plane_f32_chw_rows", "vn_gather_leaves_f32_chw", "vn_nstep_returns", "vn_nstep_returns_scan", "vn_discounted_backup", "vn_pixel_control",
-           "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_replay_sample",
+           "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_pixel_control_returns", "vn_replay_sample",
            "vn_aux_target", "vn_rp_labels")
 
 
@@ -101,9 +102,12 @@ def load(build_if_missing=True):
     if build_if_missing and _build.needs_build():
         try:
             _build.build()
-        except Exception as e:   # keep a stale-but-present library usable on boxes without nvcc
+        except Exception as e:   # keep a stale-but-present library usable on boxes without nvcc - but say so
             if not os.path.exists(path):
                 raise VnError("libvn_b200.so is missing and could not be built: %s" % e)
+            import warnings
+            warnings.warn("libvn_b200.so is OLDER than its sources and the rebuild failed (%s): running the stale "
+                          "library (the ABI version and struct sizes are still checked below)" % e, RuntimeWarning)
     if not os.path.exists(path):
         raise VnError("libvn_b200.so not found at %s - run `python __graft_entry__.py` (build()) first" % path)
     lib = C.CDLL(path)
@@ -130,16 +134,18 @@ def load(build_if_missing=True):
         "vn_gather_plane_f32_chw": (i32, [S, i32, _P, i32, i32, i32, i32, _P, _P]),
         "vn_gather_plane_f32_chw_rows": (i32, [S, i32, _P, i32, i32, i32, i32, i32, _P, _P]),
         "vn_gather_leaves_f32_chw": (i32, [S, C.POINTER(FloatLeaf), i32, _P, i32, i32, i32, _P]),
-        "vn_nstep_returns": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, _P]),
-        "vn_nstep_returns_scan": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, _P]),
-        "vn_discounted_backup": (i32, [_P, _P, _P, f32, i32, i32, i32, _P, _P]),
-        "vn_pixel_control": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, i32, _P, _P]),
-        "vn_transition_rows": (i32, [_P, _P, i32, i32, _P, _P, _P, _P]),
-        "vn_gather_rows": (i32, [_P, i64, _P, i64, _P, _P]),
-        "vn_pixel_control_list": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, i32, _P, _P, i32, _P, _P]),
+        "vn_nstep_returns": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, i64, i64, _P]),
+        "vn_nstep_returns_scan": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, i64, i64, _P]),
+        "vn_discounted_backup": (i32, [_P, _P, i64, i64, _P, f32, i32, i32, i32, _P, _P]),
+        "vn_pixel_control": (i32, [S, i32, _P, i32, i32, i64, i64, i32, i32, i32, i32, i32, i32, _P, _P]),
+        "vn_transition_rows": (i32, [_P, _P, i32, i32, i64, i64, _P, _P, _P, _P]),
+        "vn_gather_rows": (i32, [_P, i64, _P, i64, i32, i64, i64, _P, _P]),
+        "vn_pixel_control_list": (i32, [S, i32, _P, i32, i32, i64, i64, i32, i32, i32, i32, i32, i32, _P, _P, i32, i32,
+                                        _P, _P]),
+        "vn_pixel_control_returns": (i32, [_P, i32, _P, _P, _P, i64, i64, _P, f32, i32, i32, _P, _P, _P]),
         "vn_replay_sample": (i32, [C.POINTER(Replay), i32, i32, u64, C.c_uint32, i32, _P, _P, _P, _P, _P, _P, _P, _P]),
         "vn_aux_target": (i32, [S, i32, _P, i32, i32, i32, i32, i32, i32, i32, _P, _P]),
-        "vn_rp_labels": (i32, [_P, i32, _P, _P, _P, _P, _P, _P]),
+        "vn_rp_labels": (i32, [_P, i32, i32, i64, i64, _P, _P, _P, _P, _P, _P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -20,42 +20,54 @@ def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _strided2d(x, dtype):
+    """A 2-D tensor as the kernels take it: any element strides (a ``.t()`` view of time-major rollout storage is
+    read in place, no transpose kernel), the given dtype (bool is read as uint8 in place)."""
+    if x.dtype == torch.bool and dtype == torch.uint8:
+        x = x.view(torch.uint8)
+    if x.dtype != dtype:
+        x = x.to(dtype)
+    if x.dim() != 2:
+        raise ValueError("expected a 2-D [B, T] tensor, got %s" % (tuple(x.shape),))
+    return x
+
+
 def nstep_returns(rewards, dones, last_values, gamma, time_major=False, method="serial"):
     """A2C n-step returns (deep_rl RolloutStorage.batch).
-    rewards float32, dones uint8/bool: [B, T] (or [T, B] with time_major=True); last_values [B].
+    rewards float32, dones uint8/bool: [B, T] with ANY strides (``storage.t()`` views are read in place); last_values
+    [B].  Returns a contiguous [B, T] tensor.  ``time_major=True``: the arguments are [T, B] and so is the result.
     method="serial" (default): thread per env, the reference's loop order, bit-identical to it.
     method="scan": warp per env, 32 steps per pass composed with shuffles - for few envs and long rollouts; equal
     within ~1e-6 relative (float re-association), not bit for bit."""
     lib = L.load()
     fn = {"serial": lib.vn_nstep_returns, "scan": lib.vn_nstep_returns_scan}[method]
-    rewards = rewards.contiguous().float()
-    dones = dones.contiguous().to(torch.uint8)
-    last_values = last_values.contiguous().float()
+    rewards, dones = _strided2d(rewards, torch.float32), _strided2d(dones, torch.uint8)
     if time_major:
-        t, n = rewards.shape
-        sn, st = 1, n
-    else:
-        n, t = rewards.shape
-        sn, st = t, 1
-    out = torch.empty_like(rewards)
+        rewards, dones = rewards.t(), dones.t()
+    if dones.stride() != rewards.stride():
+        rewards, dones = rewards.contiguous(), dones.contiguous()
+    last_values = last_values.contiguous().float()
+    n, t = rewards.shape
+    out = torch.empty((t, n) if time_major else (n, t), dtype=torch.float32, device=rewards.device)
+    ob = out.t() if time_major else out
     with torch.cuda.device(rewards.device):
-        L.check(fn(rewards.data_ptr(), dones.data_ptr(), last_values.data_ptr(), float(gamma), n, t, sn, st,
-                   out.data_ptr(), _stream(rewards)))
+        L.check(fn(rewards.data_ptr(), dones.data_ptr(), last_values.data_ptr(), float(gamma), n, t, rewards.stride(0),
+                   rewards.stride(1), out.data_ptr(), ob.stride(0), ob.stride(1), _stream(rewards)))
     return out
 
 
 def discounted_backup(rewards, dones, bootstrap, gamma):
-    """rewards [B, T, ...]; dones [B, T]; bootstrap [B, ...] -> R_t = r_t + gamma (1 - done_t) R_{t+1}."""
+    """rewards [B, T, ...]; dones [B, T] (any strides); bootstrap [B, ...] -> R_t = r_t + gamma (1 - done_t) R_{t+1}."""
     lib = L.load()
     b, t = rewards.shape[:2]
     d = rewards[0, 0].numel()
     rewards = rewards.contiguous().float()
-    dones = dones.contiguous().to(torch.uint8)
+    dones = _strided2d(dones, torch.uint8)
     bootstrap = bootstrap.contiguous().float()
     out = torch.empty_like(rewards)
     with torch.cuda.device(rewards.device):
-        L.check(lib.vn_discounted_backup(rewards.data_ptr(), dones.data_ptr(), bootstrap.data_ptr(), float(gamma), b, t,
-                                         d, out.data_ptr(), _stream(rewards)))
+        L.check(lib.vn_discounted_backup(rewards.data_ptr(), dones.data_ptr(), dones.stride(0), dones.stride(1),
+                                         bootstrap.data_ptr(), float(gamma), b, t, d, out.data_ptr(), _stream(rewards)))
     return out
 
 
@@ -69,20 +81,29 @@ def _geom(dw, plane, cell, output_size):
     return pi, h, w, c, int(output_size[0]), int(output_size[1])
 
 
+def _states2d(dw, states):
+    if states.device != dw.device or states.dtype != torch.int32:
+        states = states.to(device=dw.device, dtype=torch.int32)
+    if states.dim() != 2:
+        raise ValueError("states must be [B, T+1]")
+    return states
+
+
 def _pixel_control_direct(dw, states, cell_size, output_size, plane):
     lib = L.load()
     pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
     b, t1 = states.shape
     out = torch.empty((b, t1 - 1, 1, oh, ow), dtype=torch.float32, device=dw.device)
     with torch.cuda.device(dw.device):
-        L.check(lib.vn_pixel_control(C.byref(dw.store), pi, states.data_ptr(), b, t1 - 1, h, w, c, cell_size, oh, ow,
-                                     out.data_ptr(), _stream(states)))
+        L.check(lib.vn_pixel_control(C.byref(dw.store), pi, states.data_ptr(), b, t1 - 1, states.stride(0),
+                                     states.stride(1), h, w, c, cell_size, oh, ow, out.data_ptr(), _stream(states)))
     return out
 
 
 def _aux_direct(dw, states, plane, cell_size, output_size):
     lib = L.load()
     pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
+    states = states.contiguous()
     out = torch.empty(tuple(states.shape) + (c, oh, ow), dtype=torch.float32, device=dw.device)
     with torch.cuda.device(dw.device):
         L.check(lib.vn_aux_target(C.byref(dw.store), pi, states.data_ptr(), states.numel(), h, w, c, cell_size, oh, ow,
@@ -115,6 +136,7 @@ class TargetTables:
         for lo in range(0, 4 * S, step):
             self.pc[lo:lo + step] = _pixel_control_direct(dw, pairs[lo:lo + step], cell_size, (oh, ow), plane).view(-1, oh * ow)
         self._aux = {}
+        self._scratch = {}
 
     def aux(self, plane):
         if plane not in self._aux:
@@ -122,6 +144,14 @@ class TargetTables:
             me = torch.arange(S, dtype=torch.int32, device=self.dw.device)
             self._aux[plane] = _aux_direct(self.dw, me, plane, self.cell, self.out_hw).contiguous()
         return self._aux[plane]
+
+    def scratch(self, n):
+        """(rows, miss_pos, miss_count) int32 scratch for n transitions, reused between calls on the same stream."""
+        if n not in self._scratch:
+            dev = self.dw.device
+            self._scratch = {n: (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
+                                 torch.empty(1, dtype=torch.int32, device=dev))}
+        return self._scratch[n]
 
     def nbytes(self):
         return self.pc.numel() * 4 + sum(t.numel() * 4 for t in self._aux.values())
@@ -139,47 +169,93 @@ def target_tables(dw: DeviceWorld, cell_size=4, output_size=None, plane="rgb") -
 
 def pixel_control_reward(dw: DeviceWorld, states, cell_size=4, output_size=None, plane="rgb", method="table"):
     """deep_rl.a2c_unreal.util.pixel_control_reward computed from state indices.
-    states: int32 [B, T+1] GLOBAL state of every observation of the sequence -> float32 [B, T, 1, h, w].
+    states: int32 [B, T+1] (any strides) GLOBAL state of every observation of the sequence -> float32 [B, T, 1, h, w].
 
     method="table" (default): rows of the per-world transition table (TargetTables) are gathered; the few
     transitions the table cannot serve (resets) are computed directly by a list kernel in the same pass.
     method="direct": every transition is computed from the two frames.  Both give identical bits."""
     lib = L.load()
     pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
-    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
+    states = _states2d(dw, states)
     if method == "direct" or (oh * ow) % 4:
         return _pixel_control_direct(dw, states, cell_size, (oh, ow), plane)
     tab = target_tables(dw, cell_size, (oh, ow), plane)
     b, t1 = states.shape
     t = t1 - 1
     out = torch.empty((b, t, 1, oh, ow), dtype=torch.float32, device=dw.device)
-    rows = torch.empty(b * t, dtype=torch.int32, device=dw.device)
-    miss_pos = torch.empty(b * t, dtype=torch.int32, device=dw.device)
-    miss_count = torch.empty(1, dtype=torch.int32, device=dw.device)
+    rows, miss_pos, miss_count = tab.scratch(b * t)
+    sn, st_ = states.stride()
     with torch.cuda.device(dw.device):
         st = _stream(states)
-        L.check(lib.vn_transition_rows(dw.adj.data_ptr(), states.data_ptr(), b, t, rows.data_ptr(), miss_pos.data_ptr(),
-                                       miss_count.data_ptr(), st))
-        L.check(lib.vn_gather_rows(tab.pc.data_ptr(), oh * ow * 4, rows.data_ptr(), b * t, out.data_ptr(), st))
-        L.check(lib.vn_pixel_control_list(C.byref(dw.store), pi, states.data_ptr(), b, t, h, w, c, cell_size, oh, ow,
-                                          miss_pos.data_ptr(), miss_count.data_ptr(), b * t, out.data_ptr(), st))
+        L.check(lib.vn_transition_rows(dw.adj.data_ptr(), states.data_ptr(), b, t, sn, st_, rows.data_ptr(),
+                                       miss_pos.data_ptr(), miss_count.data_ptr(), st))
+        L.check(lib.vn_gather_rows(tab.pc.data_ptr(), oh * ow * 4, rows.data_ptr(), b * t, 1, 1, 0, out.data_ptr(), st))
+        L.check(lib.vn_pixel_control_list(C.byref(dw.store), pi, states.data_ptr(), b, t, sn, st_, h, w, c, cell_size, oh,
+                                          ow, miss_pos.data_ptr(), miss_count.data_ptr(), b * t, 0, out.data_ptr(), st))
     return out
+
+
+def pixel_control_returns(dw: DeviceWorld, states, dones, bootstrap, gamma, cell_size=4, output_size=None, plane="rgb",
+                          with_reward=False, max_miss=None):
+    """Pixel-control rewards AND their discounted back-up (UNREAL: gamma_pc = 0.9, bootstrap = max_a Q_aux(s_T);
+    SURVEY.md D5) in one pass over the per-world transition table: equal, bit for bit, to
+    ``discounted_backup(pixel_control_reward(states), dones, bootstrap, gamma)`` without ever writing the rewards.
+
+    states int32 [B, T+1], dones uint8/bool [B, T] (any strides: ``storage.t()`` views are read in place), bootstrap
+    float32 [B, h*w] (or [B, h, w]).  Returns float32 [B, T, h*w] (and the rewards [B, T, h*w] with with_reward).
+    max_miss bounds the side buffer for the transitions the table cannot serve (episode resets; default: all B*T)."""
+    lib = L.load()
+    pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
+    cells = oh * ow
+    if cells % 4:
+        r = pixel_control_reward(dw, states, cell_size, (oh, ow), plane).view(states.shape[0], -1, cells)
+        ret = discounted_backup(r, dones, bootstrap.reshape(states.shape[0], cells), gamma)
+        return (ret, r) if with_reward else ret
+    states = _states2d(dw, states)
+    dones = _strided2d(dones, torch.uint8)
+    tab = target_tables(dw, cell_size, (oh, ow), plane)
+    b, t1 = states.shape
+    t = t1 - 1
+    bootstrap = bootstrap.reshape(b, cells).contiguous().float()
+    out = torch.empty((b, t, cells), dtype=torch.float32, device=dw.device)
+    rew = torch.empty((b, t, cells), dtype=torch.float32, device=dw.device) if with_reward else None
+    rows, miss_pos, miss_count = tab.scratch(b * t)
+    max_miss = b * t if max_miss is None else int(max_miss)
+    key = ("miss", max_miss, cells)
+    side = tab._aux.get(key)
+    if side is None:
+        side = tab._aux[key] = torch.empty((max(max_miss, 1), cells), dtype=torch.float32, device=dw.device)
+    sn, st_ = states.stride()
+    with torch.cuda.device(dw.device):
+        st = _stream(states)
+        L.check(lib.vn_transition_rows(dw.adj.data_ptr(), states.data_ptr(), b, t, sn, st_, rows.data_ptr(),
+                                       miss_pos.data_ptr(), miss_count.data_ptr(), st))
+        L.check(lib.vn_pixel_control_list(C.byref(dw.store), pi, states.data_ptr(), b, t, sn, st_, h, w, c, cell_size, oh,
+                                          ow, miss_pos.data_ptr(), miss_count.data_ptr(), max_miss, 1, side.data_ptr(), st))
+        L.check(lib.vn_pixel_control_returns(tab.pc.data_ptr(), cells, rows.data_ptr(), side.data_ptr(), dones.data_ptr(),
+                                             dones.stride(0), dones.stride(1), bootstrap.data_ptr(), float(gamma), b, t,
+                                             out.data_ptr(), L.ptr(rew), st))
+    return (out, rew) if with_reward else out
 
 
 def auxiliary_target(dw: DeviceWorld, states, plane, cell_size=4, output_size=None, method="table"):
     """compute_auxiliary_target (experiments/ai2_auxiliary/trainer.py:9-15) from state indices.
-    states int32 [B, T] -> float32 [B, T, C, h, w].  method="table": one row gather from the per-world
+    states int32 [B, T] (any strides) -> float32 [B, T, C, h, w].  method="table": one row gather from the per-world
     pooled-plane table; method="direct": pooled from the frame."""
     lib = L.load()
     pi, h, w, c, oh, ow = _geom(dw, plane, cell_size, output_size)
-    states = states.to(device=dw.device, dtype=torch.int32).contiguous()
+    if states.device != dw.device or states.dtype != torch.int32:
+        states = states.to(device=dw.device, dtype=torch.int32)
     if method == "direct" or (c * oh * ow) % 4:
         return _aux_direct(dw, states, plane, cell_size, (oh, ow))
+    shape = tuple(states.shape)
+    if states.dim() != 2:
+        states = states.contiguous().view(-1, 1)
     tab = target_tables(dw, cell_size, (oh, ow)).aux(plane)
-    out = torch.empty(tuple(states.shape) + (c, oh, ow), dtype=torch.float32, device=dw.device)
+    out = torch.empty(shape + (c, oh, ow), dtype=torch.float32, device=dw.device)
     with torch.cuda.device(dw.device):
-        L.check(lib.vn_gather_rows(tab.data_ptr(), c * oh * ow * 4, states.data_ptr(), states.numel(), out.data_ptr(),
-                                   _stream(states)))
+        L.check(lib.vn_gather_rows(tab.data_ptr(), c * oh * ow * 4, states.data_ptr(), states.numel(), states.shape[1],
+                                   states.stride(0), states.stride(1), out.data_ptr(), _stream(states)))
     return out
 
 
@@ -203,35 +279,43 @@ def policy_input(dw: DeviceWorld, states, plane="rgb"):
     return out
 
 
-def reward_prediction_labels(rewards, with_lists=True):
+def reward_prediction_labels(rewards, with_lists=True, sync=True):
     """UNREAL reward-prediction classes (0 zero / 1 positive / 2 negative) and the ascending lists of
-    zero / non-zero reward positions (flattened) that the 50/50 sampler draws from.
-    Returns (labels int8 like rewards, zero_idx int32, nonzero_idx int32); the lists are device tensors
-    trimmed to their lengths (one 8-byte D2H read for the two counts)."""
+    zero / non-zero reward positions (row-major positions of the [B, T] argument, whatever its strides) that the
+    50/50 sampler draws from.
+    Returns (labels int8 [B, T] contiguous, zero_idx int32, nonzero_idx int32).  sync=True: the lists are trimmed
+    to their lengths (one 8-byte D2H read for the two counts).  sync=False: nothing waits for the device - the
+    lists come back at full length together with a device tensor ``counts`` = (#zero, #non-zero) as a 4th value."""
     lib = L.load()
-    r = rewards.contiguous().float()
+    r = rewards if rewards.dtype == torch.float32 else rewards.float()
+    flat = r.dim() != 2
+    if flat:
+        r = r.contiguous().view(-1, 1).t()        # [1, n]: positions in storage order
     n = r.numel()
-    labels = torch.empty(r.shape, dtype=torch.int8, device=r.device)
+    labels = torch.empty(tuple(rewards.shape), dtype=torch.int8, device=r.device)
     if n == 0:
         e = torch.empty(0, dtype=torch.int32, device=r.device)
         return labels, (e if with_lists else None), (e.clone() if with_lists else None)
     scratch = torch.empty((n + 1023) // 1024 + 1, dtype=torch.int32, device=r.device)
-    counts = torch.zeros(2, dtype=torch.int32, device=r.device)
+    counts = torch.empty(2, dtype=torch.int32, device=r.device)     # always written by the scan kernel
     zero = torch.empty(n, dtype=torch.int32, device=r.device) if with_lists else None
     nonzero = torch.empty(n, dtype=torch.int32, device=r.device) if with_lists else None
     with torch.cuda.device(r.device):
-        L.check(lib.vn_rp_labels(r.data_ptr(), n, labels.data_ptr(), L.ptr(zero), L.ptr(nonzero), counts.data_ptr(),
-                                 scratch.data_ptr(), _stream(r)))
+        L.check(lib.vn_rp_labels(r.data_ptr(), n, r.shape[1], r.stride(0), r.stride(1), labels.data_ptr(), L.ptr(zero),
+                                 L.ptr(nonzero), counts.data_ptr(), scratch.data_ptr(), _stream(r)))
     if not with_lists:
         return labels, None, None
+    if not sync:
+        return labels, zero, nonzero, counts
     cz, cn = counts.tolist()
     return labels, zero[:cz], nonzero[:cn]
 
 
 class RolloutBuffer:
     """Device-resident rollout of T steps x B envs: int32 states / goals, float32 rewards, uint8 dones,
-    int32 actions; time-major storage (each env step appends one contiguous row), batch-major views
-    handed to the builders."""
+    int32 actions; time-major storage (each env step appends one contiguous row).  The builders read the storage in
+    place through ``.t()`` views (explicit strides at the C ABI) and write batch-major ``[B, T, ...]`` results like the
+    reference tensors: no transpose or copy kernel between the step and the loss."""
 
     def __init__(self, dw: DeviceWorld, num_envs, num_steps):
         self.dw, self.B, self.T = dw, num_envs, num_steps
@@ -245,7 +329,7 @@ class RolloutBuffer:
 
     def start(self, env):
         """Records the observation the rollout starts from (after reset() or the previous rollout)."""
-        self.states[0].copy_(env.obs_state)
+        self.states[0].copy_(env.obs_state)      # contiguous same-dtype rows: cudaMemcpyAsync, not a kernel
         self.goals[0].copy_(env.goal)
         self.t = 0
 
@@ -271,18 +355,23 @@ class RolloutBuffer:
 
     def returns(self, last_values, gamma):
         """[B, T] n-step returns."""
-        return nstep_returns(self.rewards, self.dones, last_values, gamma, time_major=True).t().contiguous()
+        return nstep_returns(self.rewards.t(), self.dones.t(), last_values, gamma)
 
     def pixel_control(self, cell_size=4, output_size=None):
-        return pixel_control_reward(self.dw, self.states.t().contiguous(), cell_size, output_size)
+        return pixel_control_reward(self.dw, self.states.t(), cell_size, output_size)
+
+    def pixel_control_returns(self, bootstrap, gamma, cell_size=4, output_size=None, with_reward=False, max_miss=None):
+        """[B, T, h*w] discounted pixel-control returns (rewards + back-up in one pass, see pixel_control_returns)."""
+        return pixel_control_returns(self.dw, self.states.t(), self.dones.t(), bootstrap, gamma, cell_size, output_size,
+                                     with_reward=with_reward, max_miss=max_miss)
 
     def auxiliary_targets(self, cell_size=4, output_size=None):
-        s = self.states[:-1].t().contiguous()
-        g = self.goals[:-1].t().contiguous()
-        return auxiliary_targets(self.dw, s, g, cell_size, output_size)
+        return auxiliary_targets(self.dw, self.states[:-1].t(), self.goals[:-1].t(), cell_size, output_size)
 
-    def reward_prediction(self):
-        return reward_prediction_labels(self.rewards.t().contiguous())
+    def reward_prediction(self, sync=False):
+        """(labels [B, T], zero positions, non-zero positions, counts) - see reward_prediction_labels; sync=False
+        (default here) keeps the whole data pass free of host synchronisation."""
+        return reward_prediction_labels(self.rewards.t(), sync=sync)
 
 
 class ReplayRing:
@@ -299,13 +388,15 @@ class ReplayRing:
         dev = dw.device
         z = lambda dt: torch.zeros((capacity, num_envs), dtype=dt, device=dev)
         self.before, self.after, self.goal, self.action = z(torch.int32), z(torch.int32), z(torch.int32), z(torch.int32)
+        self.goal_before = z(torch.int32)      # goal of the BEFORE observation (differs from `goal` across an auto-reset)
         self.reward, self.done = z(torch.float32), z(torch.uint8)
         self.head, self.count, self.calls = 0, 0, 0
-        self._prev = None
+        self._prev = self._prev_goal = None
 
     def start(self, env):
         """Remember the observation the next inserted step starts from (after reset())."""
         self._prev = env.obs_state.clone()
+        self._prev_goal = env.goal.clone()
 
     def insert(self, env, actions):
         """Call after env.step(actions)."""
@@ -313,12 +404,14 @@ class ReplayRing:
             raise RuntimeError("ReplayRing.start(env) must be called after env.reset()")
         h = self.head
         self.before[h].copy_(self._prev)
+        self.goal_before[h].copy_(self._prev_goal)
         self.after[h].copy_(env.obs_state)
         self.goal[h].copy_(env.goal)
         self.action[h].copy_(actions.to(torch.int32) if torch.is_tensor(actions) else torch.as_tensor(actions))
         self.reward[h].copy_(env.reward)
         self.done[h].copy_(env.done)
         self._prev.copy_(env.obs_state)
+        self._prev_goal.copy_(env.goal)
         self.head = (h + 1) % self.cap
         self.count = min(self.count + 1, self.cap)
 
@@ -330,8 +423,8 @@ class ReplayRing:
             return
         if T > self.cap:
             raise ValueError("rollout of %d steps does not fit a replay ring of %d" % (T, self.cap))
-        src = dict(before=buf.states[:T], after=buf.states[1:T + 1], goal=buf.goals[1:T + 1], action=buf.actions[:T],
-                   reward=buf.rewards[:T], done=buf.dones[:T])
+        src = dict(before=buf.states[:T], after=buf.states[1:T + 1], goal=buf.goals[1:T + 1], goal_before=buf.goals[:T],
+                   action=buf.actions[:T], reward=buf.rewards[:T], done=buf.dones[:T])
         h = self.head
         first = min(T, self.cap - h)
         for name, rows in src.items():
@@ -340,9 +433,10 @@ class ReplayRing:
             if first < T:
                 dst[:T - first].copy_(rows[first:])
         if self._prev is None:
-            self._prev = buf.states[T].clone()
+            self._prev, self._prev_goal = buf.states[T].clone(), buf.goals[T].clone()
         else:
             self._prev.copy_(buf.states[T])
+            self._prev_goal.copy_(buf.goals[T])
         self.head = (h + T) % self.cap
         self.count = min(self.count + T, self.cap)
 
@@ -358,7 +452,8 @@ class ReplayRing:
                    start=torch.full((n,), -1, dtype=torch.int32, device=dev))
         if mode == 1:
             out["label"] = torch.zeros(n, dtype=torch.int8, device=dev)
-        ring = L.Replay(self.before.data_ptr(), self.after.data_ptr(), self.goal.data_ptr(), self.action.data_ptr(),
+        ring = L.Replay(self.before.data_ptr(), self.after.data_ptr(), self.goal.data_ptr(), self.goal_before.data_ptr(),
+                        self.action.data_ptr(),
                         self.reward.data_ptr(), self.done.data_ptr(), n, self.cap, self.head, self.count)
         with torch.cuda.device(dev):
             L.check(lib.vn_replay_sample(C.byref(ring), Lw, mode, C.c_uint64(self.seed), self.calls, self.env_id_base,

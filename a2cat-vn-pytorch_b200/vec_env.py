@@ -298,6 +298,7 @@ class GraphVecEnv:
                             1 if name.startswith("goal_") else 0, buf.shape[1], 0, buf.data_ptr())
                 for name, buf in self.float_buf.items()])
         self._pending = False
+        self._h2d_done = None
         self._serial_next = False
         self._obs_cache = None
         self.closed = False
@@ -455,6 +456,9 @@ class GraphVecEnv:
         gather was enqueued (pre-computed action streams, CUDA-graph replays): the scalar kernel of this step
         then overlaps the previous gather (include/vn_b200.h VN_STEP_ACTIONS_READY)."""
         self._check_open()
+        if self._pending:
+            # the staging buffers (pinned actions, host pack) of the step in flight would be overwritten
+            raise RuntimeError("step_async() called again before step_wait()")
         inj = C.byref(self._c_inject) if self._c_inject is not None else None
         if self.host_outputs and not (torch.is_tensor(actions) and actions.is_cuda):
             # reference-facing path: host actions in, host scalars out - ONE C call enqueues
@@ -482,8 +486,15 @@ class GraphVecEnv:
             a = a.contiguous()
         else:
             src = actions if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions))
+            # one pinned staging buffer: the asynchronous H2D copy of the PREVIOUS step must have read it before it
+            # is rewritten (step_wait does not synchronise when host_outputs is False)
+            if self._h2d_done is not None:
+                self._h2d_done.synchronize()
             self._actions_host.copy_(src.reshape(-1).to(torch.int32))
             self.actions_dev.copy_(self._actions_host, non_blocking=True)
+            if self._h2d_done is None:
+                self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.device))
             a = self.actions_dev
         if a.numel() != self.num_envs:
             raise ValueError("expected %d actions, got %d" % (self.num_envs, a.numel()))

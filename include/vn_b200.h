@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VN_ABI_VERSION 2
+#define VN_ABI_VERSION 3
 #define VN_MAX_PLANES 6 /* rgb, depth, segmentation (+ the 3 third-person planes of graph/thor_graph.py:25-31) */
 
 /* error codes */
@@ -267,7 +267,9 @@ int32_t vn_event_destroy(void *event);
 int32_t vn_event_wait(void *event);      /* cudaEventSynchronize; releases the GIL under ctypes */
 
 /* out[i] = plane `plane` of store record idx[i] (replay / sample_sequence gathers,
- * experiments/ai2_auxiliary/trainer.py:29). */
+ * experiments/ai2_auxiliary/trainer.py:29).  idx may be live env state (envs->state, out->obs_state, envs->goal): the
+ * kernel does not release its stream successor early, so a following vn_env_step* call - even one with
+ * VN_STEP_ACTIONS_READY - only starts rewriting those arrays after this gather has completed. */
 int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *idx, int32_t n, uint8_t *out,
                         int32_t gather_variant, void *stream);
 
@@ -297,55 +299,81 @@ typedef struct vn_float_leaf {
 int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t *leaves /* [host] */, int32_t n_leaves,
                                  const int32_t *desc /* [n][2] */, int32_t n, int32_t h, int32_t w, void *stream);
 
+/* Index conventions of the rollout builders.  A rollout storage is TIME-major (row t of a [T, n_envs] array is
+ * what one env step appends; deep_rl RolloutStorage), the tensors a loss consumes are BATCH-major ([B, T, ...] like
+ * the reference's).  Every builder therefore takes its INPUT arrays with explicit element strides - element (n, t)
+ * lives at n * stride_n + t * stride_t: (T, 1) for batch-major, (1, n_envs) for time-major storage - and writes its
+ * output batch-major, so no transpose kernel ever runs between the storage and the loss. */
+
 /* A2C n-step returns (deep_rl RolloutStorage.batch):
  *   R_T = (1 - done[T-1]) * last_value;  R_t = reward[t] + gamma * (1 - done[t]) * R_{t+1}.
- * Element (n, t) of reward/done/out lives at n * stride_n + t * stride_t. */
+ * Element (n, t) of reward / done lives at n * stride_n + t * stride_t, of out at n * out_stride_n + t * out_stride_t. */
 int32_t vn_nstep_returns(const float *reward, const uint8_t *done, const float *last_value, float gamma, int32_t n,
-                         int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream);
+                         int32_t t, int64_t stride_n, int64_t stride_t, float *out, int64_t out_stride_n,
+                         int64_t out_stride_t, void *stream);
 
 /* The same returns by a warp-level scan (one warp per env, 32 steps per pass, affine maps composed with shuffles):
  * for few envs and long rollouts.  Re-associates the float operations: within ~1e-6 relative of vn_nstep_returns,
  * not bit-identical. */
 int32_t vn_nstep_returns_scan(const float *reward, const uint8_t *done, const float *last_value, float gamma,
-                              int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, float *out, void *stream);
+                              int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, float *out,
+                              int64_t out_stride_n, int64_t out_stride_t, void *stream);
 
 /* Backward discounted scan with a trailing feature axis of width d (pixel-control returns):
- *   R_T = bootstrap;  R_t = reward[t] + gamma * (1 - done[t]) * R_{t+1};  arrays are [n][t][d]. */
-int32_t vn_discounted_backup(const float *reward, const uint8_t *done, const float *bootstrap, float gamma,
-                             int32_t n, int32_t t, int32_t d, float *out, void *stream);
+ *   R_T = bootstrap;  R_t = reward[t] + gamma * (1 - done[t]) * R_{t+1};  reward / out are [n][t][d], bootstrap [n][d],
+ * done(n, t) lives at n * done_stride_n + t * done_stride_t. */
+int32_t vn_discounted_backup(const float *reward, const uint8_t *done, int64_t done_stride_n, int64_t done_stride_t,
+                             const float *bootstrap, float gamma, int32_t n, int32_t t, int32_t d, float *out,
+                             void *stream);
 
 /* UNREAL pixel-control reward (deep_rl.a2c_unreal.util.pixel_control_reward) computed
- * straight from the store: for states[n][0..t] (t+1 entries, row stride t+1)
- *   out[n][k] = mean_c avg_pool_cell( | f(states[n][k+1]) - f(states[n][k]) | ),  f = plane / 255 in fp32,
+ * straight from the store: for the t + 1 observations states(n, 0..t) of every env (element (n, k) at
+ * n * state_stride_n + k * state_stride_t)
+ *   out[n][k] = mean_c avg_pool_cell( | f(states(n, k+1)) - f(states(n, k)) | ),  f = plane / 255 in fp32,
  * centred crop to (out_h*cell, out_w*cell).  out is [n][t][out_h][out_w] float32. */
 int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
-                         int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out,
-                         void *stream);
+                         int64_t state_stride_n, int64_t state_stride_t, int32_t h, int32_t w, int32_t c, int32_t cell,
+                         int32_t out_h, int32_t out_w, float *out, void *stream);
 
 /* Table-driven pixel control.  On a cached graph the pixel-control reward of a transition is a pure
  * function of the state pair, so it is computed ONCE per (state, action) into a table
  * pc_table[n_states * 4][out_h * out_w] (vn_pixel_control over the pairs (s, adj[s][a])) and a rollout's
  * rewards become row gathers:
  *   vn_transition_rows   rows[n][k] = s*4 + a with adj[s][a] == s' ; -1 (zeros) when s' == s (collision /
- *                        no-op: identical frames); -2 for transitions the table cannot serve (resets):
- *                        their positions n*t + k are appended to miss_pos and counted in miss_count[0]
- *   vn_gather_rows       out[i] = table[idx[i]] (rows of row_bytes, multiple of 16); idx -1 writes zeros,
- *                        idx -2 leaves the row untouched.  Also serves the auxiliary-target tables.
+ *                        no-op: identical frames); -(2 + m) for transitions the table cannot serve (resets):
+ *                        their positions n*t + k are appended to miss_pos[m] and counted in miss_count[0]
+ *   vn_gather_rows       out[i] = table[idx(i)] (rows of row_bytes, multiple of 16); idx -1 writes zeros,
+ *                        idx <= -2 leaves the row untouched.  Output row i = (a, k) of a batch-major
+ *                        [n / idx_t][idx_t] result reads idx[a * idx_stride_n + k * idx_stride_t] (a flat index
+ *                        list is idx_t = 1, strides (1, 0)).  Also serves the auxiliary-target tables.
  *   vn_pixel_control_list direct computation for the listed positions (count read from device memory,
- *                        at most max_count), written into the same [n][t][out_h][out_w] output. */
-int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int32_t *rows,
-                           int32_t *miss_pos, int32_t *miss_count, void *stream);
-int32_t vn_gather_rows(const void *table, int64_t row_bytes, const int32_t *idx, int64_t n, void *out, void *stream);
+ *                        at most max_count), written into row p of the same [n][t][out_h][out_w] output, or
+ *                        (compact != 0) into row m of a side buffer [max_count][out_h][out_w]
+ *   vn_pixel_control_returns  the discounted back-up (gamma_pc = 0.9 from max_a Q(s_T)) fused with
+ *                        the row gather: R_T = bootstrap; R_k = pc(n, k) + gamma (1 - done(n, k)) R_{k+1} with
+ *                        pc(n, k) = table[rows] | 0 | miss_rows[m] read on the fly; out_returns [n][t][cells],
+ *                        out_reward (optional) receives pc itself.  cells must be a multiple of 4. */
+int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int64_t state_stride_n,
+                           int64_t state_stride_t, int32_t *rows, int32_t *miss_pos, int32_t *miss_count,
+                           void *stream);
+int32_t vn_gather_rows(const void *table, int64_t row_bytes, const int32_t *idx, int64_t n, int32_t idx_t,
+                       int64_t idx_stride_n, int64_t idx_stride_t, void *out, void *stream);
 int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
-                              int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h, int32_t out_w,
-                              const int32_t *pos, const int32_t *count, int32_t max_count, float *out, void *stream);
+                              int64_t state_stride_n, int64_t state_stride_t, int32_t h, int32_t w, int32_t c,
+                              int32_t cell, int32_t out_h, int32_t out_w, const int32_t *pos, const int32_t *count,
+                              int32_t max_count, int32_t compact, float *out, void *stream);
+int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int32_t *rows, const float *miss_rows,
+                                 const uint8_t *done, int64_t done_stride_n, int64_t done_stride_t,
+                                 const float *bootstrap, float gamma, int32_t n, int32_t t, float *out_returns,
+                                 float *out_reward, void *stream);
 
 /* Device-side UNREAL experience replay (deep_rl's replay behind `self.replay.sample_sequence()`,
  * experiments/ai2_auxiliary/trainer.py:29, and sample_rp_sequence).
  * The ring holds state INDICES, not frames: per inserted env step the state observed before the action,
- * the state observed after it (post auto-reset), goal, action, reward, done; time-major [cap][n]. */
+ * the state observed after it (post auto-reset), the goal of each of the two observations (they differ when
+ * the step ended an episode and the env drew a new task), action, reward, done; time-major [cap][n]. */
 typedef struct vn_replay {
-    const int32_t *before, *after, *goal, *action;
+    const int32_t *before, *after, *goal, *goal_before, *action;
     const float *reward;
     const uint8_t *done;
     int32_t n, cap;
@@ -370,11 +398,13 @@ int32_t vn_aux_target(const vn_store_t *store, int32_t plane, const int32_t *idx
                       int32_t c, int32_t cell, int32_t out_h, int32_t out_w, float *out, void *stream);
 
 /* Reward-prediction classes (0 zero, 1 positive, 2 negative) and the ascending position lists of
- * zero / non-zero rewards the 50/50 sampler draws from.  counts[0..1] receive the list
- * lengths.  Ballot / warp-scan compaction in three small launches, order preserving, up to 2^24
- * positions per call; scratch is int32 [(n + 1023) / 1024] caller-owned device memory. */
-int32_t vn_rp_labels(const float *reward, int32_t n, int8_t *labels, int32_t *zero_idx, int32_t *nonzero_idx,
-                     int32_t *counts, int32_t *scratch, void *stream);
+ * zero / non-zero rewards the 50/50 sampler draws from.  n positions in all; position
+ * i = (a, k) of the batch-major [n / t][t] result reads reward[a * stride_n + k * stride_t] (flat input: t = 1,
+ * strides (1, 0)).  counts[0..1] receive the list lengths (always written).  Ballot / warp-scan compaction in three
+ * small launches, order preserving, up to 2^24 positions per call; scratch is int32 [(n + 1023) / 1024]
+ * caller-owned device memory. */
+int32_t vn_rp_labels(const float *reward, int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, int8_t *labels,
+                     int32_t *zero_idx, int32_t *nonzero_idx, int32_t *counts, int32_t *scratch, void *stream);
 
 #ifdef __cplusplus
 }

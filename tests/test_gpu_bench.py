@@ -22,11 +22,20 @@ def test_default_arm_json_contract():
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 300 and d["scaling"] == "weak" and d["dtype"] == "u8"
     assert d["config"]["workload"].startswith("C2") and "model" not in d["config"]
-    assert d["gpu_launches"] == 600 and d["value"] > 0
+    import argparse
+    import bench
+    assert d["config"] == bench.static_config(argparse.Namespace(workload="c2", envs_per_gpu=None, hardness="none"), 1)
+    rs = d["run_stats"]
+    # a 300-step block is ~10 ms: the region is repeated until it lasts >= 0.2 s, the median block is reported
+    assert rs["blocks"] >= 5 and rs["timed_steps_total"] == 300 * rs["blocks"] and rs["timed_region_ms"] >= 150
+    assert rs["ms_per_step_min"] <= d["ms_per_step"] <= rs["ms_per_step_max"]
+    assert d["gpu_launches"] == rs["launches_per_step"] * 300 * rs["blocks"] and d["value"] > 0
+    assert d["clocks"]["samples"] >= 5
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["traffic"] is None or r["traffic"] > 0
+    assert r["traffic"] is None or (r["traffic"] > 0 and r["dram_frac"] > 0)
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4 * 4096 and e["d2h_bytes_per_step"] == 20 * 4096
+    assert {"numpy_obs", "aux5_scaled_float", "aux5_uint8"} <= set(e["variants"])
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
-    assert {"rgb_only", "float_chw", "a2c_pass"} <= set(d["secondary"])
+    assert {"rgb_only", "float_chw", "a2c_pass", "reference_run_config"} <= set(d["secondary"])
