@@ -15,6 +15,10 @@
 
 #include "vn_common.cuh"
 
+#ifndef VN_PERSISTENT_DEFAULT
+#define VN_PERSISTENT_DEFAULT 0  // VN_GATHER_AUTO beyond one wave: 0 = scalar kernel + gather kernel, 1 = persistent launch
+#endif
+
 namespace vn {
 
 static thread_local std::string g_error;
@@ -574,6 +578,100 @@ __global__ void __launch_bounds__(kFusedWarps * 32) vn_step_fused_kernel(const S
     bulk_wait_read<0>();
 }
 
+// ---- persistent single launch for large batches -----------------------------------------------------
+// ONE launch per vectorised step for batches beyond one wave of CTAs: a persistent grid of one-warp CTAs (as many per
+// SM as shared memory holds records).  CTA b OWNS the envs b, b + G, b + 2G, ... for the whole launch:
+//   phase A  its lanes step those envs (step_env, one env per lane and round) - every env of the batch is stepped
+//            within the first microseconds of the launch, so a host caller gets rewards / dones while the copies run:
+//            lane 1 issues ONE system-scope fence for the CTA's writes to the mapped host pack and arrives on a
+//            device counter; the last CTA to arrive publishes `seq` in host_seq[0];
+//   phase B  lane 0 moves the records of the same envs with bulk async copies (global -> shared -> global), reading
+//            the (record, goal record) pairs its own warp just wrote to the gather descriptors.
+// No CTA ever waits for another one (ownership is static), nothing goes through a second launch, and there is no
+// descriptor hand-off between kernels: the scalar kernel, the PDL hand-off and the ticket counter of the two-kernel
+// path are gone.  Records that need slicing (split > 1) stay on the two-kernel path.
+template <bool kReset>
+__global__ void __launch_bounds__(32) vn_step_gather_kernel(const StepParams sp, const GatherParams gp, int hint_mode) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    const int lane = threadIdx.x;
+    if (lane == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // everything above overlapped the previous kernel of the stream; its env state is needed from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int n = sp.env.n_envs, G = (int)gridDim.x, b = (int)blockIdx.x;
+    int2 *desc = reinterpret_cast<int2 *>(sp.out.gather_desc) + (size_t)(sp.out.parity & 1) * n;
+
+    // ---- phase A: step the envs this CTA owns
+    EnvStats acc;
+    for (int base = b; base < n; base += 32 * G) {   // uniform trip count across the warp
+        const int e = base + lane * G;
+        if (e < n) {
+            EnvStats st;
+            int rec, grec;
+            step_env<kReset>(sp, e, st, rec, grec);
+            desc[e] = make_int2(rec, grec);
+            acc.episodes += st.episodes;
+            acc.len += st.len;
+            acc.succ += st.succ;
+            acc.coll += st.coll;
+            acc.steps += st.steps;
+            acc.trunc += st.trunc;
+            acc.resets += st.resets;
+            acc.skipped += st.skipped;
+            acc.ret += st.ret;
+        }
+    }
+    if (sp.out.stats) {
+        EnvStats w;
+        w.episodes = warp_sum(acc.episodes);
+        w.len = warp_sum(acc.len);
+        w.succ = warp_sum(acc.succ);
+        w.coll = warp_sum(acc.coll);
+        w.steps = warp_sum(acc.steps);
+        w.trunc = warp_sum(acc.trunc);
+        w.resets = warp_sum(acc.resets);
+        w.skipped = warp_sum(acc.skipped);
+        w.ret = acc.ret;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w.ret += __shfl_xor_sync(0xffffffffu, w.ret, o);
+        if (lane == 0) add_stats(sp.out.stats, w);
+    }
+    __syncwarp();   // the lanes' descriptor / host-pack writes are ordered before what lanes 0 and 1 do next
+    if (lane == 1 && sp.out.host_seq) {
+        // one system-scope fence per CTA (cumulative over the warp's writes ordered by the barrier above), then arrive;
+        // the last CTA publishes the sequence word the host spins on and re-arms the counter
+        __threadfence_system();
+        unsigned int *arrive = sp.out.sched + 2;
+        if (atomicAdd(arrive, 1u) == (unsigned int)G - 1u) {
+            *arrive = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(sp.out.host_seq) = sp.out.seq;
+        }
+    }
+    if (lane != 0) return;
+
+    // ---- phase B: copy the records of the same envs
+    uint32_t parity = 0;
+    BulkHints hints;
+    hints.load_policy = (hint_mode & 1) ? l2_policy_evict_last() : (hint_mode & 4) ? l2_policy_evict_first() : 0;
+    hints.store_policy = (hint_mode & 2) ? l2_policy_evict_first() : (hint_mode & 8) ? l2_policy_evict_last() : 0;
+    hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
+    for (int e = b; e < n; e += G) {
+        const int2 d = desc[e];
+        if (d.x >= 0)  // < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
+            bulk_copy_slice(gp.store, gp.store.base + (size_t)d.x * gp.store.state_pitch, gp.obs, e, 0, 1, smem, &bar,
+                            parity, hints);
+        if (d.y >= 0 && gp.goal)
+            bulk_copy_slice(gp.store, gp.store.base + (size_t)d.y * gp.store.state_pitch, gp.goal_obs, e, 0, 1, smem, &bar,
+                            parity, hints);
+    }
+    bulk_wait_read<0>();
+}
+
 // =====================================================================================================
 // synthetic store fill
 // =====================================================================================================
@@ -664,7 +762,8 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         VN_REQUIRE(!gp.goal_obs[pl] || (reinterpret_cast<uintptr_t>(gp.goal_obs[pl]) & 15) == 0,
                    "gather: goal_obs[%d] must be 16-byte aligned", pl);
     }
-    if (variant == VN_GATHER_FUSED) variant = VN_GATHER_BULK;  // no scalar half here: the fused launch does not apply
+    if (variant == VN_GATHER_FUSED || variant == VN_GATHER_PERSISTENT)
+        variant = VN_GATHER_BULK;  // no scalar half here: the one-launch modes do not apply
     // measured on B200 (profiles/): the bulk-copy variant reaches 94 % of the copy peak, LDG.128 86 %
     if (variant == VN_GATHER_AUTO) variant = VN_GATHER_BULK;
     if (variant == VN_GATHER_LDG) {
@@ -804,7 +903,8 @@ static int32_t run_gather(const vn_store_t *store, const vn_envs_t *envs, const 
     int32_t rc = make_gather_params(gp, store, envs, out, &any);
     if (rc) return rc;
     if (!any) return VN_OK;
-    if (variant == VN_GATHER_FUSED) variant = VN_GATHER_BULK;  // the halves were requested separately
+    if (variant == VN_GATHER_FUSED || variant == VN_GATHER_PERSISTENT)
+        variant = VN_GATHER_BULK;  // the halves were requested separately
     return launch_gather(gp, variant, static_cast<cudaStream_t>(stream));
 }
 
@@ -851,6 +951,67 @@ static int32_t run_fused(const vn_store_t *store, const vn_tables_t *tab, const 
     return check_launch("vn_step_fused_kernel");
 }
 
+// Shared memory of one CTA of the persistent single launch (largest of the observation / goal plane sets), or 0 when
+// the batch does not qualify: needs the descriptor and scheduler scratch, whole records per CTA (no slicing) and at
+// least two CTAs per SM.
+static int32_t persistent_smem_bytes(const vn_store_t *store, const vn_step_out_t *out) {
+    if (!out || !out->gather_desc || !out->sched) return 0;
+    int obs = 0, goal = 0;
+    for (int pl = 0; pl < store->n_planes; ++pl) {
+        if (out->obs[pl]) obs += store->plane_bytes[pl];
+        if (out->goal_obs[pl]) goal += store->plane_bytes[pl];
+    }
+    const int smem = max(obs, goal);
+    if (smem == 0 || smem > 52 * 1024) return 0;   // >= 4 CTAs per SM; larger records are sliced by the two-kernel path
+    return smem;
+}
+
+static int32_t run_persistent(const vn_store_t *store, const vn_tables_t *tab, const vn_envs_t *envs,
+                              const vn_rules_t *rules, const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask,
+                              const vn_step_out_t *out, void *stream, bool reset, int32_t *actions_copy, int32_t smem) {
+    StepParams sp;
+    int32_t rc = make_step_params(sp, tab, envs, rules, inj, actions, mask, out, reset, actions_copy);
+    if (rc) return rc;
+    GatherParams gp;
+    bool any = false;
+    rc = make_gather_params(gp, store, envs, out, &any);
+    if (rc) return rc;
+    for (int pl = 0; pl < gp.store.n_planes; ++pl) {
+        VN_REQUIRE(!gp.obs[pl] || (reinterpret_cast<uintptr_t>(gp.obs[pl]) & 15) == 0,
+                   "gather: obs[%d] must be 16-byte aligned", pl);
+        VN_REQUIRE(!gp.goal_obs[pl] || (reinterpret_cast<uintptr_t>(gp.goal_obs[pl]) & 15) == 0,
+                   "gather: goal_obs[%d] must be 16-byte aligned", pl);
+    }
+    static int configured[kMaxDevices][2] = {{0, 0}};
+    const int dev = current_device();
+    if (smem > configured[dev][reset]) {
+        if (reset)
+            cudaFuncSetAttribute(vn_step_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        else
+            cudaFuncSetAttribute(vn_step_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured[dev][reset] = smem;
+    }
+    static const int env_per_sm = getenv("VN_BULK_PER_SM") ? atoi(getenv("VN_BULK_PER_SM")) : 0;
+    static const int env_hints = getenv("VN_BULK_L2_HINTS") ? atoi(getenv("VN_BULK_L2_HINTS")) : 3;
+    int per_sm = max(1, min(32, (220 * 1024) / (smem + 1024)));
+    if (env_per_sm > 0) per_sm = min(per_sm, env_per_sm);
+    const int grid = (int)min((int64_t)envs->n_envs, (int64_t)sm_count() * per_sm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (reset)
+        launch_pdl(vn_step_gather_kernel<true>, dim3(grid), dim3(32), (size_t)smem, st, sp, gp, env_hints);
+    else
+        launch_pdl(vn_step_gather_kernel<false>, dim3(grid), dim3(32), (size_t)smem, st, sp, gp, env_hints);
+    return check_launch("vn_step_gather_kernel");
+}
+
+enum StepMode { kModeError = -1, kModeSplit = 0, kModeFused = 1, kModePersistent = 2 };
+
+// How vn_env_reset / vn_env_step / vn_env_step_host run: *smem receives the dynamic shared memory of the one-launch
+// modes.  VN_GATHER_AUTO: the CTA-per-env fused launch for batches of one wave, the persistent launch beyond that when
+// the batch qualifies, else scalar kernel + gather kernel.
+static StepMode choose_mode(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant,
+                            int32_t *smem);
+
 // -1: error already set; 0: two launches; > 0: fused, shared memory bytes
 static int32_t choose_fused(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant) {
     if (variant != VN_GATHER_FUSED && variant != VN_GATHER_AUTO) return 0;
@@ -874,6 +1035,34 @@ static int32_t choose_fused(const vn_store_t *store, const vn_envs_t *envs, cons
     return smem;
 }
 
+static StepMode choose_mode(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant,
+                            int32_t *smem) {
+    *smem = 0;
+    if (variant == VN_GATHER_PERSISTENT) {
+        *smem = persistent_smem_bytes(store, out);
+        if (*smem <= 0) {
+            set_error("gather(persistent): needs out->gather_desc, out->sched and plane sets of at most 52 KB per env");
+            return kModeError;
+        }
+        return kModePersistent;
+    }
+    const int32_t fused = choose_fused(store, envs, out, variant);
+    if (fused < 0) return kModeError;
+    if (fused > 0) {
+        *smem = fused;
+        return kModeFused;
+    }
+    if (variant == VN_GATHER_AUTO) {
+        static const int env_persistent = getenv("VN_PERSISTENT") ? atoi(getenv("VN_PERSISTENT")) : VN_PERSISTENT_DEFAULT;
+        const int32_t ps = env_persistent ? persistent_smem_bytes(store, out) : 0;
+        if (ps > 0) {
+            *smem = ps;
+            return kModePersistent;
+        }
+    }
+    return kModeSplit;
+}
+
 static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const vn_envs_t *envs, const vn_rules_t *rules,
                         const vn_inject_t *inj, const int32_t *actions, const uint8_t *mask, const vn_step_out_t *out,
                         int32_t variant, void *stream, bool reset) {
@@ -881,9 +1070,12 @@ static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const v
     if (envs->n_envs == 0) return VN_OK;
     int32_t rc = validate_store(store);  // fail before anything is enqueued
     if (rc) return rc;
-    const int32_t fused = choose_fused(store, envs, out, variant);
-    if (fused < 0) return VN_EINVAL;
-    if (fused > 0) return run_fused(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, fused);
+    int32_t smem = 0;
+    const StepMode mode = choose_mode(store, envs, out, variant, &smem);
+    if (mode == kModeError) return VN_EINVAL;
+    if (mode == kModeFused) return run_fused(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, smem);
+    if (mode == kModePersistent)
+        return run_persistent(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, smem);
     rc = run_scalar(tab, envs, rules, inj, actions, mask, out, stream, reset);
     if (rc) return rc;
     return run_gather(store, envs, out, variant, stream);
@@ -995,12 +1187,17 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
                "step_host: out->host_pack must be pinned (page-locked, device-mapped) host memory");
     VN_REQUIRE(!out || !out->host_seq || vn::is_mapped_host(out->host_seq),
                "step_host: out->host_seq must be pinned (page-locked, device-mapped) host memory");
-    const int32_t fused = vn::choose_fused(store, envs, out, gather_variant);
-    if (fused < 0) return VN_EINVAL;
-    // the scalar kernel reads the actions from, and mirrors its per-env results to, mapped host memory
-    if (fused > 0)
+    int32_t smem = 0;
+    const vn::StepMode mode = vn::choose_mode(store, envs, out, gather_variant, &smem);
+    if (mode == vn::kModeError) return VN_EINVAL;
+    const bool one_launch = mode != vn::kModeSplit;
+    // the scalar part reads the actions from, and mirrors its per-env results to, mapped host memory
+    if (mode == vn::kModeFused)
         rc = vn::run_fused(store, tables, envs, rules, inject, host_actions, nullptr, out, stream, false,
-                           dev_actions_copy, fused);
+                           dev_actions_copy, smem);
+    else if (mode == vn::kModePersistent)
+        rc = vn::run_persistent(store, tables, envs, rules, inject, host_actions, nullptr, out, stream, false,
+                                dev_actions_copy, smem);
     else
         rc = vn::run_scalar(tables, envs, rules, inject, host_actions, nullptr, out, stream, false, dev_actions_copy);
     if (rc) return rc;
@@ -1011,7 +1208,7 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
             return VN_ECUDA;
         }
     }
-    if (fused > 0) return VN_OK;
+    if (one_launch) return VN_OK;
     return vn::run_gather(store, envs, out, gather_variant, stream);
 }
 
@@ -1020,10 +1217,11 @@ int32_t vn_env_host_seq_words(const vn_store_t *store, const vn_envs_t *envs, co
     VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
     int32_t rc = vn::validate_store(store);
     if (rc) return rc;
-    const int32_t fused = vn::choose_fused(store, envs, out, gather_variant);
-    if (fused < 0) return VN_EINVAL;
-    if (envs->n_envs == 0) return 1;
-    return fused > 0 ? envs->n_envs : (envs->n_envs + vn::kStepThreads - 1) / vn::kStepThreads;
+    int32_t smem = 0;
+    const vn::StepMode mode = vn::choose_mode(store, envs, out, gather_variant, &smem);
+    if (mode == vn::kModeError) return VN_EINVAL;
+    if (envs->n_envs == 0 || mode == vn::kModePersistent) return 1;
+    return mode == vn::kModeFused ? envs->n_envs : (envs->n_envs + vn::kStepThreads - 1) / vn::kStepThreads;
 }
 
 int32_t vn_host_wait_seq(const uint32_t *host_seq, int32_t words, uint32_t seq, void *stream, int64_t timeout_us) {

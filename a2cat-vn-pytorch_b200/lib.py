@@ -19,7 +19,7 @@ RULE_TWO_LEVEL = 0x10
 RULE_NOOP_ACTION = 0x20
 RULE_AUTO_RESET = 0x40
 
-GATHER_AUTO, GATHER_LDG, GATHER_BULK, GATHER_FUSED = 0, 1, 2, 3
+GATHER_AUTO, GATHER_LDG, GATHER_BULK, GATHER_FUSED, GATHER_PERSISTENT = 0, 1, 2, 3, 4
 STEP_ACTIONS_READY = 0x01
 STEP_SKIP_UNCHANGED = 0x02
 ABI_VERSION = 3

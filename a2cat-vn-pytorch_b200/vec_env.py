@@ -135,9 +135,10 @@ class GraphVecEnv:
                          (experiments/thor_cached_auxiliary.py:61-62) hand to the model - in persistent batches filled
                          by one fused gather/convert kernel per leaf straight from the store (no uint8 batch is
                          written; rows that did not change / goal rows of envs that did not reset are skipped)
-        gather           "auto" | "ldg" | "bulk" | "fused" (include/vn_b200.h VN_GATHER_*); "auto" runs the whole step
-                         as ONE fused launch for batches of at most one env per SM and as scalar kernel + bulk-copy
-                         gather otherwise
+        gather           "auto" | "ldg" | "bulk" | "fused" | "persistent" (include/vn_b200.h VN_GATHER_*); "auto" runs the
+                         whole step as ONE fused launch for batches of one wave of CTAs; beyond that "persistent" is one
+                         launch of a persistent grid (CTAs own envs: lanes step them, lane 0 copies their records) and
+                         "bulk" / "ldg" are scalar kernel + gather kernel
         numpy_obs        return the observation leaves (and last_action_reward) as fresh numpy arrays, like the
                          reference's SubprocVecEnv, for a trainer that cannot take CUDA tensors: one device-to-host
                          copy of the whole batch per step (PCIe-bound - C2: ~1.9 M instead of ~110 M env-steps/s)
@@ -166,7 +167,7 @@ class GraphVecEnv:
         self.episode_info = episode_info     # RewardCollector's info['episode'] (create_envs wraps with it, :60)
         self.n_actions = 4
         self.gather = {"auto": L.GATHER_AUTO, "ldg": L.GATHER_LDG, "bulk": L.GATHER_BULK,
-                       "fused": L.GATHER_FUSED}[gather]
+                       "fused": L.GATHER_FUSED, "persistent": L.GATHER_PERSISTENT}[gather]
         self._step_flags = L.STEP_SKIP_UNCHANGED if skip_unchanged else 0
         lay = self.world.layout
         self.leaves = resolve_layout(obs_layout)

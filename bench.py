@@ -652,10 +652,10 @@ def run_cuda(args):
     copy_ms = c0.elapsed_time(c1) / 200
     del pairs
 
-    kname = {1: "vn_step_gather_kernel" if N > 444 else "vn_step_fused_kernel"}.get(
-        launches_per_step, "vn_gather_%s_kernel" % ("ldg" if args.gather == "ldg" else "bulk"))
-    if hasattr(env, "step_kernel_name"):
-        kname = env.step_kernel_name
+    if launches_per_step == 1:      # one launch per step: persistent grid (ONE host sequence word) or CTA-per-env fused
+        kname = "vn_step_gather_kernel" if (env._seq_words == 1 and N > 1) else "vn_step_fused_kernel"
+    else:
+        kname = "vn_gather_%s_kernel" % ("ldg" if args.gather == "ldg" else "bulk")
     prof = profiled_traffic(args.workload if hardness is None else None, kname)
     traffic = (prof["dram_bytes_read_per_launch"] + prof["dram_bytes_write_per_launch"]) if prof else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -946,7 +946,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk", "fused", "split"])
+    ap.add_argument("--gather", default="auto", choices=["auto", "ldg", "bulk", "fused", "persistent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--port-only", action="store_true", help="reference arm: time the oracle port even where "
                                                              "/root/reference exists")

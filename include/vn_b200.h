@@ -162,8 +162,8 @@ typedef struct vn_step_out {
     int32_t parity;                   /* step counter (only bit 0 is used); the caller increments it every reset / step */
     int32_t flags;                    /* VN_STEP_* */
     uint32_t *sched;                  /* optional scratch of 4 uint32, zeroed once by the caller: [0..1] ticket counters of
-                                         the gather's dynamic scheduler ([2..3] reserved; self re-arming; one scratch per
-                                         env batch / stream) */
+                                         the gather's dynamic scheduler, [2] arrival counter of the persistent launch's host
+                                         signal ([3] reserved; self re-arming; one scratch per env batch / stream) */
     uint8_t *host_pack;               /* optional MAPPED PINNED HOST block of 20 * n_envs bytes ("host pack") that the
                                          scalar kernel also writes, n = n_envs:
                                            [0, 4n) reward f32 | [4n, 8n) episode_return f32 | [8n, 12n) episode_length i32
@@ -193,6 +193,11 @@ typedef struct vn_step_out {
                                 bulk copies); what VN_GATHER_AUTO picks for batches that fit in one wave of CTAs (as many
                                 envs per SM as shared memory holds records, at most 4), where the step is bound by launch
                                 latency.  Elsewhere it means VN_GATHER_BULK. */
+#define VN_GATHER_PERSISTENT 4 /* vn_env_reset / vn_env_step / vn_env_step_host as ONE launch for batches of any size: a
+                                persistent grid of one-warp CTAs, each owning a fixed set of envs - its lanes step them,
+                                then lane 0 moves their records with bulk copies.  Needs out->gather_desc and out->sched
+                                and plane sets of at most 52 KB per env; a host caller polls ONE host_seq word.  In the
+                                gather-only entry points it means VN_GATHER_BULK. */
 
 int32_t vn_abi_version(void);
 /* sizeof of the descriptor structs as compiled into the library (0 store, 1 tables, 2 envs, 3 rules, 4 inject,
@@ -247,7 +252,8 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
                          int32_t *dev_actions_copy, const vn_step_out_t *out, void *ready_event,
                          int32_t gather_variant, void *stream);
 /* Number of host_seq words vn_env_step_host will publish for this batch (= thread blocks of its scalar half:
- * one per env when the step runs as the fused launch, one per 128 envs otherwise); <= 0 on error. */
+ * one per env when the step runs as the fused launch, ONE for the persistent launch, one per 128 envs otherwise);
+ * <= 0 on error. */
 int32_t vn_env_host_seq_words(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
                               int32_t gather_variant);
 /* Spins (pause loop, no GIL under ctypes) until host_seq[0 .. words) all equal seq.  Every ~50 us it looks at the

@@ -87,7 +87,7 @@ def starts_to_index(scene, starts, counts):
 
 
 @pytest.mark.parametrize("gather,skip", [("ldg", True), ("bulk", True), ("bulk", False), ("fused", True),
-                                         ("fused", False), ("auto", True)])
+                                         ("fused", False), ("auto", True), ("persistent", True), ("persistent", False)])
 def test_golden_gym_graph_auxiliary(gather, skip):
     g = H.load("gym_graph_aux")
     scene = H.scene_from_golden(g, True, ("rgb", "depth", "segmentation"))
@@ -106,7 +106,7 @@ def test_golden_gym_graph_auxiliary(gather, skip):
     same = (g["post_states"] == np.concatenate([g["reset_states"][None], g["post_states"][:-1]])).all(-1)
     assert st["rows_skipped"] == (same.sum() if skip else 0)
     # one launch per step when fused, two otherwise (+ the reset)
-    per_step = 1 if gather in ("fused", "auto") else 2
+    per_step = 1 if gather in ("fused", "auto", "persistent") else 2
     assert env.kernel_launches == per_step * (g["actions"].shape[0] + 1)
 
 
@@ -257,16 +257,48 @@ def test_store_fill_matches_host_hash():
     assert not dw.frames.cpu().numpy()[:, pad].any()
 
 
+_ORACLE_SCENES = {}
+
+
+def _oracle_scene(key, scene):
+    """All-pairs tables of a full-size scene take ~15 s in the scalar oracle: built once per test session."""
+    from oracle import envs as oenvs
+    if key not in _ORACLE_SCENES:
+        _ORACLE_SCENES[key] = oenvs.OracleScene(scene)
+    return _ORACLE_SCENES[key]
+
+
+def _oracle_subsample(world, scene, osc, env_ids, seed, limit, complexity, make_env):
+    """Scalar oracle envs for the GLOBAL env ids `env_ids` of a default-task-dealt batch (env i owns task i % n_tasks),
+    driven by the device path's own Philox reset stream."""
+    from oracle import graph_util as gu, vec as ovec
+    cands = {}
+    oes = []
+    for i in env_ids:
+        task = world.tasks[int(i) % len(world.tasks)]
+        goal = tuple(task.goal) if not isinstance(task.goal, (int, np.integer)) else world.state_tuple(int(task.goal))
+        if goal not in cands:
+            cands[goal] = gu.initial_state_candidates(scene.maze, osc.graph, osc.optimal_actions, goal)
+        oe = make_env(osc, goal)
+        oe.set_complexity(complexity)
+        oe.reset_source = ovec.PhiloxResetSource(seed, int(i), [cands[goal]], lambda t, oe=oe: oe.optimal_distance(), False)
+        oes.append(ovec.RewardCollector(ovec.TimeLimit(oe, limit)))
+    return ovec.VecEnv(oes), oes
+
+
 def test_full_size_properties_c2():
-    """BASELINE.json configs[1] at full size (1,500 cells x 4 rotations, 4,096 envs): size-independent
-    properties instead of a slow scalar oracle."""
+    """BASELINE.json configs[1] at full size (1,500 cells x 4 rotations, 4,096 envs): every launch mode is bit-identical
+    to the others, size-independent properties hold for ALL envs, and a sub-sample of 64 envs (every 64th) is driven
+    through the scalar oracle with the same actions and the same Philox reset stream: states, rewards, dones and
+    observation bytes of those envs equal the oracle's bit for bit at every step."""
     import torch
+    from oracle import envs as oenvs, graph_util as gu, vec as ovec
     scene = H.scenes.make_thor_scene(1500, (50, 60), seed=0, n_goals=4, planes=("rgb", "depth"))
     world = T.compile_world([scene], T.GYM_GRAPH)
     assert world.n_states == 6000
-    N = 4096
-    envs = {v: vn.GraphVecEnv(world, N, seed=7, max_episode_steps=50, obs_layout="rgbd_goal", gather=v,
-                              host_outputs=False) for v in ("ldg", "bulk")}
+    N, seed, limit = 4096, 7, 50
+    envs = {v: vn.GraphVecEnv(world, N, seed=seed, max_episode_steps=limit, obs_layout="rgbd_goal", gather=v,
+                              host_outputs=False) for v in ("ldg", "bulk", "persistent")}
     dw = envs["ldg"].dw
     adj = dw.adj.view(-1, 4)
     rgb, depth = dw.plane_view("rgb"), dw.plane_view("depth")
@@ -274,15 +306,31 @@ def test_full_size_properties_c2():
     for e in envs.values():
         e.set_complexity(0.1)
         e.reset()
-    e0, e1 = envs["ldg"], envs["bulk"]
+    e0, e1, e2 = envs["ldg"], envs["bulk"], envs["persistent"]
+    # the oracle sub-sample: env i owns task i % 4 (default env_tasks: tasks dealt round-robin)
+    sub = np.arange(0, N, 64)
+    osc = _oracle_scene("thor1500-s0", scene)
+    ov, oes = _oracle_subsample(world, scene, osc, sub, seed, limit, 0.1,
+                                lambda o, goal: oenvs.GymGraphRgbdGoalEnv(o, goals=goal))
+    (oobs, _) = ov.reset()
+    assert [oe.state for oe in oes] == [world.state_tuple(int(v)) for v in e0.state[sub].cpu().numpy()]
     for t in range(120):
         a = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
         prev = e0.state.clone()
         ((o_rgb, o_goal, o_depth), lar), rew, done, _ = e0.step(a)
-        ((b_rgb, b_goal, b_depth), blar), brew, bdone, _ = e1.step(a)
-        # the two gather variants are bit-identical
-        assert torch.equal(o_rgb, b_rgb) and torch.equal(o_depth, b_depth) and torch.equal(o_goal, b_goal)
-        assert torch.equal(rew, brew) and torch.equal(done, bdone) and torch.equal(e0.state, e1.state)
+        for other in (e1, e2):
+            ((b_rgb, b_goal, b_depth), blar), brew, bdone, _ = other.step(a)
+            # the launch modes are bit-identical
+            assert torch.equal(o_rgb, b_rgb) and torch.equal(o_depth, b_depth) and torch.equal(o_goal, b_goal)
+            assert torch.equal(rew, brew) and torch.equal(done, bdone) and torch.equal(e0.state, other.state)
+            assert torch.equal(lar, blar)
+        # the oracle sub-sample
+        (oobs, olar), orew, odone, _ = ov.step(a[sub].cpu().numpy())
+        assert np.array_equal(done[sub].cpu().numpy(), odone) and np.array_equal(f32bits(rew[sub].cpu().numpy()), f32bits(orew))
+        assert [oe.state for oe in oes] == [world.state_tuple(int(v)) for v in e0.state[sub].cpu().numpy()], t
+        for leaf, oleaf in zip((o_rgb, o_goal, o_depth), oobs):
+            assert np.array_equal(leaf[sub].cpu().numpy(), oleaf), t
+        assert np.array_equal(f32bits(lar[sub].cpu().numpy()), f32bits(olar)), t
         # transition table property: next = adj[prev, a], unchanged on collision
         nxt = adj[prev.long(), a.long()]
         moved = torch.where(nxt >= 0, nxt, prev)
@@ -351,8 +399,10 @@ def test_c_abi_rejects_bad_arguments():
         vn.GraphVecEnv(T.compile_world([scene], T.GYM_GRAPH), 4, obs_layout="aux5")
 
 
-def _property_run(env, world, steps, obs_names):
-    """Size-independent properties of a vectorised run (used for the full-size C3 / C4 configurations)."""
+def _property_run(env, world, steps, obs_names, oracle=None):
+    """Size-independent properties of a vectorised run (used for the full-size C3 / C4 configurations).
+    oracle = (local env indices, oracle VecEnv, oracle envs, local scene base): those envs are also checked, bit for
+    bit, against the scalar oracle driven with the same actions and the same Philox reset stream."""
     import torch
     dw = env.dw
     adj = dw.adj.view(-1, 4)
@@ -362,10 +412,24 @@ def _property_run(env, world, steps, obs_names):
     gen = torch.Generator(device="cuda").manual_seed(0)
     env.reset()
     N = env.num_envs
+    if oracle is not None:
+        sub, ov, oes = oracle
+        ov.reset()
+        assert [oe.state for oe in oes] == [world.state_tuple(int(v)) for v in env.state[sub].cpu().numpy()]
     for t in range(steps):
         a = torch.randint(0, 4, (N,), device="cuda", generator=gen, dtype=torch.int32)
         prev = env.state.clone()
         obs, rew, done, _ = env.step(a)
+        if oracle is not None:
+            (oobs, olar), orew, odone, _ = ov.step(a[sub].cpu().numpy())
+            assert np.array_equal(done[sub].cpu().numpy(), odone), t
+            assert np.array_equal(f32bits(rew[sub].cpu().numpy()), f32bits(orew)), t
+            assert [oe.state for oe in oes] == [world.state_tuple(int(v)) for v in env.state[sub].cpu().numpy()], t
+            oleaves = oobs if isinstance(oobs, tuple) else (oobs,)
+            leaves = obs[0] if env.unreal_wrapper else obs
+            leaves = leaves if isinstance(leaves, tuple) else (leaves,)
+            for leaf, oleaf in zip(leaves, oleaves):          # the oracle class may emit fewer leaves (frame only)
+                assert np.array_equal(leaf[sub].cpu().numpy(), oleaf), t
         nxt = adj[prev.long(), a.long()]
         assert torch.equal(env.info_state, torch.where(nxt >= 0, nxt, prev))
         s = env.state.long()
@@ -387,9 +451,18 @@ def test_full_size_properties_c3_dungeon():
     """BASELINE.json configs[2]: dungeon 64x64 multi-room, 65,536 envs, goal-image conditioning, auto-reset."""
     sc = H.scenes.make_dungeon_scene((64, 64), 0, oriented=True, planes=("rgb",))
     world = T.compile_world([sc], T.GYM_GRAPH)
-    env = vn.GraphVecEnv(world, 65536, seed=3, max_episode_steps=40, obs_layout="pair", host_outputs=False)
-    env.set_complexity(0.1)
-    _property_run(env, world, 25, ("rgb",))
+    from oracle import envs as oenvs
+    for gather in ("auto", "persistent"):
+        env = vn.GraphVecEnv(world, 65536, seed=3, max_episode_steps=40, obs_layout="pair", host_outputs=False,
+                             gather=gather)
+        env.set_complexity(0.1)
+        # 64 of the 65,536 envs also run through the scalar oracle (OrientedGraphEnv: the frame leaf; the goal leaf is
+        # checked against the store for every env by the property run)
+        sub = np.arange(0, 65536, 1024)
+        osc = _oracle_scene("dungeon64-s0", sc)
+        ov, oes = _oracle_subsample(world, sc, osc, sub, 3, 40, 0.1, lambda o, goal: oenvs.GymGraphEnv(o, goals=goal))
+        _property_run(env, world, 25, ("rgb",), oracle=(sub, ov, oes))
+        del env
 
 
 def test_full_size_properties_c4_multi_scene():
@@ -403,7 +476,15 @@ def test_full_size_properties_c4_multi_scene():
                          rank=3, world_size=8)
     assert env.num_envs == 32768 and env.env_lo == 3 * 32768
     env.set_complexity(0.05)
-    _property_run(env, world, 12, ("rgb", "depth"))
+    # oracle sub-sample: the first 64 envs of this shard whose task lives in scene 0 (tasks are dealt round-robin by
+    # GLOBAL env id: task = id % 120, scene 0 owns tasks 0..3) - scene 0 is the C2 scene, its oracle tables are shared
+    from oracle import envs as oenvs
+    ids = np.arange(env.env_lo, env.env_lo + env.num_envs)
+    sub_global = ids[(ids % 120) < 4][:64]
+    osc = _oracle_scene("thor1500-s0", scs[0])
+    ov, oes = _oracle_subsample(world, scs[0], osc, sub_global, 5, 30, 0.05,
+                                lambda o, goal: oenvs.GymGraphRgbdGoalEnv(o, goals=goal))
+    _property_run(env, world, 12, ("rgb", "depth"), oracle=(sub_global - env.env_lo, ov, oes))
     # the hash-filled store matches the host hash for a sample of (scene, state) pairs
     import torch
     rgb = env.dw.plane_view("rgb")
@@ -743,7 +824,7 @@ def test_skipping_unchanged_rows_changes_nothing(family):
             world, layout = T.compile_world([scene], T.GYM_GRAPH), "rgbd_goal"
         else:       # flat-index goals, cached.py:39
             world, layout = T.compile_world([scene], T.THOR_CACHED, tasks=[(0, 5), (0, 77), (0, 301)]), "pair"
-    for N, modes in ((1500, ("bulk", "ldg", "pipelined")), (24, ("auto", "fused"))):
+    for N, modes in ((1500, ("bulk", "ldg", "pipelined", "persistent")), (24, ("auto", "fused", "persistent"))):
         S = 60
         ref = vn.GraphVecEnv(world, N, seed=9, max_episode_steps=13, host_outputs=False, obs_layout=layout,
                              skip_unchanged=False, gather="bulk")
@@ -788,7 +869,7 @@ def test_outputs_stay_inside_their_buffers():
     scene = H.scenes.make_thor_scene(120, (14, 18), seed=5, n_goals=3, planes=("rgb", "depth", "segmentation"))
     world = T.compile_world([scene], T.GYM_GRAPH)
     lay = world.layout
-    for N, gather in ((23, "fused"), (23, "bulk"), (777, "bulk"), (777, "ldg")):
+    for N, gather in ((23, "fused"), (23, "bulk"), (777, "bulk"), (777, "ldg"), (777, "persistent"), (5, "persistent")):
         env = vn.GraphVecEnv(world, N, seed=3, max_episode_steps=5, host_outputs=False, obs_layout="aux5", gather=gather)
         guards = []
 
@@ -841,7 +922,7 @@ def test_frames_that_are_not_a_multiple_of_16_bytes(hw, cell, out):
     dw = vn.DeviceWorld(world)
     for p in planes:
         assert np.array_equal(dw.plane_view(p).cpu().numpy(), scene.plane_frames(p)), p
-    for N, gather in ((12, "auto"), (300, "bulk"), (300, "ldg")):
+    for N, gather in ((12, "auto"), (300, "bulk"), (300, "ldg")):     # 212 KB records: sliced, never one persistent launch
         env = vn.GraphVecEnv(world, N, seed=2, max_episode_steps=6, obs_layout="aux5", gather=gather, device_world=dw)
         env.set_complexity(0.4)
         (obs, lar) = env.reset()
@@ -951,7 +1032,8 @@ def test_randomised_configurations_against_oracle(case):
     limit = int(rng.randint(2, 40))
     rewards = tuple(float(x) for x in rng.choice([1.0, 0.0, -0.01, 0.5, -1.0, 2.0], 3))
     seed = int(rng.randint(1 << 30))
-    gather = str(rng.choice(["auto", "bulk", "ldg", "fused"] if N <= 148 else ["auto", "bulk", "ldg"]))
+    gather = str(rng.choice(["auto", "bulk", "ldg", "fused", "persistent"] if N <= 148 else
+                            ["auto", "bulk", "ldg", "persistent"]))
     skip = bool(rng.randint(2))
     goals = list(scene.goals)
     env_tasks = np.tile(np.array([[0, len(goals)]], np.int32), (N, 1)) if oriented else None
@@ -1028,6 +1110,8 @@ def test_host_facing_c_abi_failure_paths():
     wbig = T.compile_world([big], T.GYM_GRAPH)
     with pytest.raises(L.VnError, match="fused"):
         vn.GraphVecEnv(wbig, 4, obs_layout="aux5", gather="fused")
+    with pytest.raises(L.VnError, match="persistent"):               # ... and for whole-record CTAs of the persistent launch
+        vn.GraphVecEnv(wbig, 4, obs_layout="aux5", gather="persistent")
     ok = vn.GraphVecEnv(wbig, 4, obs_layout="aux5", gather="auto")       # AUTO falls back to two launches
     ok.reset()
     ok.step(np.zeros(4, np.int32))

@@ -17,7 +17,11 @@ def main():
     import torch
     vn = importlib.import_module("a2cat-vn-pytorch_b200")
     workload, world, n, layout = bench.make_workload(vn, sys.argv[1] if len(sys.argv) > 1 else "c2")
-    env = vn.GraphVecEnv(world, n, device="cuda:0", seed=2, max_episode_steps=900, obs_layout=layout, host_outputs=True)
+    gather = sys.argv[2] if len(sys.argv) > 2 else "auto"
+    env = vn.GraphVecEnv(world, n, device="cuda:0", seed=2, max_episode_steps=900, obs_layout=layout, host_outputs=True,
+                         gather=gather)
+    print("workload %s, gather %s, %d envs, %d host sequence words" % (sys.argv[1] if len(sys.argv) > 1 else "c2", gather,
+                                                                          n, env._seq_words))
     env.reset()
     rng = np.random.RandomState(0)
     acts = rng.randint(0, 4, (256, n)).astype(np.int32)
