@@ -16,7 +16,7 @@
 #include "vn_common.cuh"
 
 #ifndef VN_PERSISTENT_DEFAULT
-#define VN_PERSISTENT_DEFAULT 0  // VN_GATHER_AUTO beyond one wave: 0 = scalar kernel + gather kernel, 1 = persistent launch
+#define VN_PERSISTENT_DEFAULT 1  // VN_GATHER_AUTO beyond one wave: 0 never, 1 mid-size device-resident batches, 2 always
 #endif
 
 namespace vn {
@@ -1053,11 +1053,24 @@ static StepMode choose_mode(const vn_store_t *store, const vn_envs_t *envs, cons
         return kModeFused;
     }
     if (variant == VN_GATHER_AUTO) {
+        // Measured on B200 (profiles/r2a_launch_modes.txt, C2 records, device-resident loop): the persistent launch wins
+        // while every CTA owns at most two envs (512 envs 9.5 -> 7.0 us per step, 1,024: 10.7 -> 9.9, 2,048: 17.7 -> 17.4)
+        // - there the step is bound by launches and dependency hops.  Beyond that the two-kernel path wins (4,096: 34.6
+        // vs 35.8 us; 16,384: 120 vs 137 us): its scalar kernel hides behind the previous gather and its tickets balance
+        // the copies, while the persistent launch exposes its stepping phase and owns envs statically.  A HOST caller
+        // (out->host_pack) always takes two kernels: the stepping phase of a persistent grid cannot become resident
+        // before the previous launch's CTAs release their shared memory, so the host would get its rewards a whole gather
+        // late, and lanes that own strided envs read / write the mapped host buffers 4 bytes at a time.
+        // VN_PERSISTENT=0 / 2 (development): never / whenever the batch qualifies.
         static const int env_persistent = getenv("VN_PERSISTENT") ? atoi(getenv("VN_PERSISTENT")) : VN_PERSISTENT_DEFAULT;
         const int32_t ps = env_persistent ? persistent_smem_bytes(store, out) : 0;
         if (ps > 0) {
-            *smem = ps;
-            return kModePersistent;
+            const int per_sm = max(1, min(32, (220 * 1024) / (ps + 1024)));
+            const bool mid_size = !out->host_pack && envs->n_envs <= 2 * sm_count() * per_sm;
+            if (env_persistent >= 2 || mid_size) {
+                *smem = ps;
+                return kModePersistent;
+            }
         }
     }
     return kModeSplit;
@@ -1266,7 +1279,8 @@ int32_t vn_host_wait_seq(const uint32_t *host_seq, int32_t words, uint32_t seq, 
 int32_t vn_env_step_host_sync(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
                               const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
                               int32_t *dev_actions_copy, const vn_step_out_t *out, uint8_t *pack_copy,
-                              int32_t seq_words, int32_t gather_variant, void *stream, int64_t timeout_us) {
+                              float *reward_copy, uint8_t *done_copy, int32_t seq_words, int32_t gather_variant,
+                              void *stream, int64_t timeout_us) {
     VN_REQUIRE(out && out->host_pack && out->host_seq, "step_host_sync: out->host_pack and out->host_seq are required");
     VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
     int32_t rc = vn_env_step_host(store, tables, envs, rules, inject, host_actions, dev_actions_copy, out, nullptr,
@@ -1274,7 +1288,10 @@ int32_t vn_env_step_host_sync(const vn_store_t *store, const vn_tables_t *tables
     if (rc || envs->n_envs == 0) return rc;
     rc = vn_host_wait_seq(out->host_seq, seq_words, out->seq, stream, timeout_us);
     if (rc) return rc;
-    if (pack_copy) memcpy(pack_copy, out->host_pack, (size_t)20 * envs->n_envs);
+    const size_t n = (size_t)envs->n_envs;
+    if (pack_copy) memcpy(pack_copy, out->host_pack, 20 * n);
+    if (reward_copy) memcpy(reward_copy, out->host_pack, 4 * n);
+    if (done_copy) memcpy(done_copy, out->host_pack + 16 * n, n);
     return VN_OK;
 }
 

@@ -124,7 +124,7 @@ def load(build_if_missing=True):
         "vn_env_step_scalar": (i32, [T, E, R, I, _P, O, _P]),
         "vn_env_gather": (i32, [S, E, O, i32, _P]),
         "vn_env_step_host": (i32, [S, T, E, R, I, _P, _P, O, _P, i32, _P]),
-        "vn_env_step_host_sync": (i32, [S, T, E, R, I, _P, _P, O, _P, i32, i32, _P, i64]),
+        "vn_env_step_host_sync": (i32, [S, T, E, R, I, _P, _P, O, _P, _P, _P, i32, i32, _P, i64]),
         "vn_env_host_seq_words": (i32, [S, E, O, i32]),
         "vn_host_wait_seq": (i32, [_P, i32, C.c_uint32, _P, i64]),
         "vn_event_create": (i32, [C.POINTER(_P)]),

@@ -18,6 +18,7 @@ for envs that reset; all envs advance in two kernel launches (one for small batc
 change is not copied again.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -71,11 +72,21 @@ class LazyInfos:
     the packed per-env info arrays only when an element is read (host_outputs=False: the arrays are
     fetched from the device on first access and are valid until the next step)."""
 
-    def __init__(self, env, arrays, noop):
+    def __init__(self, env, arrays, noop, in_place=False):
         self._env, self._a, self._noop = env, arrays, noop
+        self._in_place = in_place      # `arrays` is a pinned host pack of the env, read in place (no copy was taken)
 
     def __len__(self):
         return self._env.num_envs
+
+    def _snapshot(self):
+        """The env is about to reuse the pinned host pack this object still reads in place: take a private copy."""
+        if self._in_place:
+            if isinstance(self._a, np.ndarray):
+                self._a = self._a.copy()
+            elif isinstance(self._a, dict):
+                self._a = {k: v.copy() for k, v in self._a.items()}
+            self._in_place = False
 
     def _host(self):
         if callable(self._a):
@@ -222,7 +233,10 @@ class GraphVecEnv:
                 self.obs_buf = {p: lay.batch(p, n, self.device) for p in self.obs_planes}
                 self.goal_buf = {p: lay.batch(p, n, self.device) for p in self.goal_planes}
                 self.float_buf = {}
-            self._pack_host = torch.zeros(n * 20, dtype=torch.uint8).pin_memory()
+            # two host packs used alternately: rewards / dones are copied out of the pinned block every step, the rest
+            # (what `infos` is built from) is read in place, lazily, and stays valid until the step after next
+            self._pack_hosts = [torch.zeros(n * 20, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._pack_host = self._pack_hosts[0]
             self._actions_host = torch.zeros(n, dtype=torch.int32).pin_memory()
         self._inject_keep = None
         self._c_inject = None
@@ -308,7 +322,11 @@ class GraphVecEnv:
         # host path: pinned staging seen as numpy views; the scalar kernel publishes a sequence word once its
         # results have landed on the host (the gather is still running when step() returns)
         self._actions_np = self._actions_host.numpy()
-        self._pack_np = self._pack_host.numpy()
+        self._pack_nps = [t.numpy() for t in self._pack_hosts]
+        self._pack_ptrs = [t.data_ptr() for t in self._pack_hosts]
+        self._pack_np = self._pack_nps[0]
+        self._infos_refs = [None, None]        # weak references to the LazyInfos reading each pack in place
+        self._slot = 0
 
     @property
     def kernel_launches(self):
@@ -474,6 +492,7 @@ class GraphVecEnv:
             self._tick(self._c_out_host, L.STEP_ACTIONS_READY | self._step_flags)
             self._seq = (self._seq % 0x7FFFFFFF) + 1
             self._c_out_host.seq = self._seq
+            self._next_pack()
             r = self._ref
             self._call(self.lib.vn_env_step_host, r["store"], r["tables"], r["envs"], r["rules"], inj,
                        self._actions_host.data_ptr(), self.actions_dev.data_ptr(), r["out_host"], None,
@@ -563,6 +582,25 @@ class GraphVecEnv:
         self.gather_current()
         torch.cuda.synchronize(self.device)
 
+    def _next_pack(self):
+        """Points the step about to be enqueued at the other pinned host pack.  An `infos` object of two steps ago that
+        is still alive and still reads that pack in place gets its private copy first."""
+        s = self._slot = self._slot ^ 1
+        ref = self._infos_refs[s]
+        if ref is not None:
+            old = ref()
+            if old is not None:
+                old._snapshot()
+            self._infos_refs[s] = None
+        self._c_out_host.host_pack = self._pack_ptrs[s]
+        self._pack_np = self._pack_nps[s]
+
+    def _host_results(self, reward, done, noop):
+        """(rewards, dones, infos) of the host-facing step whose scalars have just arrived in the current pack."""
+        infos = LazyInfos(self, self._pack_np, noop, in_place=True)
+        self._infos_refs[self._slot] = weakref.ref(infos)
+        return reward, done, infos
+
     def _unpack(self, host):
         n = self.num_envs
         return dict(reward=host[:4 * n].view(np.float32), episode_return=host[4 * n:8 * n].view(np.float32),
@@ -582,13 +620,13 @@ class GraphVecEnv:
             if n:
                 L.check(self.lib.vn_host_wait_seq(self._seq_host.data_ptr(), self._seq_words, self._seq, self._stream(),
                                                   60_000_000))
-            h = self._pack_np.copy()
-            return (self._obs_out(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
-                    LazyInfos(self, h, noop))
+            h = self._pack_np
+            return (self._obs_out(),) + self._host_results(h[:4 * n].view(np.float32).copy(),
+                                                           h[16 * n:17 * n].view(np.bool_).copy(), noop)
         if self.host_outputs:
-            self._pack_host.copy_(self._pack, non_blocking=True)
+            self._pack_hosts[0].copy_(self._pack, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            h = self._unpack(self._pack_np.copy())
+            h = self._unpack(self._pack_nps[0].copy())
             return self._obs_out(), h["reward"], h["done"].view(np.bool_), LazyInfos(self, h, noop)
         fetch = lambda: self._unpack(self._pack.cpu().numpy())
         return self._obs_out(), self.reward, self.done.bool(), LazyInfos(self, fetch, noop)
@@ -604,15 +642,16 @@ class GraphVecEnv:
             self._tick(out, L.STEP_ACTIONS_READY | self._step_flags)
             self._seq = (self._seq % 0x7FFFFFFF) + 1
             out.seq = self._seq
-            h = np.empty(20 * n, np.uint8)
+            self._next_pack()
+            rew, done = np.empty(n, np.float32), np.empty(n, np.bool_)
             r = self._ref
             self._call(self.lib.vn_env_step_host_sync, r["store"], r["tables"], r["envs"], r["rules"],
                        C.byref(self._c_inject) if self._c_inject is not None else None,
-                       self._actions_ptr, self._actions_dev_ptr, r["out_host"], h.__array_interface__["data"][0],
+                       self._actions_ptr, self._actions_dev_ptr, r["out_host"], None,
+                       rew.__array_interface__["data"][0], done.__array_interface__["data"][0],
                        self._seq_words, self.gather, _raw_stream(self._dev_index), 60_000_000)
             noop = (self._actions_np < 0) if self.family.noop_action else None
-            return (self._obs_out(), h[:4 * n].view(np.float32), h[16 * n:17 * n].view(np.bool_),
-                    LazyInfos(self, h, noop))
+            return (self._obs_out(),) + self._host_results(rew, done, noop)
         self.step_async(actions)
         return self.step_wait()
 

@@ -261,13 +261,17 @@ int32_t vn_env_host_seq_words(const vn_store_t *store, const vn_envs_t *envs, co
  * does timeout_us (> 0). */
 int32_t vn_host_wait_seq(const uint32_t *host_seq, int32_t words, uint32_t seq, void *stream, int64_t timeout_us);
 /* VecEnv.step(actions) in ONE call for a host caller: vn_env_step_host (out->host_pack and out->host_seq are
- * required, no event), vn_host_wait_seq on out->host_seq / out->seq, then a copy of the 20 * n_envs host pack into
- * pack_copy [host, pageable is fine] so that the caller owns the results while the next step overwrites the
- * pinned block.  seq_words = vn_env_host_seq_words(...).  The gather of this step is still running on return. */
+ * required, no event), vn_host_wait_seq on out->host_seq / out->seq, then copies [host, pageable is fine; each
+ * optional] so that the caller owns the results while a later step overwrites the pinned block: pack_copy receives
+ * the whole 20 * n_envs host pack, reward_copy the n_envs rewards, done_copy the n_envs done bytes.  A caller that
+ * alternates between two host packs only needs rewards and dones copied (20 KB instead of 80 KB at 4,096 envs): the
+ * rest of the pack - what `infos` is built from - stays readable in place until the step after next.
+ * seq_words = vn_env_host_seq_words(...).  The gather of this step is still running on return. */
 int32_t vn_env_step_host_sync(const vn_store_t *store, const vn_tables_t *tables, const vn_envs_t *envs,
                               const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
                               int32_t *dev_actions_copy, const vn_step_out_t *out, uint8_t *pack_copy,
-                              int32_t seq_words, int32_t gather_variant, void *stream, int64_t timeout_us);
+                              float *reward_copy, uint8_t *done_copy, int32_t seq_words, int32_t gather_variant,
+                              void *stream, int64_t timeout_us);
 int32_t vn_event_create(void **event);   /* cudaEventDisableTiming */
 int32_t vn_event_destroy(void *event);
 int32_t vn_event_wait(void *event);      /* cudaEventSynchronize; releases the GIL under ctypes */

@@ -1287,3 +1287,34 @@ def test_host_received_scalars_are_never_stale():
     for t, ln, d in got_len:                         # episode lengths are reported where done, and plausible
         assert ((ln[d] >= 1) & (ln[d] <= 9)).all()
     assert torch.equal(log_s[-1], env.obs_state)
+
+
+@pytest.mark.parametrize("N", [7, 700])
+def test_lazy_infos_stay_valid_after_later_steps(N):
+    """The host-facing step copies rewards / dones out of the pinned host pack and lets `infos` read the rest in place
+    from one of two alternating packs.  An `infos` object that is still alive when its pack is about to be reused gets
+    a private copy first: infos kept from every step, evaluated only at the end, equal the ones evaluated right away on
+    a twin env - in both the one-call step() and the step_async / step_wait forms."""
+    scene = H.scenes.make_thor_scene(120, (14, 18), seed=5, n_goals=3, planes=("rgb", "depth"))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    a = vn.GraphVecEnv(world, N, seed=4, max_episode_steps=7, obs_layout="rgbd_goal")
+    b = vn.GraphVecEnv(world, N, seed=4, max_episode_steps=7, obs_layout="rgbd_goal", device_world=a.dw)
+    a.reset()
+    b.reset()
+    rng = np.random.RandomState(8)
+    kept, eager, kept_rd = [], [], []
+    for t in range(40):
+        act = rng.randint(0, 4, N).astype(np.int32)
+        if t % 3 == 2:
+            a.step_async(act)
+            _, r, d, infos = a.step_wait()
+        else:
+            _, r, d, infos = a.step(act)
+        _, rb, db, infos_b = b.step(act)
+        kept.append(infos)                      # NOT evaluated yet; the pack it reads is reused two steps later
+        kept_rd.append((r, d))
+        eager.append(([dict(x) for x in infos_b], rb.copy(), db.copy()))
+    for t, (infos, (r, d), (want, rb, db)) in enumerate(zip(kept, kept_rd, eager)):
+        assert np.array_equal(r, rb) and np.array_equal(d, db), t      # rewards / dones are private copies
+        assert [dict(x) for x in infos] == want, t
+    assert sum("episode" in x for w, _, _ in eager for x in w) > N
