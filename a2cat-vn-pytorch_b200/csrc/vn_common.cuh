@@ -17,6 +17,10 @@ namespace vn {
 void set_error(const char *fmt, ...);
 int32_t check_launch(const char *what);
 int sm_count();  // multiprocessors of the current device (cached per device)
+// All float leaves of one step in one launch (vn_rollout.cu); in_step = enqueued by vn_env_reset / vn_env_step* right
+// after the kernels that wrote `desc` (programmatic launch, releases its stream successor early).
+int32_t launch_float_leaves(const vn_store_t *store, const vn_float_leaf_t *leaves, int32_t n_leaves, const int32_t *desc,
+                            int32_t n, int32_t h, int32_t w, void *stream, bool in_step);
 
 #define VN_REQUIRE(cond, ...)            \
     do {                                 \

@@ -1035,6 +1035,15 @@ static int32_t choose_fused(const vn_store_t *store, const vn_envs_t *envs, cons
     return smem;
 }
 
+// Float observation mode as part of the step: one more kernel converts this step's records into the float leaves.
+static int32_t run_float_leaves(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, void *stream) {
+    if (!out->float_leaves || out->n_float_leaves <= 0) return VN_OK;
+    VN_REQUIRE(out->gather_desc, "float_leaves: out->gather_desc is required");
+    const int32_t *desc = out->gather_desc + (size_t)(out->parity & 1) * envs->n_envs * 2;
+    return launch_float_leaves(store, out->float_leaves, out->n_float_leaves, desc, envs->n_envs, out->float_h,
+                               out->float_w, stream, true);
+}
+
 static StepMode choose_mode(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out, int32_t variant,
                             int32_t *smem) {
     *smem = 0;
@@ -1086,12 +1095,17 @@ static int32_t run_step(const vn_store_t *store, const vn_tables_t *tab, const v
     int32_t smem = 0;
     const StepMode mode = choose_mode(store, envs, out, variant, &smem);
     if (mode == kModeError) return VN_EINVAL;
-    if (mode == kModeFused) return run_fused(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, smem);
-    if (mode == kModePersistent)
-        return run_persistent(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, smem);
-    rc = run_scalar(tab, envs, rules, inj, actions, mask, out, stream, reset);
+    if (mode == kModeFused)
+        rc = run_fused(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, smem);
+    else if (mode == kModePersistent)
+        rc = run_persistent(store, tab, envs, rules, inj, actions, mask, out, stream, reset, nullptr, smem);
+    else {
+        rc = run_scalar(tab, envs, rules, inj, actions, mask, out, stream, reset);
+        if (rc) return rc;
+        rc = run_gather(store, envs, out, variant, stream);
+    }
     if (rc) return rc;
-    return run_gather(store, envs, out, variant, stream);
+    return run_float_leaves(store, envs, out, stream);
 }
 
 // Pinned + device-mapped?  The answer for the last few pointers is remembered per thread: the query costs about
@@ -1221,8 +1235,11 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
             return VN_ECUDA;
         }
     }
-    if (one_launch) return VN_OK;
-    return vn::run_gather(store, envs, out, gather_variant, stream);
+    if (!one_launch) {
+        rc = vn::run_gather(store, envs, out, gather_variant, stream);
+        if (rc) return rc;
+    }
+    return vn::run_float_leaves(store, envs, out, stream);
 }
 
 int32_t vn_env_host_seq_words(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,

@@ -423,7 +423,12 @@ __device__ __forceinline__ void store_group(float *o, const uint32_t *w, int c, 
 // host so that a thread has about a dozen independent loads in flight without running out of registers.
 template <int kLeaves, int kUnroll>
 __global__ void __launch_bounds__(256) vn_gather_leaves_f32_kernel(const FloatLeaves L, int64_t pitch,
-                                                                   const int2 *__restrict__ desc, int n, int hw) {
+                                                                   const int2 *__restrict__ desc, int n, int hw,
+                                                                   int early_release) {
+    // as part of a step (programmatic launch) the scalar half's descriptors are needed from here on, and the next
+    // step's scalar kernel - which touches nothing this kernel reads - may be scheduled while this one runs
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (early_release) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int groups = hw >> 2;
     const int64_t total = (int64_t)n * groups;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -957,18 +962,22 @@ int32_t vn_gather_plane_f32_chw_rows(const vn_store_t *store, int32_t plane, con
     return vn::check_launch("vn_gather_f32_chw_kernel");
 }
 
-int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t *leaves, int32_t n_leaves,
-                                 const int32_t *desc, int32_t n, int32_t h, int32_t w, void *stream) {
+}  // extern "C"
+
+namespace vn {
+
+int32_t launch_float_leaves(const vn_store_t *store, const vn_float_leaf_t *leaves, int32_t n_leaves, const int32_t *desc,
+                            int32_t n, int32_t h, int32_t w, void *stream, bool in_step) {
     VN_REQUIRE(store && store->base && leaves && desc && n >= 0, "gather_leaves_f32_chw: null pointer");
-    VN_REQUIRE(n_leaves >= 1 && n_leaves <= vn::kMaxFloatLeaves, "gather_leaves_f32_chw: n_leaves=%d (max %d)", n_leaves,
-               vn::kMaxFloatLeaves);
+    VN_REQUIRE(n_leaves >= 1 && n_leaves <= kMaxFloatLeaves, "gather_leaves_f32_chw: n_leaves=%d (max %d)", n_leaves,
+               kMaxFloatLeaves);
     if ((h * w) % 4 != 0) {
-        vn::set_error("gather_leaves_f32_chw: %d x %d pixels are not whole groups of 4 (use the per-leaf call)", h, w);
+        set_error("gather_leaves_f32_chw: %d x %d pixels are not whole groups of 4 (use the per-leaf call)", h, w);
         return VN_EUNSUPPORTED;
     }
-    vn::FloatLeaves L;
+    FloatLeaves L;
     L.n_leaves = n_leaves;
-    for (int l = 0; l < vn::kMaxFloatLeaves; ++l) {
+    for (int l = 0; l < kMaxFloatLeaves; ++l) {
         L.pbase[l] = nullptr;
         L.out[l] = nullptr;
         L.c[l] = 1;
@@ -978,7 +987,7 @@ int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t 
         int32_t rc = check_plane(store, leaves[l].plane, h, w, leaves[l].channels, "gather_leaves_f32_chw");
         if (rc) return rc;
         if (leaves[l].channels != 1 && leaves[l].channels != 3) {
-            vn::set_error("gather_leaves_f32_chw: %d channels (use the per-leaf call)", leaves[l].channels);
+            set_error("gather_leaves_f32_chw: %d channels (use the per-leaf call)", leaves[l].channels);
             return VN_EUNSUPPORTED;
         }
         VN_REQUIRE(leaves[l].out && (reinterpret_cast<uintptr_t>(leaves[l].out) & 15) == 0,
@@ -992,20 +1001,39 @@ int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t 
     if (n == 0) return VN_OK;
     const int64_t total = (int64_t)n * (h * w / 4);
     const int unroll = n_leaves == 1 ? 4 : (n_leaves <= 3 ? 2 : 1);
-    const int64_t want = (total + unroll * 256 - 1) / (unroll * 256), cap = (int64_t)vn::sm_count() * 16;
+    const int64_t want = (total + unroll * 256 - 1) / (unroll * 256), cap = (int64_t)sm_count() * 16;
     const int grid = (int)(want < cap ? want : cap);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int2 *d2 = reinterpret_cast<const int2 *>(desc);
     const int64_t pitch = store->state_pitch;
+    const int hw = h * w, early = in_step ? 1 : 0;
+    // programmatic launch only as part of a step: there the predecessor is the step's own scalar / gather kernel
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = in_step ? 1 : 0;
     switch (n_leaves) {
-        case 1: vn::vn_gather_leaves_f32_kernel<1, 4><<<grid, 256, 0, st>>>(L, pitch, d2, n, h * w); break;
-        case 2: vn::vn_gather_leaves_f32_kernel<2, 2><<<grid, 256, 0, st>>>(L, pitch, d2, n, h * w); break;
-        case 3: vn::vn_gather_leaves_f32_kernel<3, 2><<<grid, 256, 0, st>>>(L, pitch, d2, n, h * w); break;
-        case 4: vn::vn_gather_leaves_f32_kernel<4, 1><<<grid, 256, 0, st>>>(L, pitch, d2, n, h * w); break;
-        case 5: vn::vn_gather_leaves_f32_kernel<5, 1><<<grid, 256, 0, st>>>(L, pitch, d2, n, h * w); break;
-        default: vn::vn_gather_leaves_f32_kernel<6, 1><<<grid, 256, 0, st>>>(L, pitch, d2, n, h * w); break;
+        case 1: cudaLaunchKernelEx(&cfg, vn_gather_leaves_f32_kernel<1, 4>, L, pitch, d2, n, hw, early); break;
+        case 2: cudaLaunchKernelEx(&cfg, vn_gather_leaves_f32_kernel<2, 2>, L, pitch, d2, n, hw, early); break;
+        case 3: cudaLaunchKernelEx(&cfg, vn_gather_leaves_f32_kernel<3, 2>, L, pitch, d2, n, hw, early); break;
+        case 4: cudaLaunchKernelEx(&cfg, vn_gather_leaves_f32_kernel<4, 1>, L, pitch, d2, n, hw, early); break;
+        case 5: cudaLaunchKernelEx(&cfg, vn_gather_leaves_f32_kernel<5, 1>, L, pitch, d2, n, hw, early); break;
+        default: cudaLaunchKernelEx(&cfg, vn_gather_leaves_f32_kernel<6, 1>, L, pitch, d2, n, hw, early); break;
     }
-    return vn::check_launch("vn_gather_leaves_f32_kernel");
+    return check_launch("vn_gather_leaves_f32_kernel");
+}
+
+}  // namespace vn
+
+extern "C" {
+
+int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t *leaves, int32_t n_leaves,
+                                 const int32_t *desc, int32_t n, int32_t h, int32_t w, void *stream) {
+    return vn::launch_float_leaves(store, leaves, n_leaves, desc, n, h, w, stream, false);
 }
 
 int32_t vn_rp_labels(const float *reward, int32_t n, int32_t t, int64_t stride_n, int64_t stride_t, int8_t *labels,

@@ -55,24 +55,26 @@ class Inject(C.Structure):
     _fields_ = [("task", _P), ("start", _P), ("stride", C.c_int32), ("reserved", C.c_int32)]
 
 
+class FloatLeaf(C.Structure):
+    _fields_ = [("plane", C.c_int32), ("source", C.c_int32), ("channels", C.c_int32), ("reserved", C.c_int32),
+                ("out", _P)]
+
+
 class StepOut(C.Structure):
     _fields_ = [("obs", _P * VN_MAX_PLANES), ("goal_obs", _P * VN_MAX_PLANES), ("reward", _P), ("done", _P),
                 ("truncated", _P), ("win", _P), ("did_reset", _P), ("last_action_reward", _P),
                 ("episode_return", _P), ("episode_length", _P), ("info_state", _P), ("obs_state", _P), ("stats", _P),
                 ("gather_desc", _P), ("parity", C.c_int32), ("flags", C.c_int32), ("sched", _P), ("host_pack", _P),
                 ("host_seq", _P), ("seq", C.c_uint32), ("reserved", C.c_uint32),
-                ("rec_action", _P), ("rec_reward", _P), ("rec_done", _P), ("rec_state", _P), ("rec_goal", _P)]
+                ("rec_action", _P), ("rec_reward", _P), ("rec_done", _P), ("rec_state", _P), ("rec_goal", _P),
+                ("float_leaves", _P), ("n_float_leaves", C.c_int32), ("float_h", C.c_int32), ("float_w", C.c_int32),
+                ("reserved2", C.c_int32)]
 
 
 class Replay(C.Structure):
     _fields_ = [("before", _P), ("after", _P), ("goal", _P), ("goal_before", _P), ("action", _P), ("reward", _P),
                 ("done", _P),
                 ("n", C.c_int32), ("cap", C.c_int32), ("head", C.c_int32), ("count", C.c_int32)]
-
-
-class FloatLeaf(C.Structure):
-    _fields_ = [("plane", C.c_int32), ("source", C.c_int32), ("channels", C.c_int32), ("reserved", C.c_int32),
-                ("out", _P)]
 
 
 class VnError(RuntimeError):

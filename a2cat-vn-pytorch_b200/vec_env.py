@@ -150,9 +150,10 @@ class GraphVecEnv:
                          whole step as ONE fused launch for batches of one wave of CTAs; beyond that "persistent" is one
                          launch of a persistent grid (CTAs own envs: lanes step them, lane 0 copies their records) and
                          "bulk" / "ldg" are scalar kernel + gather kernel
-        numpy_obs        return the observation leaves (and last_action_reward) as fresh numpy arrays, like the
-                         reference's SubprocVecEnv, for a trainer that cannot take CUDA tensors: one device-to-host
-                         copy of the whole batch per step (PCIe-bound - C2: ~1.9 M instead of ~110 M env-steps/s)
+        numpy_obs        return the observation leaves (and last_action_reward) as numpy arrays, like the reference's
+                         SubprocVecEnv, for a trainer that cannot take CUDA tensors: one device-to-host copy of the whole
+                         batch per step (PCIe-bound).  True: views of two alternating sets of pinned buffers, valid
+                         until the step after next; "copy": private arrays (one more host copy of the batch)
         skip_unchanged   the observation leaves are views of persistent batch buffers owned by this object, so the
                          row of an env whose state did not change (collision, no-op) is not copied again
                          (VN_STEP_SKIP_UNCHANGED).  Pass False if the returned observation tensors are modified in
@@ -312,6 +313,10 @@ class GraphVecEnv:
                 L.FloatLeaf(lay.planes.index(name[5:] if name.startswith("goal_") else name),
                             1 if name.startswith("goal_") else 0, buf.shape[1], 0, buf.data_ptr())
                 for name, buf in self.float_buf.items()])
+            # the conversion is part of every reset / step call (vn_step_out_t.float_leaves): no extra C call per step
+            for o in (self._c_out, self._c_out_host):
+                o.float_leaves = C.cast(self._float_leaves, C.c_void_p)
+                o.n_float_leaves, o.float_h, o.float_w = len(self._float_leaves), h, w
         self._pending = False
         self._h2d_done = None
         self._serial_next = False
@@ -390,15 +395,20 @@ class GraphVecEnv:
             return len(leaves) - 1
 
         shape = walk(obs)
+        # two sets of pinned staging buffers used alternately: the arrays handed back are views of pinned memory (no
+        # second host copy of a 100+ MB batch, no page faults on fresh allocations) and stay valid until the step after
+        # next.  numpy_obs="copy" returns private copies instead, like SubprocVecEnv's np.stack.
+        self._stage_slot = getattr(self, "_stage_slot", 0) ^ 1
         staged = []
         for i, t in enumerate(leaves):
-            buf = self._host_stage.get(i)
+            key = (self._stage_slot, i)
+            buf = self._host_stage.get(key)
             if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-                buf = self._host_stage[i] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                buf = self._host_stage[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
             buf.copy_(t, non_blocking=True)
             staged.append(buf)
         torch.cuda.current_stream(self.device).synchronize()
-        host = [b.numpy().copy() for b in staged]
+        host = [b.numpy().copy() if self.numpy_obs == "copy" else b.numpy() for b in staged]
 
         def build(x):
             if isinstance(x, tuple):
@@ -411,20 +421,17 @@ class GraphVecEnv:
 
     def _convert_float_leaves(self, all_rows=False):
         """Float mode: TransposeImage + ScaledFloatFrame (thor_cached_auxiliary.py:61-62) of the step just enqueued,
-        one launch per leaf, reading the step's gather descriptors (record or -1 = row unchanged; goal record or
-        -1 = no reset): rows that did not change are not converted again."""
+        reading the step's gather descriptors (record or -1 = row unchanged; goal record or -1 = no reset): rows that
+        did not change are not converted again.  Normally the step call itself enqueues the one-launch conversion
+        (vn_step_out_t.float_leaves); this method serves odd geometries (one launch per leaf) and full refreshes."""
         if self.num_envs == 0:
             return
+        if not all_rows and self._float_leaves is not None:
+            return      # already enqueued by the reset / step call
         lay = self.world.layout
         h, w = lay.frame_hw
         desc = self._gather_desc[self._calls & 1]
         stream = self._stream()
-        if not all_rows and self._float_leaves is not None:
-            # one launch for every leaf (whole 4-pixel groups, 1- or 3-channel planes)
-            arr = self._float_leaves
-            self._call(self.lib.vn_gather_leaves_f32_chw, self._ref["store"], arr, len(arr), desc.data_ptr(),
-                       self.num_envs, h, w, stream)
-            return
         for name, buf in self.float_buf.items():
             goal = name.startswith("goal_")
             pi = lay.planes.index(name[5:] if goal else name)
@@ -633,7 +640,8 @@ class GraphVecEnv:
 
     def step(self, actions):
         if self.host_outputs and type(actions) is np.ndarray and not self._pending and not self.closed \
-                and actions.size == self.num_envs and self.num_envs and not self.scaled_float:
+                and actions.size == self.num_envs and self.num_envs and \
+                (not self.scaled_float or self._float_leaves is not None):
             # the reference-facing call, numpy in / numpy out, as ONE C call: stage the actions, enqueue both
             # kernels, spin until the scalars are in pinned memory, copy them out (vn_env_step_host_sync)
             n = self.num_envs

@@ -141,6 +141,15 @@ typedef struct vn_inject {
     int32_t reserved;
 } vn_inject_t;
 
+/* One float observation leaf (see vn_gather_leaves_f32_chw and vn_step_out_t.float_leaves). */
+typedef struct vn_float_leaf {
+    int32_t plane;
+    int32_t source;   /* 0 observation record, 1 goal record */
+    int32_t channels; /* 1 or 3 */
+    int32_t reserved;
+    float *out;       /* [n][channels][h][w] */
+} vn_float_leaf_t;
+
 /* Outputs of one vectorised step.  Any pointer may be NULL to skip that output. */
 typedef struct vn_step_out {
     uint8_t *obs[VN_MAX_PLANES];      /* [n_envs][plane_bytes[p]] observation batch, rows plane_bytes[p] apart */
@@ -183,6 +192,15 @@ typedef struct vn_step_out {
     uint8_t *rec_done;                /* = done */
     int32_t *rec_state;               /* state whose frames the NEXT observation shows (= obs_state, post auto-reset) */
     int32_t *rec_goal;                /* goal state of the next observation's episode */
+    /* Optional float observation mode (TransposeImage + ScaledFloatFrame, thor_cached_auxiliary.py:61-62, as part of the
+     * step): after the scalar half (and the uint8 gather, if obs[] are set) vn_env_reset / vn_env_step /
+     * vn_env_step_host* enqueue ONE more kernel that converts the records named by this step's descriptors into the
+     * persistent float32 CHW batches of these leaves (rows whose record did not change - and goal rows of envs that
+     * did not reset - keep their content).  Same restrictions as vn_gather_leaves_f32_chw; needs gather_desc. */
+    const vn_float_leaf_t *float_leaves; /* [host] n_float_leaves descriptors, read during the call; NULL = off */
+    int32_t n_float_leaves;
+    int32_t float_h, float_w;         /* frame geometry of the leaves */
+    int32_t reserved2;
 } vn_step_out_t;
 
 /* gather kernel variants (all bit-identical) */
@@ -299,13 +317,6 @@ int32_t vn_gather_plane_f32_chw_rows(const vn_store_t *store, int32_t plane, con
  * just enqueued - written as float32 CHW / 255 into row i of the persistent batch leaves[l].out; negative records
  * leave the row untouched.  VN_EUNSUPPORTED when H * W is not a multiple of 4 or a plane has neither 1 nor 3
  * channels (use vn_gather_plane_f32_chw_rows per leaf then).  At most 6 leaves. */
-typedef struct vn_float_leaf {
-    int32_t plane;
-    int32_t source;   /* 0 observation record, 1 goal record */
-    int32_t channels; /* 1 or 3 */
-    int32_t reserved;
-    float *out;       /* [n][channels][h][w] */
-} vn_float_leaf_t;
 int32_t vn_gather_leaves_f32_chw(const vn_store_t *store, const vn_float_leaf_t *leaves /* [host] */, int32_t n_leaves,
                                  const int32_t *desc /* [n][2] */, int32_t n, int32_t h, int32_t w, void *stream);
 

@@ -1155,27 +1155,35 @@ def test_cuda_graph_replays_with_an_odd_number_of_steps():
 
 
 def test_numpy_observation_mode_for_host_trainers():
-    """numpy_obs=True: reset() / step() return fresh numpy arrays in the reference's layout (what deep_rl's trainer
-    gets from SubprocVecEnv), equal to the CUDA batches of a twin env, in uint8 and in float mode."""
+    """numpy_obs: reset() / step() return numpy arrays in the reference's layout (what deep_rl's trainer gets from
+    SubprocVecEnv), equal to the CUDA batches of a twin env, in uint8 and in float mode.  True hands out views of two
+    alternating pinned staging sets (valid until the step after next), "copy" private arrays."""
     scene = H.scenes.make_maze_scene((10, 10), 0.25, 0, n_goals=2)
     world = T.compile_world([scene], T.GYM_GRAPH)
     for flt in (False, True):
-        a = vn.GraphVecEnv(world, 6, seed=1, max_episode_steps=9, scaled_float=flt)
-        b = vn.GraphVecEnv(world, 6, seed=1, max_episode_steps=9, scaled_float=flt, numpy_obs=True, device_world=a.dw)
-        (oa, la), (ob, lb) = a.reset(), b.reset()
-        rng = np.random.RandomState(0)
-        kept = None
-        for t in range(12):
-            act = rng.randint(0, 4, 6)
-            (oa, la), ra, da, _ = a.step(act)
-            (ob, lb), rb, db, _ = b.step(act)
-            assert all(isinstance(x, np.ndarray) for x in ob) and isinstance(lb, np.ndarray)
-            assert all(np.array_equal(x.cpu().numpy(), y) for x, y in zip(oa, ob)) and np.array_equal(la.cpu().numpy(), lb)
-            assert np.array_equal(ra, rb) and np.array_equal(da, db)
-            if t == 3:
-                kept = (ob[0], ob[0].copy())
-        assert np.array_equal(*kept)              # arrays handed out earlier are not overwritten by later steps
-        assert ob[0].dtype == (np.float32 if flt else np.uint8)
+        for mode in (True, "copy"):
+            a = vn.GraphVecEnv(world, 6, seed=1, max_episode_steps=9, scaled_float=flt)
+            b = vn.GraphVecEnv(world, 6, seed=1, max_episode_steps=9, scaled_float=flt, numpy_obs=mode, device_world=a.dw)
+            (oa, la), (ob, lb) = a.reset(), b.reset()
+            rng = np.random.RandomState(0)
+            kept, prev = None, None
+            for t in range(12):
+                act = rng.randint(0, 4, 6)
+                (oa, la), ra, da, _ = a.step(act)
+                if prev is not None:
+                    prev = (prev[0], prev[0].copy())
+                (ob, lb), rb, db, _ = b.step(act)
+                if prev is not None:
+                    assert np.array_equal(*prev)      # the previous step's arrays survive one more step in both modes
+                prev = (ob[0], None)
+                assert all(isinstance(x, np.ndarray) for x in ob) and isinstance(lb, np.ndarray)
+                assert all(np.array_equal(x.cpu().numpy(), y) for x, y in zip(oa, ob)) and np.array_equal(la.cpu().numpy(), lb)
+                assert np.array_equal(ra, rb) and np.array_equal(da, db)
+                if t == 3:
+                    kept = (ob[0], ob[0].copy())
+            if mode == "copy":
+                assert np.array_equal(*kept)          # private arrays are never overwritten by later steps
+            assert ob[0].dtype == (np.float32 if flt else np.uint8)
 
 
 def test_make_vec_from_scene_pickles(tmp_path):
