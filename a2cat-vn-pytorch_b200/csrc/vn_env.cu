@@ -273,6 +273,9 @@ __global__ void __launch_bounds__(kStepThreads) vn_step_kernel(const StepParams 
     if (!defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // the ticket counter the gather of THIS step draws from (the previous gather, possibly still running, uses the
+    // other one; the last launch that used this one completed before the previous scalar half did)
+    if (i == 0 && p.out.sched) p.out.sched[p.out.parity & 1] = 0u;
     EnvStats st;
     if (i < p.env.n_envs) {
         int rec, grec;
@@ -315,6 +318,7 @@ struct GatherParams {
     uint8_t *goal_obs[VN_MAX_PLANES];
     unsigned int *sched;  // optional ticket counters (dynamic scheduling), see vn_gather_bulk_kernel
     int32_t n;
+    int32_t parity;  // which of the two ticket counters (sched[0..1]) this launch draws from
     // 1: let the next kernel in the stream be scheduled while this one runs (the step path, where the successor is the
     // next scalar kernel and never writes what this gather reads).  0 (vn_gather_plane): the index list is caller
     // memory - often env.state / obs_state / goal themselves - that a following step kernel REWRITES, so the successor
@@ -400,9 +404,16 @@ struct BulkHints {
     uint64_t load_policy, store_policy;
 };
 
+struct NoPrefetch {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// `while_loading()` runs after the global->shared copies of the slice have been issued and before the wait for them: the
+// place to fetch whatever the NEXT unit needs (ticket, descriptor) so that its latency hides behind this transfer.
+template <typename F = NoPrefetch>
 __device__ __forceinline__ void bulk_copy_slice(const vn_store_t &st, const uint8_t *src, uint8_t *const *dst,
                                                 int env, int slice, int split, uint8_t *smem, uint64_t *bar,
-                                                uint32_t &parity, const BulkHints &hints) {
+                                                uint32_t &parity, const BulkHints &hints, F while_loading = F()) {
     // the previous shared->global reads of this buffer must have drained before it is refilled
     bulk_wait_read<0>();
     uint32_t total = 0;
@@ -428,6 +439,7 @@ __device__ __forceinline__ void bulk_copy_slice(const vn_store_t &st, const uint
                 off += (uint32_t)(hi - lo) << 4;
             }
         }
+    while_loading();
     mbar_wait(bar, parity);
     parity ^= 1;
     off = 0;
@@ -466,40 +478,47 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
     const int units = p.n * split;
     const bool dynamic = sched != nullptr;
+    static_assert(sizeof(int2) == 8, "descriptor layout");
+    // (record, goal record) of a unit; -1 = nothing to copy (row unchanged / no reset / past the end)
+    auto unit_desc = [&](int u) -> int2 {
+        if (u >= units) return make_int2(-1, -1);
+        const int env = u / split;
+        if (p.desc) return p.desc[env];
+        int2 d = make_int2(p.obs_state[env], -1);
+        if (p.goal && (!p.did_reset || p.did_reset[env])) d.y = p.goal[env];
+        return d;
+    };
     // the first unit of every CTA is its block index (no atomic round trip before the first copy); the units
-    // beyond the grid are handed out by the ticket counter
+    // beyond the grid are handed out by the ticket counter.  The NEXT unit - its ticket and its descriptor, two
+    // dependent round trips through L2 - is fetched while the copies of the current one are in flight (prefetch != 0).
     int u = (int)blockIdx.x;
+    int2 d = unit_desc(u);
     while (u < units) {
         const int env = u / split, slice = u - env * split;
-        int rec, grec = -1;
-        if (p.desc) {
-            const int2 d = p.desc[env];
-            rec = d.x;
-            grec = d.y;
-        } else {
-            rec = p.obs_state[env];
-            if (p.goal && (!p.did_reset || p.did_reset[env])) grec = p.goal[env];
+        int u_next = 0;
+        int2 d_next = make_int2(-1, -1);
+        bool have_next = false;
+        auto fetch_next = [&]() {
+            if (have_next) return;
+            u_next = dynamic ? (int)gridDim.x + (int)atomicAdd(sched, 1u) : u + (int)gridDim.x;
+            d_next = unit_desc(u_next);
+            have_next = true;
+        };
+        if (d.x >= 0) {  // < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
+            const uint8_t *src = p.store.base + (size_t)d.x * p.store.state_pitch;
+            bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, &bar, parity, hints, fetch_next);
         }
-        if (rec >= 0) {  // rec < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
-            const uint8_t *src = p.store.base + (size_t)rec * p.store.state_pitch;
-            bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, &bar, parity, hints);
+        if (d.y >= 0) {
+            const uint8_t *gsrc = p.store.base + (size_t)d.y * p.store.state_pitch;
+            bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints, fetch_next);
         }
-        if (grec >= 0) {
-            const uint8_t *gsrc = p.store.base + (size_t)grec * p.store.state_pitch;
-            bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints);
-        }
-        u = dynamic ? (int)gridDim.x + (int)atomicAdd(&sched[0], 1u) : u + (int)gridDim.x;
+        fetch_next();
+        u = u_next;
+        d = d_next;
     }
     bulk_wait_read<0>();
-    if (dynamic) {
-        // last CTA out re-arms the slot for the launch that will reuse it
-        __threadfence();
-        if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {
-            sched[0] = 0;
-            sched[1] = 0;
-            __threadfence();
-        }
-    }
+    // no epilogue: the ticket counter of this launch (sched[parity]) is zeroed by the scalar half of the step that
+    // next uses it - a fence + atomic + re-arm here sat on the critical path of every launch (~1 us)
 }
 
 // ---- fused single launch for small batches ----------------------------------------------------------
@@ -660,14 +679,22 @@ __global__ void __launch_bounds__(32) vn_step_gather_kernel(const StepParams sp,
     hints.load_policy = (hint_mode & 1) ? l2_policy_evict_last() : (hint_mode & 4) ? l2_policy_evict_first() : 0;
     hints.store_policy = (hint_mode & 2) ? l2_policy_evict_first() : (hint_mode & 8) ? l2_policy_evict_last() : 0;
     hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
+    int2 d = desc[b];
     for (int e = b; e < n; e += G) {
-        const int2 d = desc[e];
+        int2 d_next = make_int2(-1, -1);
+        bool have_next = false;
+        auto fetch_next = [&]() {  // the next descriptor is read while this env's copies are in flight
+            if (!have_next && e + G < n) d_next = desc[e + G];
+            have_next = true;
+        };
         if (d.x >= 0)  // < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
             bulk_copy_slice(gp.store, gp.store.base + (size_t)d.x * gp.store.state_pitch, gp.obs, e, 0, 1, smem, &bar,
-                            parity, hints);
+                            parity, hints, fetch_next);
         if (d.y >= 0 && gp.goal)
             bulk_copy_slice(gp.store, gp.store.base + (size_t)d.y * gp.store.state_pitch, gp.goal_obs, e, 0, 1, smem, &bar,
-                            parity, hints);
+                            parity, hints, fetch_next);
+        fetch_next();
+        d = d_next;
     }
     bulk_wait_read<0>();
 }
@@ -810,7 +837,7 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         if (env_per_sm > 0) per_sm = min(per_sm, env_per_sm);
         const int grid = (int)min((int64_t)gp.n * split, (int64_t)sm_count() * per_sm);
         launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, split,
-                   env_dynamic ? gp.sched : nullptr, env_hints);
+                   (env_dynamic && gp.sched) ? gp.sched + (gp.parity & 1) : nullptr, env_hints);
         return check_launch("vn_gather_bulk_kernel");
     }
     set_error("gather: unknown variant %d", variant);
@@ -885,6 +912,7 @@ static int32_t make_gather_params(GatherParams &gp, const vn_store_t *store, con
     gp.goal = any_goal ? envs->goal : nullptr;
     gp.did_reset = out->did_reset;
     gp.sched = out->sched;
+    gp.parity = out->parity;
     gp.early_release = 1;
     gp.desc = out->gather_desc
                   ? reinterpret_cast<const int2 *>(out->gather_desc) + (size_t)(out->parity & 1) * envs->n_envs
@@ -1352,6 +1380,7 @@ int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *i
     gp.did_reset = nullptr;
     gp.desc = nullptr;
     gp.sched = nullptr;  // static unit assignment: no scratch in this signature
+    gp.parity = 0;
     gp.early_release = 0;  // idx is caller memory a following step may rewrite: no early start of the successor
     gp.n = n;
     for (int pl = 0; pl < VN_MAX_PLANES; ++pl) {

@@ -170,9 +170,11 @@ typedef struct vn_step_out {
                                          descriptors handed from the scalar half to the gather half of step `parity` */
     int32_t parity;                   /* step counter (only bit 0 is used); the caller increments it every reset / step */
     int32_t flags;                    /* VN_STEP_* */
-    uint32_t *sched;                  /* optional scratch of 4 uint32, zeroed once by the caller: [0..1] ticket counters of
-                                         the gather's dynamic scheduler, [2] arrival counter of the persistent launch's host
-                                         signal ([3] reserved; self re-arming; one scratch per env batch / stream) */
+    uint32_t *sched;                  /* optional scratch of 4 uint32, zeroed once by the caller: [parity & 1] is the ticket
+                                         counter of this step's gather (zeroed by the step's scalar half, so
+                                         vn_env_gather runs exactly ONCE after each vn_env_step_scalar), [2] the arrival
+                                         counter of the persistent launch's host signal (self re-arming), [3] reserved; one
+                                         scratch per env batch / stream */
     uint8_t *host_pack;               /* optional MAPPED PINNED HOST block of 20 * n_envs bytes ("host pack") that the
                                          scalar kernel also writes, n = n_envs:
                                            [0, 4n) reward f32 | [4n, 8n) episode_return f32 | [8n, 12n) episode_length i32
