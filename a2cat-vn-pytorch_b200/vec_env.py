@@ -60,6 +60,33 @@ def resolve_layout(layout):
     return layout
 
 
+def build_spaces(store_layout, obs_layout, scaled_float=False, unreal_wrapper=True, n_actions=4):
+    """(observation_space, action_space) of a GraphVecEnv - no device needed.  What the reference's trainer reads:
+    ``observation_space.spaces[0].spaces[0].shape[0]`` = channels of the first leaf after TransposeImage and
+    ``action_space.n`` (experiments/thor_cached_auxiliary.py:55).  uint8 leaves are HWC as the raw env emits them
+    (gym_graph/graph.py:26-31,99-104); with scaled_float they are float32 CHW in [0, 1], the spaces the wrapper stack
+    TransposeImage + ScaledFloatFrame leaves behind (:61-62); unreal_wrapper appends the last_action_reward Box (:63)."""
+    lay = store_layout
+    h, w = lay.frame_hw
+    leaves = resolve_layout(obs_layout)
+
+    def frame(leaf):
+        p = leaf[5:] if leaf.startswith("goal_") else leaf
+        c = lay.channels[lay.planes.index(p)]
+        if scaled_float:
+            return spaces.Box(0.0, 1.0, (c, h, w), np.float32)
+        return spaces.Box(0, 255, (h, w, c), np.uint8)
+
+    if isinstance(leaves, dict):
+        inner = spaces.Dict({k: frame(v) for k, v in leaves.items()})
+    elif isinstance(leaves, tuple):
+        inner = spaces.Tuple(tuple(frame(v) for v in leaves))
+    else:
+        inner = frame(leaves)
+    obs = spaces.Tuple((inner, spaces.Box(0.0, 1.0, (n_actions + 1,), np.float32))) if unreal_wrapper else inner
+    return obs, spaces.Discrete(n_actions)
+
+
 def shard_range(num_envs_total, rank=0, world_size=1):
     """Envs [lo, hi) owned by ``rank``: contiguous, sizes differ by at most one."""
     base, rem = divmod(num_envs_total, world_size)
@@ -289,22 +316,8 @@ class GraphVecEnv:
         self._ref = dict(store=C.byref(self.dw.store), tables=C.byref(self.dw.tables), envs=C.byref(self._c_envs),
                          rules=C.byref(self._c_rules), out=C.byref(self._c_out), out_host=C.byref(self._c_out_host))
 
-        def frame(leaf):
-            p = leaf[5:] if leaf.startswith("goal_") else leaf
-            c = lay.channels[lay.planes.index(p)]
-            if scaled_float:
-                return spaces.Box(0.0, 1.0, (c, h, w), np.float32)
-            return spaces.Box(0, 255, (h, w, c), np.uint8)
-
-        if isinstance(self.leaves, dict):
-            inner = spaces.Dict({k: frame(v) for k, v in self.leaves.items()})
-        elif isinstance(self.leaves, tuple):
-            inner = spaces.Tuple(tuple(frame(v) for v in self.leaves))
-        else:
-            inner = frame(self.leaves)
-        self.observation_space = spaces.Tuple((inner, spaces.Box(0.0, 1.0, (self.n_actions + 1,), np.float32))) \
-            if unreal_wrapper else inner
-        self.action_space = spaces.Discrete(self.n_actions)
+        self.observation_space, self.action_space = build_spaces(lay, obs_layout, scaled_float, unreal_wrapper,
+                                                                 self.n_actions)
         self.set_hardness = self.set_complexity     # experiments/thor_cached_auxiliary.py:68
         self._float_leaves = None
         if self.float_buf and (h * w) % 4 == 0 and len(self.float_buf) <= 6 and \

@@ -57,6 +57,9 @@ class GymGraphEnv:
     def __init__(self, scene: OracleScene, goals=None, rewards=(1.0, 0.0, 0.0)):
         self.graph = scene
         self.goals = scene.goals if goals is None else goals           # :21-24
+        from .vec import _Box
+        self.observation_space = _Box(0, 255, scene.observation_shape, np.uint8)    # :26-31 (uint8 scenes)
+        self.action_space = type("Discrete", (), {"n": 4})()                        # :33
         self.state = None
         self.largest_distance = int(np.max(scene.graph))               # :35
         self.complexity = None
@@ -97,8 +100,15 @@ class GymGraphAuxiliaryEnv(GymGraphEnv):
     """environments/gym_graph/graph.py:96-120 GoalGymGraphAuxiliaryEnv: 5-tuple observation
     ``(rgb, goal_rgb, depth, segmentation, goal_segmentation)``, goal planes memoised per goal."""
 
-    def __init__(self, *a, **k):
+    def __init__(self, *a, screen_size=None, **k):
         super().__init__(*a, **k)
+        from .vec import _Box, _Tuple
+        # :98-104 - the declared Boxes of leaves 1.. use the env's own `screen_size` argument, which it does NOT forward
+        # to the scene's GraphResize (SURVEY.md A10): the frames keep the scene's size whatever is declared here
+        ss = tuple(screen_size) if screen_size is not None else tuple(self.graph.observation_shape[:2])
+        self.observation_space = _Tuple((self.observation_space, _Box(0, 255, ss + (3,), np.uint8),
+                                         _Box(0, 255, ss + (1,), np.uint8), _Box(0, 255, ss + (3,), np.uint8),
+                                         _Box(0, 255, ss + (3,), np.uint8)))
         self._cached_goal = (None, None)
 
     def render_goal(self):                                              # :110-115

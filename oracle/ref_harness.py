@@ -187,6 +187,88 @@ def ref_aux_trainer():
     return importlib.import_module("experiments.ai2_auxiliary.trainer")
 
 
+_EXPERIMENT = {"get_graph": None, "model_calls": []}      # what the (import-once) experiment module currently sees
+
+
+def ref_experiment(get_graph, model_calls=None):
+    """experiments/thor_cached_auxiliary.py imported UNMODIFIED: ``Trainer`` (:26-56), ``create_envs`` (:58-71) and
+    ``default_args`` (:73-84).  What the module needs from outside the tree is supplied as follows:
+
+      * ``deep_rl`` (un-vendored): the wrapper stack and the VecEnv are the restatements of oracle/vec.py
+        (RewardCollector, TransposeImage, ScaledFloatFrame, UnrealEnvBaseWrapper, SubprocVecEnv = in-process);
+        ``register_trainer`` / schedules / tester classes are inert stand-ins;
+      * ``environments.make(id=..., **kwargs)``: gym.make for the ids registered in environments/gym_graph/__init__.py
+        (entry point + TimeLimit(max_episode_steps)), building the reference's own env class;
+      * ``get_graph(name)`` (environments/gym_graph/download.py:37-75 reads ~/.visual_navigation/scenes): the callable
+        given here, returning a ThorGridWorld built from a synthetic scene;
+      * ``models.AuxiliaryBigGoalHouseModel``: a recorder - ``model_calls`` receives the constructor arguments.
+    """
+    install()
+    from oracle import vec as ovec
+    import torch  # noqa: F401  (the module imports it)
+
+    def _stub(name, **attrs):
+        mod = sys.modules.get(name) or types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(mod, k, v)
+        sys.modules[name] = mod
+        return mod
+
+    ref_aux_trainer()          # deep_rl.a2c_unreal.* stubs + experiments namespace packages
+    _EXPERIMENT["get_graph"] = get_graph
+    _EXPERIMENT["model_calls"] = model_calls if model_calls is not None else []
+    if "experiments.thor_cached_auxiliary" in sys.modules:      # imported once per process; only the state changes
+        return sys.modules["experiments.thor_cached_auxiliary"]
+
+    class _Model:
+        def __init__(self, *args, **kwargs):
+            _EXPERIMENT["model_calls"].append((args, kwargs))
+
+    class _Schedule:
+        def __init__(self, *a, **k):
+            self.args = a
+
+    def register_trainer(**kwargs):
+        def deco(cls):
+            cls.registered_kwargs = kwargs
+            for k, v in kwargs.items():      # deep_rl exposes the registration kwargs as trainer attributes
+                setattr(cls, k, v)           # (Trainer.__init__ reads self.max_time_steps, :36)
+            return cls
+        return deco
+
+    class _UnrealTrainer:
+        def __init__(self, *a, **k):
+            self.max_time_steps = k.get("max_time_steps", 2e6)
+
+    sys.modules["deep_rl.a2c_unreal"].UnrealTrainer = _UnrealTrainer
+    _stub("deep_rl", register_trainer=register_trainer)
+    _stub("deep_rl.common.env", RewardCollector=ovec.RewardCollectorWrapper, TransposeImage=ovec.TransposeImageWrapper,
+          ScaledFloatFrame=ovec.ScaledFloatFrameWrapper)
+    _stub("deep_rl.common.vec_env", DummyVecEnv=ovec.InProcessVecEnv, SubprocVecEnv=ovec.InProcessVecEnv)
+    sys.modules["deep_rl.a2c_unreal.util"].UnrealEnvBaseWrapper = ovec.UnrealEnvBaseWrapper
+    _stub("deep_rl.configuration", configuration=types.SimpleNamespace())
+    _stub("deep_rl.common.schedules", LinearSchedule=_Schedule, MultistepSchedule=_Schedule)
+    _stub("deep_rl.model", TimeDistributed=object, Flatten=object, MaskedRNN=object)
+    _stub("deep_rl.common.tester", TestingEnv=type("TestingEnv", (), {}), TestingVecEnv=type("TestingVecEnv", (), {}))
+    _stub("models", AuxiliaryBigGoalHouseModel=_Model)
+    _stub("environments.gym_house")
+    _stub("environments.gym_house.multi", create_multiscene=lambda *a, **k: None)
+
+    gym_graph = importlib.import_module("environments.gym_graph.graph")
+    gym_graph.get_graph = lambda name: _EXPERIMENT["get_graph"](name)
+    registry = {   # environments/gym_graph/__init__.py:18-28
+        "OrientedGraph-v0": (gym_graph.OrientedGraphEnv, 900),
+        "AuxiliaryGraph-v0": (gym_graph.GoalGymGraphAuxiliaryEnv, 900),
+    }
+
+    def make(id, **kwargs):
+        cls, limit = registry[id]
+        return ovec.TimeLimitWrapper(cls(**kwargs), limit)
+
+    sys.modules["environments"].make = make
+    return importlib.import_module("experiments.thor_cached_auxiliary")
+
+
 # --------------------------------------------------------------------------- stream injection
 class InjectedRandom:
     """Replaces the module-level ``random`` seen by a reference env module so that

@@ -182,3 +182,180 @@ class ReferenceStyleResetSource:
         w = gu.initial_state_weights(dists, self.od(t))
         x = self.rng.choice(np.arange(len(pots)), p=w)
         return t, pots[x]
+
+
+# --------------------------------------------------------------------------- the experiment's wrapper stack as classes
+# experiments/thor_cached_auxiliary.py:58-64 builds every env as
+#     UnrealEnvBaseWrapper(ScaledFloatFrame(TransposeImage(RewardCollector(env))))
+# and hands the env functions to SubprocVecEnv.  The four wrappers and the VecEnv live in deep_rl (UN-VENDORED,
+# PARITY UNPINNED): the classes below restate them [recalled] as gym-style wrappers - observation_space included,
+# because Trainer.create_model reads it (thor_cached_auxiliary.py:55) - so that the reference's own create_envs /
+# Trainer can be executed unmodified against them (oracle/ref_harness.ref_experiment).
+class _Box:
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), np.dtype(dtype)
+
+
+class _Tuple:
+    def __init__(self, spaces):
+        self.spaces = tuple(spaces)
+
+
+def _map_space(space, fn):
+    if hasattr(space, "spaces"):
+        return _Tuple(tuple(_map_space(s, fn) for s in space.spaces))
+    return fn(space)
+
+
+def _map_obs(obs, fn):
+    if isinstance(obs, tuple):
+        return tuple(_map_obs(o, fn) for o in obs)
+    return fn(obs)
+
+
+class _Wrapper:
+    def __init__(self, env):
+        self.env = env
+        self.observation_space = getattr(env, "observation_space", None)
+        self.action_space = getattr(env, "action_space", None)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped if hasattr(self.env, "unwrapped") else self.env
+
+    def reset(self):
+        return self.observation(self.env.reset())
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        return self.observation(obs), reward, done, info
+
+    def observation(self, obs):
+        return obs
+
+
+class TimeLimitWrapper(_Wrapper):
+    """gym 0.15.7 TimeLimit as gym.make applies it for ids registered with max_episode_steps
+    (environments/gym_graph/__init__.py:24-28: 900 for AuxiliaryGraph-v0)."""
+
+    def __init__(self, env, max_episode_steps):
+        super().__init__(env)
+        self._max, self._elapsed = max_episode_steps, 0
+
+    def reset(self):
+        self._elapsed = 0
+        return self.env.reset()
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        self._elapsed += 1
+        if self._elapsed >= self._max:
+            info["TimeLimit.truncated"] = not done
+            done = True
+        return obs, reward, done, info
+
+
+class RewardCollectorWrapper(_Wrapper):
+    """deep_rl.common.env.RewardCollector [recalled]."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.ret, self.len = 0.0, 0
+
+    def reset(self):
+        self.ret, self.len = 0.0, 0
+        return self.env.reset()
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        self.ret = float(np.float32(np.float32(self.ret) + np.float32(reward)))
+        self.len += 1
+        if done:
+            info["episode"] = dict(r=self.ret, l=self.len)
+        return obs, reward, done, info
+
+
+class TransposeImageWrapper(_Wrapper):
+    """deep_rl.common.env.TransposeImage [recalled]: every image leaf HWC -> CHW, spaces included."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = _map_space(env.observation_space,
+                                            lambda b: _Box(b.low, b.high, (b.shape[2], b.shape[0], b.shape[1]), b.dtype))
+
+    def observation(self, obs):
+        return _map_obs(obs, lambda x: np.transpose(x, (2, 0, 1)))
+
+
+class ScaledFloatFrameWrapper(_Wrapper):
+    """deep_rl.common.env.ScaledFloatFrame [recalled]: float32(x) / 255.0, spaces become Box(0, 1, float32)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = _map_space(env.observation_space, lambda b: _Box(0.0, 1.0, b.shape, np.float32))
+
+    def observation(self, obs):
+        return _map_obs(obs, lambda x: np.asarray(x).astype(np.float32) / 255.0)
+
+
+class UnrealEnvBaseWrapper(_Wrapper):
+    """deep_rl.a2c_unreal.util.UnrealEnvBaseWrapper [recalled]: obs -> (obs, last_action_reward)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.n_actions = env.action_space.n
+        self.observation_space = _Tuple((env.observation_space, _Box(0.0, 1.0, (self.n_actions + 1,), np.float32)))
+
+    def reset(self):
+        return self.env.reset(), np.zeros(self.n_actions + 1, np.float32)
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        return (obs, last_action_reward(int(action), reward, self.n_actions)), reward, done, info
+
+
+class InProcessVecEnv:
+    """deep_rl.common.vec_env.SubprocVecEnv / DummyVecEnv [recalled], all workers in this process: the worker loop
+    ``ob, r, done, info = env.step(a); if done: ob = env.reset()``, leaves stacked on axis 0, ``call_unwrapped``."""
+
+    def __init__(self, env_fns):
+        self.envs = [fn() for fn in env_fns]
+        self.num_envs = len(self.envs)
+        self.observation_space = self.envs[0].observation_space
+        self.action_space = self.envs[0].action_space
+        self.unwrapped_calls = []
+
+    @staticmethod
+    def _stack(obs_list):
+        first = obs_list[0]
+        if isinstance(first, tuple):
+            return tuple(InProcessVecEnv._stack([o[i] for o in obs_list]) for i in range(len(first)))
+        return np.stack(obs_list)
+
+    def reset(self):
+        return self._stack([e.reset() for e in self.envs])
+
+    def step(self, actions):
+        obs, rews, dones, infos = [], [], [], []
+        for e, a in zip(self.envs, actions):
+            ob, r, d, info = e.step(int(a))
+            if d:
+                ob = e.reset()
+            obs.append(ob)
+            rews.append(r)
+            dones.append(d)
+            infos.append(info)
+        return self._stack(obs), np.array(rews, np.float32), np.array(dones, bool), infos
+
+    def step_async(self, actions):
+        self._pending = actions
+
+    def step_wait(self):
+        return self.step(self._pending)
+
+    def call_unwrapped(self, name, *args, **kwargs):
+        self.unwrapped_calls.append((name, args))
+        return [getattr(e.unwrapped, name)(*args, **kwargs) for e in self.envs]
+
+    def close(self):
+        pass

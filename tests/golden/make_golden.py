@@ -409,6 +409,102 @@ def gen_aux_target(ref_trainer):
     save("aux_target", x_seed=7, y20=y20, y21=y21, yd=yd)
 
 
+def trainer_contract_scene():
+    """The synthetic stand-in for 'thor-cached-212-174' (download.py:21-29): native 174 x 174 frames."""
+    return scenes.make_maze_scene((6, 6), 0.2, 11, n_goals=1, frame_hw=(174, 174))
+
+
+def gen_trainer_contract(ref):
+    """experiments/thor_cached_auxiliary.py run UNMODIFIED (rh.ref_experiment): ``Trainer()`` is constructed,
+    ``Trainer.create_env`` (:50-52) calls the reference's own ``create_envs`` (:58-71) with ``default_args()`` - only
+    the scene name / goal are ours - and ``Trainer.create_model`` (:54-56) reads the observation space.  The VecEnv is
+    then driven with an injected action stream; what crosses the seam is recorded: spaces, Model arguments, the
+    set_hardness calls, and per step every float32 CHW leaf (CRC), last_action_reward, rewards, dones, episode infos."""
+    scene = trainer_contract_scene()
+    world = dense_world(ref, scene)
+    world.graph, world.optimal_actions = ref.util.compute_shortest_path_data(scene.maze)
+    calls = []
+    exp = rh.ref_experiment(lambda name: world, calls)
+    args = exp.default_args()
+    goal = scene.goals[0]
+    env_kwargs = dict(args["env_kwargs"], tasks=[("synthetic-174", [goal])] * 4)
+    N, T = 4, 240
+    inj_choice = rh.InjectedChoice(np.random.RandomState(5).randint(0, 1 << 32, size=100000, dtype=np.uint64))
+    orig = np.random.choice
+    np.random.choice = inj_choice
+    log = ResetLog(N)
+    try:
+        trainer = exp.Trainer()
+        assert (trainer.num_processes, trainer.num_steps, trainer.gamma) == (4, 20, .99)
+        env = trainer.env = trainer.create_env(env_kwargs)
+        trainer.create_model()
+        for i, e in enumerate(env.envs):             # record every start state the reference samples from here on
+            base = e.unwrapped
+
+            def rec_reset(orig_reset=base.reset, i=i, base=base):
+                ob = orig_reset()
+                log.choice[i].append(0)
+                log.start[i].append(base.state)
+                return ob
+            base.reset = rec_reset
+        rng = np.random.RandomState(6)
+        actions = rng.randint(0, 4, size=(T, N)).astype(np.int32)
+        greedy = rng.rand(T, N) < 0.6
+
+        def toward_goal(state):
+            """A policy that actually finishes episodes: the action whose successor is closest to the goal (grid
+            distance, then rotation mismatch) - only a way to pick the recorded action stream."""
+            best, best_a = None, 0
+            for a in range(4):
+                n = ref.util.step(state, a)
+                if not ref.util.is_valid_state(world.maze, n):
+                    continue
+                key = (int(world.graph[n[0], n[1], goal[0], goal[1]]), min((n[2] - goal[2]) % 4, (goal[2] - n[2]) % 4))
+                if best is None or key < best:
+                    best, best_a = key, a
+            return best_a
+
+        def leaf_crcs(obs):
+            leaves, lar = obs
+            return np.array([[crc(x[i]) for x in leaves] for i in range(N)], np.uint32), np.array(lar, np.float32)
+
+        obs = env.reset()
+        reset_crc, reset_lar = leaf_crcs(obs)
+        shapes = np.array([x.shape for x in obs[0]], np.int32)
+        dtypes = np.array([str(x.dtype) for x in obs[0]] + [str(obs[1].dtype)])
+        rec = dict(rewards=np.zeros((T, N), np.float32), dones=np.zeros((T, N), bool), obs_crc=np.zeros((T, N, 5), np.uint32),
+                   lar=np.zeros((T, N, 5), np.float32), ep_r=np.zeros((T, N), np.float32), ep_l=np.zeros((T, N), np.int32),
+                   states=np.zeros((T, N, 3), np.int32), hardness_t=np.array([120], np.int32), hardness_c=np.array([0.3]))
+        for t in range(T):
+            if t == 120:
+                env.set_hardness(0.3)                                   # the schedule the trainer applies, :45 / :68
+            for i, e in enumerate(env.envs):
+                if greedy[t, i]:
+                    actions[t, i] = toward_goal(e.unwrapped.state)
+            obs, r, d, infos = env.step(actions[t])
+            rec["rewards"][t], rec["dones"][t] = r, d
+            rec["obs_crc"][t], rec["lar"][t] = leaf_crcs(obs)
+            rec["states"][t] = [e.unwrapped.state for e in env.envs]
+            for i, info in enumerate(infos):
+                if d[i]:
+                    rec["ep_r"][t, i], rec["ep_l"][t, i] = info["episode"]["r"], info["episode"]["l"]
+    finally:
+        np.random.choice = orig
+    sp = env.observation_space
+    c, s, cnt = log.pack(3)
+    save("trainer_contract", maze=scene.maze, frame_seed=scene.frame_seed, scene_id=scene.scene_id,
+         goal=np.array(goal, np.int32), actions=actions, max_episode_steps=900,
+         reset_choice=c, reset_start=s, reset_count=cnt,
+         # what Trainer.create_model passed to Model (:55) and what it read it from
+         model_args=np.array(calls[0][0], np.int32),
+         space_leaf_shapes=np.array([b.shape for b in sp.spaces[0].spaces], np.int32),
+         space_lar_shape=np.array(sp.spaces[1].shape, np.int32), action_n=env.action_space.n,
+         unwrapped_calls=np.array([[a[0] for _, a in env.unwrapped_calls]]),       # set_complexity(0.01), set_complexity(0.3)
+         unwrapped_names=np.array([n for n, _ in env.unwrapped_calls]),
+         obs_shapes=shapes, obs_dtypes=dtypes, reset_obs_crc=reset_crc, reset_lar=reset_lar,
+         reset_states=np.array([log.start[i][0] for i in range(N)], np.int32), **rec)
+
+
 if __name__ == "__main__":
     ref = rh.ref_modules()
     gen_graph_util(ref)
@@ -417,3 +513,4 @@ if __name__ == "__main__":
     gen_maze_render(ref)
     gen_thor_cached(ref)
     gen_aux_target(rh.ref_aux_trainer())
+    gen_trainer_contract(ref)

@@ -146,3 +146,40 @@ def write_reference_style_pickle(scene, path, frame=12):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def trainer_contract_scene(g):
+    """The synthetic 174 x 174 scene of tests/golden/trainer_contract.npz (make_golden.trainer_contract_scene)."""
+    return scenes.GridScene(g["maze"], [tuple(int(v) for v in g["goal"])], True, (174, 174),
+                            ("rgb", "depth", "segmentation"), frame_seed=int(g["frame_seed"]), scene_id=int(g["scene_id"]))
+
+
+def check_trainer_contract_run(g, env, crc_of_leaf, complexity_setter):
+    """Replays the golden of the reference's own Trainer / create_envs (experiments/thor_cached_auxiliary.py) on `env`
+    - anything with the VecEnv surface - and compares everything that crosses the seam: leaf order / shape / dtype,
+    every float32 CHW leaf (CRC), last_action_reward, rewards, dones, episode infos."""
+    T, N = g["actions"].shape
+    obs = env.reset()
+    leaves, lar = obs
+    assert len(leaves) == 5 and [tuple(x.shape) for x in leaves] == [tuple(s) for s in g["obs_shapes"]]
+    assert [str(x.dtype).replace("torch.", "") for x in leaves] == list(g["obs_dtypes"][:5])
+    assert np.array_equal(np.array([[crc_of_leaf(x, i) for x in leaves] for i in range(N)], np.uint32), g["reset_obs_crc"])
+    assert np.array_equal(np.asarray(lar.cpu() if hasattr(lar, "cpu") else lar), g["reset_lar"])
+    sched = dict(zip(g["hardness_t"].tolist(), g["hardness_c"].tolist()))
+    for t in range(T):
+        if t in sched:
+            complexity_setter(sched[t])
+        (leaves, lar), r, d, infos = env.step(g["actions"][t])
+        assert np.array_equal(np.asarray(d), g["dones"][t]), t
+        assert np.array_equal(np.asarray(r, np.float32).view(np.uint32), g["rewards"][t].view(np.uint32)), t
+        assert np.array_equal(np.asarray(lar.cpu() if hasattr(lar, "cpu") else lar, np.float32).view(np.uint32),
+                              g["lar"][t].view(np.uint32)), t
+        got = np.array([[crc_of_leaf(x, i) for x in leaves] for i in range(N)], np.uint32)
+        assert np.array_equal(got, g["obs_crc"][t]), t
+        for i in range(N):
+            if g["dones"][t, i]:
+                ep = infos[i]["episode"]
+                assert np.float32(ep["r"]) == g["ep_r"][t, i] and ep["l"] == g["ep_l"][t, i], (t, i)
+            else:
+                assert "episode" not in infos[i]
+    assert g["dones"].sum() > 100

@@ -1326,3 +1326,33 @@ def test_lazy_infos_stay_valid_after_later_steps(N):
         assert np.array_equal(r, rb) and np.array_equal(d, db), t      # rewards / dones are private copies
         assert [dict(x) for x in infos] == want, t
     assert sum("episode" in x for w, _, _ in eager for x in w) > N
+
+
+def test_drop_in_under_the_reference_trainer_contract():
+    """INTEGRATION.md section 1's replacement of create_envs, replayed against what the reference's OWN
+    experiments/thor_cached_auxiliary.py produced (tests/golden/trainer_contract.npz: Trainer.create_env -> create_envs
+    -> wrap() run unmodified, deep_rl's wrappers restated): native 174 x 174 frames, 4 envs, 5-tuple observation as
+    float32 CHW / 255 + last_action_reward, TimeLimit 900, set_hardness(0.01) then 0.3.  Every leaf the trainer would
+    receive is bit-identical; Trainer.create_model's reads of the spaces (:55) give the same Model arguments."""
+    g = H.load("trainer_contract")
+    scene = H.trainer_contract_scene(g)
+    goal = tuple(int(v) for v in g["goal"])
+    N = g["actions"].shape[1]
+    world = T.compile_world([scene], T.GYM_GRAPH, tasks=[(0, goal)])
+    starts = np.zeros(g["reset_start"].shape[:2], np.int32)
+    for i in range(N):
+        for k in range(int(g["reset_count"][i])):
+            starts[i, k] = scene.state_index(tuple(int(v) for v in g["reset_start"][i, k]))
+    env = vn.GraphVecEnv(world, num_envs=N, max_episode_steps=int(g["max_episode_steps"]), obs_layout="aux5",
+                         unreal_wrapper=True, scaled_float=True, inject=(g["reset_choice"], starts))
+    env.set_hardness(0.01)                                                  # thor_cached_auxiliary.py:68-70
+    assert env.call_unwrapped("set_complexity", 0.01) == [None] * N
+    # Trainer.create_model (:55): Model(observation_space.spaces[0].spaces[0].shape[0], action_space.n)
+    sp = env.observation_space
+    assert [sp.spaces[0].spaces[0].shape[0], env.action_space.n] == g["model_args"].tolist()
+    assert tuple(sp.spaces[0].spaces[0].shape) == tuple(g["space_leaf_shapes"][0])
+    assert tuple(sp.spaces[1].shape) == tuple(g["space_lar_shape"]) and env.num_envs == N
+    # the reference declares leaves 1.. with its unused screen_size (172); the frames it emits are 174 - ours says 174
+    assert [tuple(b.shape) for b in sp.spaces[0].spaces] == [tuple(s[1:]) for s in g["obs_shapes"]]
+    H.check_trainer_contract_run(g, env, lambda x, i: H.crc(x[i].cpu().numpy()), env.set_hardness)
+    assert env.episode_stats()["episodes"] == g["dones"].sum()

@@ -158,3 +158,31 @@ def test_rollout_oracle_agrees_with_the_torch_formulation():
         ret[:, t] = r[:, t] + 0.99 * ret[:, t + 1] * (1.0 - dn[:, t].float())
     got = orl.nstep_returns(r.numpy(), dn.numpy(), v.numpy(), 0.99)
     np.testing.assert_allclose(got, ret[:, :-1].numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_trainer_contract_oracle_wrapper_stack():
+    """tests/golden/trainer_contract.npz was recorded by running the reference's OWN experiments/thor_cached_auxiliary.py
+    (Trainer.create_env -> create_envs -> wrap(), :50-71) unmodified.  The oracle env under the oracle's restated
+    wrapper stack reproduces it: leaf order, shapes, float32 CHW bytes, last_action_reward, rewards, dones, episodes -
+    and the observation space Trainer.create_model reads (:55), including the 172-vs-174 screen_size quirk (A10)."""
+    from oracle import vec as ovec
+    g = H.load("trainer_contract")
+    scene = H.trainer_contract_scene(g)
+    osc = oenvs.OracleScene(scene)
+    goal = tuple(int(v) for v in g["goal"])
+    N = g["actions"].shape[1]
+
+    def make(i):
+        e = oenvs.GymGraphAuxiliaryEnv(osc, goals=goal, screen_size=(172, 172))      # default_args(), :83
+        e.reset_source = H.StreamSource(g["reset_choice"][i], g["reset_start"][i], g["reset_count"][i])
+        e = ovec.TimeLimitWrapper(e, int(g["max_episode_steps"]))
+        return ovec.UnrealEnvBaseWrapper(ovec.ScaledFloatFrameWrapper(ovec.TransposeImageWrapper(
+            ovec.RewardCollectorWrapper(e))))                                        # wrap(), :59-64
+
+    env = ovec.InProcessVecEnv([(lambda i=i: make(i)) for i in range(N)])
+    env.call_unwrapped("set_complexity", 0.01)                                       # :68-70
+    sp = env.observation_space
+    assert np.array_equal(np.array([b.shape for b in sp.spaces[0].spaces]), g["space_leaf_shapes"])
+    assert tuple(sp.spaces[1].shape) == tuple(g["space_lar_shape"]) and env.action_space.n == int(g["action_n"])
+    assert [sp.spaces[0].spaces[0].shape[0], env.action_space.n] == g["model_args"].tolist()
+    H.check_trainer_contract_run(g, env, lambda x, i: H.crc(x[i]), lambda c: env.call_unwrapped("set_complexity", c))

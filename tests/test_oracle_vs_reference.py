@@ -32,8 +32,9 @@ def test_committed_goldens_reproduce_from_live_reference(tmp_path, capsys):
     mg.gen_maze_render(ref)
     mg.gen_thor_cached(ref)
     mg.gen_aux_target(rh.ref_aux_trainer())
+    mg.gen_trainer_contract(ref)
     names = sorted(f for f in os.listdir(H.GOLDEN) if f.endswith(".npz"))
-    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz")) and len(names) == 9
+    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz")) and len(names) == 10
     for f in names:
         a, b = np.load(os.path.join(H.GOLDEN, f)), np.load(os.path.join(tmp_path, f))
         assert sorted(a.files) == sorted(b.files), f
@@ -102,3 +103,49 @@ def test_loader_consumes_a_reference_pickle(tmp_path):
         assert np.array_equal(small.plane_frames("rgb", [s])[0], rgb)
         assert np.array_equal(small.plane_frames("depth", [s])[0], depth)
         assert np.array_equal(small.plane_frames("segmentation", [s])[0], seg)
+
+
+def test_reference_trainer_accepts_the_drop_in_spaces():
+    """experiments/thor_cached_auxiliary.py imported unmodified: ``Trainer.create_model`` (:54-56) builds the model from
+    ``self.env.observation_space.spaces[0].spaces[0].shape[0]`` and ``self.env.action_space.n``.  With ``self.env`` = the
+    reference's own ``create_envs`` result and with the spaces of the INTEGRATION.md drop-in (GraphVecEnv's
+    ``build_spaces``: aux5, scaled_float, unreal_wrapper) the Model receives the same arguments; ``set_hardness`` is the
+    attribute ``create_envs`` installs (:68-70)."""
+    import importlib
+    from oracle import ref_harness as rh
+    vn = importlib.import_module("a2cat-vn-pytorch_b200")
+    vec_env = importlib.import_module("a2cat-vn-pytorch_b200.vec_env")
+    g = H.load("trainer_contract")
+    scene = H.trainer_contract_scene(g)
+    ref = rh.ref_modules()
+    import io, pickle  # noqa: E401
+    X, Y = scene.maze.shape
+    arrs = {}
+    for plane, c in (("rgb", 3), ("depth", 1), ("segmentation", 3)):
+        a = np.zeros((X, Y, 4, 174, 174, c), np.uint8)
+        a[scene.cells[:, 0], scene.cells[:, 1]] = scene.plane_frames(plane).reshape(scene.n_cells, 4, 174, 174, c)
+        arrs[plane] = a
+    world = ref.thor_world.ThorGridWorld(scene.maze.copy(), arrs["rgb"], arrs["depth"], arrs["segmentation"])
+    world.graph, world.optimal_actions = ref.util.compute_shortest_path_data(scene.maze)
+    calls = []
+    exp = rh.ref_experiment(lambda name: world, calls)
+    trainer = exp.Trainer()
+    goal = tuple(int(v) for v in g["goal"])
+    trainer.env = trainer.create_env(dict(exp.default_args()["env_kwargs"], tasks=[("synthetic-174", [goal])] * 4))
+    trainer.create_model()
+    assert trainer.env.unwrapped_calls == [("set_complexity", (0.01,))]            # create_envs: env.set_hardness(0.01)
+    ref_sp = trainer.env.observation_space
+    # the drop-in's spaces, built without a device
+    w = vn.compile_world([scene], vn.GYM_GRAPH, tasks=[(0, goal)])
+    obs_space, act_space = vec_env.build_spaces(w.layout, "aux5", scaled_float=True, unreal_wrapper=True)
+    trainer.env = type("Env", (), {"observation_space": obs_space, "action_space": act_space})()
+    trainer.create_model()
+    assert calls[0] == calls[1] == ((3, 4), {})
+    assert calls[0][0] == tuple(g["model_args"].tolist())
+    # same nesting, same first leaf (the one the model and _get_input_for_pixel_control use, :47-48,55), same lar Box
+    assert len(obs_space.spaces) == len(ref_sp.spaces) == 2 and len(obs_space.spaces[0].spaces) == len(ref_sp.spaces[0].spaces) == 5
+    assert tuple(obs_space.spaces[0].spaces[0].shape) == tuple(ref_sp.spaces[0].spaces[0].shape) == (3, 174, 174)
+    assert tuple(obs_space.spaces[1].shape) == tuple(ref_sp.spaces[1].shape) == (5,)
+    assert obs_space.spaces[0].spaces[0].dtype == ref_sp.spaces[0].spaces[0].dtype == np.float32
+    # _get_input_for_pixel_control (:47-48) picks inputs[0][0]: the rgb leaf in both layouts
+    assert vec_env.OBS_LAYOUTS["aux5"][0] == "rgb"
