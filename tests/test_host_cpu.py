@@ -160,7 +160,10 @@ def test_library_exports_every_declared_symbol():
     # struct sizes agree with the header (guards the ctypes mirrors)
     assert ctypes.sizeof(L.Store) == 8 + 8 + 4 + 4 + 24 + 24
     assert ctypes.sizeof(L.Rules) == 40 and ctypes.sizeof(L.Inject) == 24
-    assert ctypes.sizeof(L.StepOut) == 8 * (6 + 6 + 15 + 2 + 5)
+    # 12 plane pointers, 12 output pointers + (parity, flags), sched / host_pack / host_seq + (seq, reserved), 5 rollout
+    # record pointers, float_leaves pointer + 4 int32
+    assert ctypes.sizeof(L.StepOut) == 8 * (6 + 6 + 15 + 2 + 5) + 8 + 16
+    assert ctypes.sizeof(L.Replay) == 7 * 8 + 16 and ctypes.sizeof(L.FloatLeaf) == 24
 
 
 def test_product_never_imports_the_oracle():
