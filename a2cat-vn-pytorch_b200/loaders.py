@@ -25,6 +25,52 @@ def _resize_frames(frames, hw):
     return out
 
 
+def skimage_resize_restated(image, out_hw):
+    """``skimage.transform.resize(image, out_hw, anti_aliasing=True)`` as THORDiscreteCachedEnv._preprocess_frame
+    calls it (environments/gym_ai2thor/envs/cached.py:62-64) for a uint8 [H, W, C] frame -> float64 [h, w, C] in [0, 1].
+    PARITY UNPINNED: scikit-image is not installed offline and its version is not pinned by the reference; this
+    restates the published algorithm (skimage 0.15-0.19): img_as_float; when down-scaling, a Gaussian pre-filter with
+    sigma = (scale - 1) / 2 per spatial axis (scipy.ndimage, mode 'mirror', truncate 4); bilinear warp (order 1) with
+    source coordinate (dst + 0.5) * scale - 0.5, out-of-range taps reflected about the edge; clip to the input range."""
+    from scipy import ndimage
+    img = np.asarray(image).astype(np.float64) / 255.0
+    if img.ndim == 2:
+        img = img[:, :, None]
+    H, W = img.shape[:2]
+    h, w = int(out_hw[0]), int(out_hw[1])
+    if (H, W) == (h, w):
+        return img
+    sigma = (max(0.0, (H / h - 1) / 2), max(0.0, (W / w - 1) / 2), 0.0)
+    lo, hi = img.min(), img.max()
+    if sigma[0] > 0 or sigma[1] > 0:
+        img = ndimage.gaussian_filter(img, sigma, cval=0, mode="mirror")
+
+    def taps(n_src, n_dst):
+        c = (np.arange(n_dst, dtype=np.float64) + 0.5) * (n_src / n_dst) - 0.5
+        f, ce = np.floor(c), np.ceil(c)
+        reflect = lambda i: np.where(i < 0, -i - 1, np.where(i >= n_src, 2 * n_src - 1 - i, i)).astype(np.int64)
+        return reflect(f), reflect(ce), c - f
+
+    r0, r1, dr = taps(H, h)
+    c0, c1, dc = taps(W, w)
+    dc_ = dc[None, :, None]
+    top = (1 - dc_) * img[r0][:, c0] + dc_ * img[r0][:, c1]
+    bot = (1 - dc_) * img[r1][:, c0] + dc_ * img[r1][:, c1]
+    dr_ = dr[:, None, None]
+    return np.clip((1 - dr_) * top + dr_ * bot, lo, hi)
+
+
+def _resize_frames_skimage(frames, hw):
+    """[n, H, W, C] uint8 -> [n, h, w, C] uint8: skimage_resize_restated, then the float64 result is stored at uint8
+    precision (rint(x * 255)) - the store holds bytes; the reference would hand the float64 frame to the model."""
+    if tuple(frames.shape[1:3]) == tuple(hw):
+        return np.ascontiguousarray(frames)
+    out = np.empty((frames.shape[0], hw[0], hw[1], frames.shape[3]), np.uint8)
+    for i, f in enumerate(frames):
+        out[i] = np.clip(np.rint(skimage_resize_restated(f, hw) * 255.0), 0, 255).astype(np.uint8)
+    return out
+
+
 def scene_from_thor_grid_world(graph, goals, screen_size=None, planes=("rgb", "depth", "segmentation"), scene_id=0,
                                name="thor"):
     """``graph``: any object with the ThorGridWorld attributes.  Frames are compacted to free cells
@@ -48,21 +94,46 @@ def scene_from_thor_grid_world(graph, goals, screen_size=None, planes=("rgb", "d
 
 
 def scene_from_h5_arrays(graph, observation, shortest_path_distance=None, location=None, goals=(), scene_id=0,
-                         name="thor-h5"):
+                         name="thor-h5", screen_size=None, resize="skimage"):
     """Flat h5 schema -> GridScene.  The grid geometry is recovered from the adjacency: states are
     grouped in fours (one free cell each, graph/util.py:229-237) and laid out on a single row of a
-    [1, cells] maze when no ``location`` is given - the env only ever uses the flat ``graph`` table."""
+    [1, cells] maze when no ``location`` is given - the env only ever uses the flat ``graph`` table.
+    ``screen_size`` other than the stored size resizes every frame ONCE here: ``resize="skimage"`` with the restated
+    anti-aliased filter of THORDiscreteCachedEnv._preprocess_frame (cached.py:62-64; unpinned, see
+    skimage_resize_restated), ``resize="cv2"`` with GraphResize's bilinear cv2.resize (graph/core.py:36-40)."""
     graph = np.asarray(graph)
     S = graph.shape[0]
     assert S % 4 == 0
     cells = S // 4
     obs = np.ascontiguousarray(observation)
+    if screen_size is not None and tuple(screen_size) != tuple(obs.shape[1:3]):
+        obs = (_resize_frames_skimage if resize == "skimage" else _resize_frames)(obs, tuple(screen_size))
     sc = GridScene(np.ones((1, cells), bool), list(goals), True, tuple(obs.shape[1:3]), ("rgb",), scene_id=scene_id,
                    name=name, explicit={"rgb": obs})
     sc.h5_graph = graph.astype(np.int32)         # used verbatim by tables.compile_world for THOR_CACHED
     # start-state candidates of a goal g are {s : shortest_path_distance[s][g] > 0} (cached.py:41-44)
     sc.h5_spd = None if shortest_path_distance is None else np.asarray(shortest_path_distance)
     return sc
+
+
+def load_scene_h5(path, goals=(), screen_size=None, resize="skimage", scene_id=0):
+    """Reads a scene file written by ``save_graph_as_h5`` (graph/util.py:202-247) the way
+    ``THORDiscreteCachedEnv.__init__`` does (cached.py:26-32: datasets ``graph``, ``observation``,
+    ``shortest_path_distance`` fully loaded with ``[()]``; ``location`` and ``resnet_feature`` are not used by the
+    env) and returns the GridScene for ``compile_world([...], THOR_CACHED, tasks=[(0, goal_state), ...])``.
+    h5py is an optional dependency (absent from the offline image): without it this raises ImportError naming
+    ``scene_from_h5_arrays`` as the way in for arrays obtained otherwise."""
+    try:
+        import h5py
+    except ImportError as e:        # pragma: no cover - exercised with a stand-in module in the tests
+        raise ImportError("load_scene_h5 needs h5py (not installed); load the datasets 'graph', 'observation', "
+                          "'shortest_path_distance' yourself and call loaders.scene_from_h5_arrays") from e
+    with h5py.File(path, "r") as f:
+        graph = f["graph"][()]
+        observation = f["observation"][()]
+        spd = f["shortest_path_distance"][()]
+    return scene_from_h5_arrays(graph, observation, spd, goals=goals, scene_id=scene_id, name=str(path),
+                                screen_size=screen_size, resize=resize)
 
 
 # --------------------------------------------------------------------------- scene pickles without the reference tree

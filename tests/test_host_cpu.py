@@ -290,3 +290,80 @@ def test_scene_pickle_loads_without_the_reference_package(tmp_path):
     assert vn.loaders.THOR_CACHED_GOALS["thor-cached-225"][0] == (3, 17, 2)
     with pytest.raises(ValueError):
         vn.loaders.make_vec("NoSuchEnv-v0", [])
+
+
+def test_h5_scene_file_reader_with_optional_h5py(monkeypatch, tmp_path):
+    """loaders.load_scene_h5 reads the datasets THORDiscreteCachedEnv loads (cached.py:26-32) through h5py when it is
+    installed; offline it is not, so a stand-in module serves a registry of arrays (the same one the reference harness
+    uses) - and without any h5py the loader raises ImportError pointing at scene_from_h5_arrays."""
+    import sys
+    import types
+    loaders = importlib.import_module("a2cat-vn-pytorch_b200.loaders")
+    T = vn.tables
+    rng = np.random.RandomState(3)
+    scene = H.scenes.make_maze_scene((5, 6), 0.2, 2, n_goals=1, planes=("rgb",))
+    w = T.compile_world([scene], T.GYM_GRAPH)
+    graph = T.build_adjacency(scene, "h5")
+    obs = scene.plane_frames("rgb")
+    spd = rng.randint(0, 9, (scene.n_states, scene.n_states)).astype(np.int64)
+    files = {"scene.h5": {"graph": graph, "observation": obs, "shortest_path_distance": spd}}
+
+    class _DS:
+        def __init__(self, a):
+            self.a = a
+
+        def __getitem__(self, k):
+            assert k == ()
+            return self.a
+
+    class _File:
+        def __init__(self, path, mode="r"):
+            self.d = files[os.path.basename(str(path))]
+
+        def __getitem__(self, k):
+            return _DS(self.d[k])
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    monkeypatch.setitem(sys.modules, "h5py", None)               # import h5py -> ImportError
+    with pytest.raises(ImportError, match="scene_from_h5_arrays"):
+        loaders.load_scene_h5(tmp_path / "scene.h5")
+    fake = types.ModuleType("h5py")
+    fake.File = _File
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    sc = loaders.load_scene_h5(tmp_path / "scene.h5")
+    ref = loaders.scene_from_h5_arrays(graph, obs, spd)
+    assert np.array_equal(sc.h5_graph, ref.h5_graph) and np.array_equal(sc.h5_spd, spd)
+    assert np.array_equal(sc.plane_frames("rgb"), obs) and sc.frame_hw == (84, 84)
+    wc = T.compile_world([sc], T.THOR_CACHED, tasks=[(0, 5)])
+    assert np.array_equal(wc.adj, graph) and w.n_states == wc.n_states
+    small = loaders.load_scene_h5(tmp_path / "scene.h5", screen_size=(42, 42))
+    assert small.frame_hw == (42, 42) and small.plane_frames("rgb").shape == (scene.n_states, 42, 42, 3)
+
+
+def test_skimage_resize_restatement_properties():
+    """skimage.transform.resize(anti_aliasing=True) (cached.py:62-64) restated - UNPINNED (scikit-image is absent).  What
+    can be checked without it: same size is a plain / 255; constants stay constant; up-scaling (no pre-filter) is the
+    half-pixel-centred bilinear interpolation cv2 implements too; an integer down-scale equals Gaussian(sigma =
+    (s - 1) / 2, mirror) followed by sampling the filtered image between the two centre taps."""
+    import cv2
+    from scipy import ndimage
+    loaders = importlib.import_module("a2cat-vn-pytorch_b200.loaders")
+    rz = loaders.skimage_resize_restated
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (30, 40, 3)).astype(np.uint8)
+    assert np.array_equal(rz(img, (30, 40)), img.astype(np.float64) / 255.0)
+    assert np.abs(rz(np.full((20, 24, 3), 77, np.uint8), (7, 9)) - 77 / 255.0).max() < 1e-15
+    up = rz(img, (75, 100))
+    want = cv2.resize(img.astype(np.float64) / 255.0, (100, 75), interpolation=cv2.INTER_LINEAR)
+    assert np.abs(up - want).max() < 1e-12
+    down = rz(img, (15, 20))                                   # factor 2 on both axes: sigma 0.5
+    f = ndimage.gaussian_filter(img.astype(np.float64) / 255.0, (0.5, 0.5, 0), mode="mirror")
+    want = 0.25 * (f[0::2, 0::2] + f[1::2, 0::2] + f[0::2, 1::2] + f[1::2, 1::2])      # source coordinate 2 i + 0.5
+    assert np.abs(down - want).max() < 1e-12
+    q = loaders._resize_frames_skimage(img[None], (15, 20))
+    assert q.dtype == np.uint8 and np.abs(q[0] / 255.0 - down).max() <= 0.5 / 255 + 1e-12
