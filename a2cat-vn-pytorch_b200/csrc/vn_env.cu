@@ -1090,20 +1090,21 @@ static StepMode choose_mode(const vn_store_t *store, const vn_envs_t *envs, cons
         return kModeFused;
     }
     if (variant == VN_GATHER_AUTO) {
-        // Measured on B200 (profiles/r2a_launch_modes.txt, C2 records, device-resident loop): the persistent launch wins
-        // while every CTA owns at most two envs (512 envs 9.5 -> 7.0 us per step, 1,024: 10.7 -> 9.9, 2,048: 17.7 -> 17.4)
-        // - there the step is bound by launches and dependency hops.  Beyond that the two-kernel path wins (4,096: 34.6
-        // vs 35.8 us; 16,384: 120 vs 137 us): its scalar kernel hides behind the previous gather and its tickets balance
-        // the copies, while the persistent launch exposes its stepping phase and owns envs statically.  A HOST caller
-        // (out->host_pack) always takes two kernels: the stepping phase of a persistent grid cannot become resident
-        // before the previous launch's CTAs release their shared memory, so the host would get its rewards a whole gather
-        // late, and lanes that own strided envs read / write the mapped host buffers 4 bytes at a time.
+        // Measured on B200 (profiles/r2a_launch_modes.txt, r2c_small_batches.txt; C2 records, device-resident loop): the
+        // persistent launch wins while the batch fills at most ~3/4 of one wave of its CTAs (300 envs 9.3 -> 6.8 us per
+        // step, 512: 9.1 -> 7.1, 768: 9.2 -> 9.0) - there the step is bound by launches and dependency hops.  Beyond that
+        // the two-kernel path wins (1,024: 9.5 vs 9.9 us; 4,096: 33.3 vs 35.8; 16,384: 120 vs 137): its scalar kernel
+        // hides behind the previous gather and its tickets balance the copies, while the persistent launch exposes its
+        // stepping phase and owns envs statically.  A HOST caller (out->host_pack) always takes two kernels: the stepping
+        // phase of a persistent grid cannot become resident before the previous launch's CTAs release their shared
+        // memory, so the host would get its rewards a whole gather late, and lanes that own strided envs read / write
+        // the mapped host buffers 4 bytes at a time.
         // VN_PERSISTENT=0 / 2 (development): never / whenever the batch qualifies.
         static const int env_persistent = getenv("VN_PERSISTENT") ? atoi(getenv("VN_PERSISTENT")) : VN_PERSISTENT_DEFAULT;
         const int32_t ps = env_persistent ? persistent_smem_bytes(store, out) : 0;
         if (ps > 0) {
             const int per_sm = max(1, min(32, (220 * 1024) / (ps + 1024)));
-            const bool mid_size = !out->host_pack && envs->n_envs <= 2 * sm_count() * per_sm;
+            const bool mid_size = !out->host_pack && 4 * (int64_t)envs->n_envs <= 3 * (int64_t)sm_count() * per_sm;
             if (env_persistent >= 2 || mid_size) {
                 *smem = ps;
                 return kModePersistent;

@@ -18,10 +18,35 @@
 
 namespace vn {
 
+// Programmatic dependent launch inside a builder CHAIN (several kernels enqueued by one C call): every kernel waits for
+// its predecessor's memory before touching data; a kernel whose successor is the next kernel of the SAME chain lets it
+// be scheduled early (its launch latency and prologue then overlap this kernel).  The LAST kernel of a call never
+// releases early: what follows it in the stream is unknown (a step kernel that rewrites the rollout rows just read).
+__device__ __forceinline__ void chain_wait(int release_successor) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (release_successor) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // =====================================================================================================
 // n-step returns: one thread per env, serial backward recurrence over T (parallel across envs)
 // =====================================================================================================
-__global__ void __launch_bounds__(256) vn_nstep_returns_kernel(const float *__restrict__ reward,
+__global__ void __launch_bounds__(64) vn_nstep_returns_kernel(const float *__restrict__ reward,
                                                                const uint8_t *__restrict__ done,
                                                                const float *__restrict__ last_value, float gamma, int n,
                                                                int t, int64_t stride_n, int64_t stride_t,
@@ -195,8 +220,9 @@ __global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_sto
                                                                     int64_t sn, int64_t st, PoolGeom g,
                                                                     const int32_t *__restrict__ pos,
                                                                     const int32_t *__restrict__ count, int max_count,
-                                                                    int compact, float *__restrict__ out) {
+                                                                    int compact, float *__restrict__ out, int chained) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
+    chain_wait(chained);
     const int fbytes = g.h * g.w * g.c;
     uint8_t *frame0 = smem_raw;
     uint8_t *frame1 = frame0 + ((fbytes + 15) & ~15);
@@ -224,7 +250,8 @@ __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *
                                                                  int64_t sn, int64_t st,
                                                                  int32_t *__restrict__ rows,
                                                                  int32_t *__restrict__ miss_pos,
-                                                                 int32_t *__restrict__ miss_count) {
+                                                                 int32_t *__restrict__ miss_count, int chained) {
+    chain_wait(chained);
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool miss = false;
     if (p < (int64_t)n * t) {
@@ -487,8 +514,11 @@ __global__ void __launch_bounds__(256) vn_pc_returns_kernel(const float4 *__rest
                                                             const uint8_t *__restrict__ done, int64_t dsn, int64_t dst,
                                                             const float4 *__restrict__ bootstrap, float gamma, int n,
                                                             int t, int d4, float4 *__restrict__ out,
-                                                            float4 *__restrict__ out_reward) {
+                                                            float4 *__restrict__ out_reward, int32_t *reset_counter) {
+    chain_wait(0);
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // the miss counter of the chain (read by the list kernel, which has completed) is re-armed for the next call
+    if (gid == 0 && reset_counter) *reset_counter = 0;
     if (gid >= (int64_t)n * d4) return;
     const int i = (int)(gid / d4), f = (int)(gid - (int64_t)i * d4);
     float4 ret = bootstrap[(int64_t)i * d4 + f];
@@ -540,6 +570,7 @@ __global__ void __launch_bounds__(kRpBlock) vn_rp_count_kernel(const float *__re
                                                                int64_t sn, int64_t st, int8_t *__restrict__ labels,
                                                                int32_t *__restrict__ block_counts) {
     __shared__ int warp_nz[kRpBlock / 32];
+    chain_wait(1);   // always followed by the scan or scatter kernel of the same call
     const int i = blockIdx.x * kRpBlock + threadIdx.x;
     const float r = i < n ? rp_reward(reward, i, t, sn, st) : 0.f;
     const bool nz = i < n && r != 0.f;
@@ -559,6 +590,7 @@ __global__ void __launch_bounds__(1024) vn_rp_scan_kernel(int32_t *__restrict__ 
                                                           int32_t *__restrict__ counts) {
     __shared__ int warp_tot[32];
     __shared__ int carry;
+    chain_wait(0);
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -595,22 +627,46 @@ __global__ void __launch_bounds__(1024) vn_rp_scan_kernel(int32_t *__restrict__ 
     }
 }
 
+// scanned != 0: block_offsets holds the exclusive scan of the per-block counts (vn_rp_scan_kernel ran).  scanned == 0
+// (few blocks): it still holds the raw counts and every block sums the counts of the blocks before it itself - one
+// launch less; the last block also writes the two totals.
 __global__ void __launch_bounds__(kRpBlock) vn_rp_scatter_kernel(const float *__restrict__ reward, int n, int t,
                                                                  int64_t sn, int64_t st,
-                                                                 const int32_t *__restrict__ block_offsets,
+                                                                 const int32_t *__restrict__ block_offsets, int scanned,
+                                                                 int32_t *__restrict__ counts,
                                                                  int32_t *__restrict__ zero_idx,
                                                                  int32_t *__restrict__ nonzero_idx) {
     __shared__ int warp_nz[kRpBlock / 32];
+    __shared__ int s_offset;
+    chain_wait(0);
     const int i = blockIdx.x * kRpBlock + threadIdx.x;
     const bool valid = i < n;
     const bool nz = valid && rp_reward(reward, i, t, sn, st) != 0.f;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned b = __ballot_sync(0xffffffffu, nz);
     if (lane == 0) warp_nz[wid] = __popc(b);
+    if (wid == 0) {
+        int off;
+        if (scanned) {
+            off = block_offsets[blockIdx.x];
+        } else {
+            off = 0;
+            for (int k = lane; k < (int)blockIdx.x; k += 32) off += block_offsets[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+        }
+        if (lane == 0) s_offset = off;
+    }
     __syncthreads();
+    if (!scanned && counts && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const int total_nz = s_offset + block_offsets[blockIdx.x];
+        counts[1] = total_nz;
+        counts[0] = n - total_nz;
+    }
+    if (!zero_idx && !nonzero_idx) return;
     int before = 0;  // non-zeros in earlier warps of this block
     for (int k = 0; k < wid; ++k) before += warp_nz[k];
-    const int nz_rank = block_offsets[blockIdx.x] + before + __popc(b & ((1u << lane) - 1u));
+    const int nz_rank = s_offset + before + __popc(b & ((1u << lane) - 1u));
     if (!valid) return;
     if (nz) {
         if (nonzero_idx) nonzero_idx[nz_rank] = i;
@@ -722,6 +778,20 @@ static int32_t pool_geom(int h, int w, int c, int cell, int out_h, int out_w, Po
     return VN_OK;
 }
 
+// The list kernel loops over a device-resident list that is almost always short (episode resets: ~0.1 % of the
+// transitions): two CTAs per SM are plenty, and a grid sized from max_count (all transitions) only paid for launching
+// hundreds of large-shared-memory CTAs that found nothing to do (14 us per call at C2's size).
+static int32_t launch_pc_list(const vn_store_t *store, int plane, const int32_t *states, int t, int64_t sn, int64_t st,
+                              const PoolGeom &g, const int32_t *pos, const int32_t *count, int max_count, int compact,
+                              float *out, int smem, int per_sm, cudaStream_t stream, bool chained) {
+    VN_ENSURE_SMEM(vn_pixel_control_list_kernel, smem);
+    const int want = sm_count() * (per_sm < 2 ? per_sm : 2);
+    const int grid = max_count < want ? max_count : want;
+    launch_chain(vn_pixel_control_list_kernel, dim3(grid), dim3(256), (size_t)smem, stream, *store, plane, states, t, sn,
+                 st, g, pos, count, max_count, compact, out, chained ? 1 : 0);
+    return check_launch("vn_pixel_control_list_kernel");
+}
+
 }  // namespace vn
 
 extern "C" {
@@ -732,7 +802,8 @@ int32_t vn_nstep_returns(const float *reward, const uint8_t *done, const float *
     VN_REQUIRE(reward && done && last_value && out, "nstep_returns: null pointer");
     VN_REQUIRE(n >= 0 && t >= 1, "nstep_returns: n=%d t=%d", n, t);
     if (n == 0) return VN_OK;
-    vn::vn_nstep_returns_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    // 64-thread blocks: 4,096 envs spread over 64 SMs instead of 16 (the loop over T is a chain of dependent FMAs)
+    vn::vn_nstep_returns_kernel<<<(n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(
         reward, done, last_value, gamma, n, t, stride_n, stride_t, out, out_stride_n, out_stride_t);
     return vn::check_launch("vn_nstep_returns_kernel");
 }
@@ -778,7 +849,7 @@ int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int
     vn::vn_pc_returns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4 *>(pc_table), rows, reinterpret_cast<const float4 *>(miss_rows), done,
         done_stride_n, done_stride_t, reinterpret_cast<const float4 *>(bootstrap), gamma, n, t, d4,
-        reinterpret_cast<float4 *>(out_returns), reinterpret_cast<float4 *>(out_reward));
+        reinterpret_cast<float4 *>(out_returns), reinterpret_cast<float4 *>(out_reward), nullptr);
     return vn::check_launch("vn_pc_returns_kernel");
 }
 
@@ -792,6 +863,58 @@ static int32_t check_plane(const vn_store_t *store, int32_t plane, int h, int w,
                    (store->plane_off[plane] & 15) == 0,
                "%s: store is not 16-byte aligned", who);
     return VN_OK;
+}
+
+static int32_t check_plane(const vn_store_t *store, int32_t plane, int h, int w, int c, const char *who);
+
+int32_t vn_pixel_control_returns_from_states(const vn_store_t *store, int32_t plane, const int32_t *adj,
+                                             const float *pc_table, const int32_t *states, int64_t state_stride_n,
+                                             int64_t state_stride_t, const uint8_t *done, int64_t done_stride_n,
+                                             int64_t done_stride_t, const float *bootstrap, float gamma, int32_t n,
+                                             int32_t t, int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h,
+                                             int32_t out_w, int32_t *rows, int32_t *miss_pos, int32_t *miss_count,
+                                             float *miss_rows, int32_t max_miss, float *out_returns, float *out_reward,
+                                             void *stream) {
+    int32_t rc = check_plane(store, plane, h, w, c, "pixel_control_returns");
+    if (rc) return rc;
+    const int32_t cells = out_h * out_w;
+    VN_REQUIRE(adj && pc_table && states && done && bootstrap && rows && miss_pos && miss_count && miss_rows && out_returns,
+               "pixel_control_returns: null pointer");
+    VN_REQUIRE(n >= 0 && t >= 1 && cells >= 4 && (cells & 3) == 0 && max_miss >= 1,
+               "pixel_control_returns: n=%d t=%d cells=%d max_miss=%d", n, t, cells, max_miss);
+    VN_REQUIRE((reinterpret_cast<uintptr_t>(adj) & 15) == 0, "pixel_control_returns: adj must be 16-byte aligned");
+    VN_REQUIRE(((reinterpret_cast<uintptr_t>(pc_table) | reinterpret_cast<uintptr_t>(miss_rows) |
+                 reinterpret_cast<uintptr_t>(bootstrap) | reinterpret_cast<uintptr_t>(out_returns) |
+                 reinterpret_cast<uintptr_t>(out_reward)) & 15) == 0,
+               "pixel_control_returns: arrays must be 16-byte aligned");
+    vn::PoolGeom g;
+    rc = vn::pool_geom(h, w, c, cell, out_h, out_w, &g);
+    if (rc) return rc;
+    if (n == 0) return VN_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // (1) table row of every transition; the misses (episode resets) go to a list.  *miss_count must be 0 on entry:
+    //     zero it once when the scratch is allocated - kernel (3) re-arms it for the next call
+    const int64_t total = (int64_t)n * t;
+    vn::launch_chain(vn::vn_transition_rows_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, adj, states, n,
+                     t, state_stride_n, state_stride_t, rows, miss_pos, miss_count, 1);
+    rc = vn::check_launch("vn_transition_rows_kernel");
+    if (rc) return rc;
+    // (2) the misses computed directly from their two frames into the compact side buffer
+    const int fb = (h * w * c + 15) & ~15;
+    const int smem = 2 * fb;
+    VN_REQUIRE(smem <= 220 * 1024, "pixel_control_returns: frame too large for shared memory");
+    const int per_sm = (220 * 1024) / (smem + 1024) < 1 ? 1 : (220 * 1024) / (smem + 1024);
+    rc = vn::launch_pc_list(store, plane, states, t, state_stride_n, state_stride_t, g, miss_pos, miss_count, max_miss, 1,
+                            miss_rows, smem, per_sm, st, true);
+    if (rc) return rc;
+    // (3) rewards gathered on the fly + discounted back-up
+    const int d4 = cells >> 2;
+    const int64_t threads = (int64_t)n * d4;
+    vn::launch_chain(vn::vn_pc_returns_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st,
+                     reinterpret_cast<const float4 *>(pc_table), rows, reinterpret_cast<const float4 *>(miss_rows), done,
+                     done_stride_n, done_stride_t, reinterpret_cast<const float4 *>(bootstrap), gamma, n, t, d4,
+                     reinterpret_cast<float4 *>(out_returns), reinterpret_cast<float4 *>(out_reward), miss_count);
+    return vn::check_launch("vn_pc_returns_kernel");
 }
 
 int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
@@ -827,7 +950,7 @@ int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n,
     cudaMemsetAsync(miss_count, 0, sizeof(int32_t), st);
     const int64_t total = (int64_t)n * t;
     vn::vn_transition_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        adj, states, n, t, state_stride_n, state_stride_t, rows, miss_pos, miss_count);
+        adj, states, n, t, state_stride_n, state_stride_t, rows, miss_pos, miss_count, 0);
     return vn::check_launch("vn_transition_rows_kernel");
 }
 
@@ -863,10 +986,8 @@ int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int3
     VN_REQUIRE(smem <= 220 * 1024, "pixel_control_list: frame too large for shared memory");
     VN_ENSURE_SMEM(vn::vn_pixel_control_list_kernel, smem);
     const int per_sm = (220 * 1024) / (smem + 1024) < 8 ? ((220 * 1024) / (smem + 1024) < 1 ? 1 : (220 * 1024) / (smem + 1024)) : 8;
-    const int grid = max_count < vn::sm_count() * per_sm ? max_count : vn::sm_count() * per_sm;
-    vn::vn_pixel_control_list_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        *store, plane, states, t, state_stride_n, state_stride_t, g, pos, count, max_count, compact, out);
-    return vn::check_launch("vn_pixel_control_list_kernel");
+    return vn::launch_pc_list(store, plane, states, t, state_stride_n, state_stride_t, g, pos, count, max_count, compact, out,
+                              smem, per_sm, static_cast<cudaStream_t>(stream), false);
 }
 
 int32_t vn_replay_sample(const vn_replay_t *ring, int32_t length, int32_t mode, uint64_t seed, uint32_t call,
@@ -1044,13 +1165,20 @@ int32_t vn_rp_labels(const float *reward, int32_t n, int32_t t, int64_t stride_n
     if (n == 0) return VN_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int blocks = (n + vn::kRpBlock - 1) / vn::kRpBlock;
-    vn::vn_rp_count_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, t, stride_n, stride_t, labels, scratch);
+    vn::launch_chain(vn::vn_rp_count_kernel, dim3(blocks), dim3(vn::kRpBlock), 0, st, reward, n, t, stride_n, stride_t,
+                     labels, scratch);
     vn::check_launch("vn_rp_count_kernel");
-    vn::vn_rp_scan_kernel<<<1, 1024, 0, st>>>(scratch, blocks, n, counts);
+    if (blocks <= 256) {
+        // few blocks (an A2C rollout: 80 blocks at 4,096 envs x 20 steps): no separate scan launch
+        vn::launch_chain(vn::vn_rp_scatter_kernel, dim3(blocks), dim3(vn::kRpBlock), 0, st, reward, n, t, stride_n,
+                         stride_t, scratch, 0, counts, zero_idx, nonzero_idx);
+        return vn::check_launch("vn_rp_scatter_kernel");
+    }
+    vn::launch_chain(vn::vn_rp_scan_kernel, dim3(1), dim3(1024), 0, st, scratch, blocks, n, counts);
     vn::check_launch("vn_rp_scan_kernel");
     if (zero_idx || nonzero_idx)
-        vn::vn_rp_scatter_kernel<<<blocks, vn::kRpBlock, 0, st>>>(reward, n, t, stride_n, stride_t, scratch, zero_idx,
-                                                                  nonzero_idx);
+        vn::launch_chain(vn::vn_rp_scatter_kernel, dim3(blocks), dim3(vn::kRpBlock), 0, st, reward, n, t, stride_n,
+                         stride_t, scratch, 1, (int32_t *)nullptr, zero_idx, nonzero_idx);
     return vn::check_launch("vn_rp_labels");
 }
 

@@ -145,13 +145,17 @@ class TargetTables:
             self._aux[plane] = _aux_direct(self.dw, me, plane, self.cell, self.out_hw).contiguous()
         return self._aux[plane]
 
-    def scratch(self, n):
-        """(rows, miss_pos, miss_count) int32 scratch for n transitions, reused between calls on the same stream."""
-        if n not in self._scratch:
+    def scratch(self, n, chained=False):
+        """(rows, miss_pos, miss_count) int32 scratch for n transitions, reused between calls on the same stream.
+        The chained call (vn_pixel_control_returns_from_states) owns its own set: its miss_count starts at zero and is
+        re-armed by the call's last kernel, while vn_transition_rows on its own zeroes the counter it is given."""
+        key = (n, chained)
+        if key not in self._scratch:
             dev = self.dw.device
-            self._scratch = {n: (torch.empty(n, dtype=torch.int32, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
-                                 torch.empty(1, dtype=torch.int32, device=dev))}
-        return self._scratch[n]
+            self._scratch[key] = (torch.empty(n, dtype=torch.int32, device=dev),
+                                  torch.empty(n, dtype=torch.int32, device=dev),
+                                  torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._scratch[key]
 
     def nbytes(self):
         return self.pc.numel() * 4 + sum(t.numel() * 4 for t in self._aux.values())
@@ -219,7 +223,7 @@ def pixel_control_returns(dw: DeviceWorld, states, dones, bootstrap, gamma, cell
     bootstrap = bootstrap.reshape(b, cells).contiguous().float()
     out = torch.empty((b, t, cells), dtype=torch.float32, device=dw.device)
     rew = torch.empty((b, t, cells), dtype=torch.float32, device=dw.device) if with_reward else None
-    rows, miss_pos, miss_count = tab.scratch(b * t)
+    rows, miss_pos, miss_count = tab.scratch(b * t, chained=True)
     max_miss = b * t if max_miss is None else int(max_miss)
     key = ("miss", max_miss, cells)
     side = tab._aux.get(key)
@@ -227,14 +231,12 @@ def pixel_control_returns(dw: DeviceWorld, states, dones, bootstrap, gamma, cell
         side = tab._aux[key] = torch.empty((max(max_miss, 1), cells), dtype=torch.float32, device=dw.device)
     sn, st_ = states.stride()
     with torch.cuda.device(dw.device):
-        st = _stream(states)
-        L.check(lib.vn_transition_rows(dw.adj.data_ptr(), states.data_ptr(), b, t, sn, st_, rows.data_ptr(),
-                                       miss_pos.data_ptr(), miss_count.data_ptr(), st))
-        L.check(lib.vn_pixel_control_list(C.byref(dw.store), pi, states.data_ptr(), b, t, sn, st_, h, w, c, cell_size, oh,
-                                          ow, miss_pos.data_ptr(), miss_count.data_ptr(), max_miss, 1, side.data_ptr(), st))
-        L.check(lib.vn_pixel_control_returns(tab.pc.data_ptr(), cells, rows.data_ptr(), side.data_ptr(), dones.data_ptr(),
-                                             dones.stride(0), dones.stride(1), bootstrap.data_ptr(), float(gamma), b, t,
-                                             out.data_ptr(), L.ptr(rew), st))
+        # one C call, three chained kernels: transition rows -> misses computed directly -> gather + back-up
+        L.check(lib.vn_pixel_control_returns_from_states(
+            C.byref(dw.store), pi, dw.adj.data_ptr(), tab.pc.data_ptr(), states.data_ptr(), sn, st_, dones.data_ptr(),
+            dones.stride(0), dones.stride(1), bootstrap.data_ptr(), float(gamma), b, t, h, w, c, cell_size, oh, ow,
+            rows.data_ptr(), miss_pos.data_ptr(), miss_count.data_ptr(), side.data_ptr(), max(max_miss, 1),
+            out.data_ptr(), L.ptr(rew), _stream(states)))
     return (out, rew) if with_reward else out
 
 

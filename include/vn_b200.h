@@ -389,6 +389,18 @@ int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int
                                  const uint8_t *done, int64_t done_stride_n, int64_t done_stride_t,
                                  const float *bootstrap, float gamma, int32_t n, int32_t t, float *out_returns,
                                  float *out_reward, void *stream);
+/* The three steps above as ONE call for a rollout's states: vn_transition_rows, vn_pixel_control_list (compact, into
+ * miss_rows [max_miss][cells]) and vn_pixel_control_returns, chained with programmatic dependent launches (each kernel's
+ * launch latency hides behind its predecessor).  rows / miss_pos are int32 scratch of n * t entries; *miss_count must be
+ * 0 on entry - zero it once when the scratch is allocated, the last kernel re-arms it for the next call. */
+int32_t vn_pixel_control_returns_from_states(const vn_store_t *store, int32_t plane, const int32_t *adj,
+                                             const float *pc_table, const int32_t *states, int64_t state_stride_n,
+                                             int64_t state_stride_t, const uint8_t *done, int64_t done_stride_n,
+                                             int64_t done_stride_t, const float *bootstrap, float gamma, int32_t n,
+                                             int32_t t, int32_t h, int32_t w, int32_t c, int32_t cell, int32_t out_h,
+                                             int32_t out_w, int32_t *rows, int32_t *miss_pos, int32_t *miss_count,
+                                             float *miss_rows, int32_t max_miss, float *out_returns, float *out_reward,
+                                             void *stream);
 
 /* Device-side UNREAL experience replay (deep_rl's replay behind `self.replay.sample_sequence()`,
  * experiments/ai2_auxiliary/trainer.py:29, and sample_rp_sequence).
