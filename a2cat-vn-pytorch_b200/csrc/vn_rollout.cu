@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) vn_pixel_control_kernel(const vn_store_t 
 // Direct pixel-control reward for a device-resident LIST of transitions (the reset transitions that the
 // per-scene transition table cannot serve).  Persistent CTAs loop over the list; its length is read from
 // device memory, so no host synchronisation is needed between the lookup pass and this one.
-__global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_store_t store, int plane,
+__global__ void __launch_bounds__(512) vn_pixel_control_list_kernel(const vn_store_t store, int plane,
                                                                     const int32_t *__restrict__ states, int t,
                                                                     int64_t sn, int64_t st, PoolGeom g,
                                                                     const int32_t *__restrict__ pos,
@@ -245,17 +245,30 @@ __global__ void __launch_bounds__(256) vn_pixel_control_list_kernel(const vn_sto
 
 // rows[n][k] = pixel-control table row of transition states[n][k] -> states[n][k+1]
 constexpr int kRowZero = -1, kRowMiss = -2;   // a miss is stored as -(2 + m), m = its index in the miss list
+// Thread q handles transition (env, k).  The thread order follows the faster axis of `states` so that a warp reads
+// consecutive addresses: time-major storage (st > sn: rollout buffers) -> env fastest, batch-major -> k fastest.  The
+// row index of (env, k) is written to rows[env * rsn + k * rst] (the caller picks the matching scratch layout).
 __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *__restrict__ adj,
                                                                  const int32_t *__restrict__ states, int n, int t,
-                                                                 int64_t sn, int64_t st,
+                                                                 int64_t sn, int64_t st, int64_t rsn, int64_t rst,
                                                                  int32_t *__restrict__ rows,
                                                                  int32_t *__restrict__ miss_pos,
                                                                  int32_t *__restrict__ miss_count, int chained) {
     chain_wait(chained);
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool miss = false;
-    if (p < (int64_t)n * t) {
-        const int env = (int)(p / t), k = (int)(p - (int64_t)env * t);
+    int64_t p = 0, at = 0;
+    if (q < (int64_t)n * t) {
+        int env, k;
+        if (st > sn) {
+            k = (int)(q / n);
+            env = (int)(q - (int64_t)k * n);
+        } else {
+            env = (int)(q / t);
+            k = (int)(q - (int64_t)env * t);
+        }
+        p = (int64_t)env * t + k;          // batch-major position: what the miss list and the outputs are indexed by
+        at = (int64_t)env * rsn + (int64_t)k * rst;
         const int s = states[(int64_t)env * sn + (int64_t)k * st], s2 = states[(int64_t)env * sn + (int64_t)(k + 1) * st];
         int row = kRowMiss;
         if (s2 == s) {
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *
             else if (nb.w == s2)
                 row = s * 4 + 3;
         }
-        if (row != kRowMiss) rows[p] = row;
+        if (row != kRowMiss) rows[at] = row;
         miss = row == kRowMiss;
     }
     // warp-aggregated append of the misses (ballot + one atomic per warp)
@@ -284,7 +297,7 @@ __global__ void __launch_bounds__(256) vn_transition_rows_kernel(const int32_t *
         if (miss) {
             const int m = base + __popc(b & ((1u << lane) - 1u));
             miss_pos[m] = (int32_t)p;
-            rows[p] = kRowMiss - m;
+            rows[at] = kRowMiss - m;
         }
     }
 }
@@ -509,7 +522,7 @@ __global__ void __launch_bounds__(256) vn_gather_leaves_f32_kernel(const FloatLe
 // The rewards are never written to memory unless out_reward is given: 1,600 B read + 1,600 B written per transition
 // instead of twice that for gather + back-up.
 __global__ void __launch_bounds__(256) vn_pc_returns_kernel(const float4 *__restrict__ table,
-                                                            const int32_t *__restrict__ rows,
+                                                            const int32_t *__restrict__ rows, int64_t rsn, int64_t rst,
                                                             const float4 *__restrict__ miss_rows,
                                                             const uint8_t *__restrict__ done, int64_t dsn, int64_t dst,
                                                             const float4 *__restrict__ bootstrap, float gamma, int n,
@@ -532,7 +545,7 @@ __global__ void __launch_bounds__(256) vn_pc_returns_kernel(const float4 *__rest
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             nd[u] = 0.f;
             if (k >= 0) {
-                const int r = __ldg(rows + (int64_t)i * t + k);
+                const int r = __ldg(rows + (int64_t)i * rsn + (int64_t)k * rst);
                 if (r >= 0)
                     v[u] = __ldg(table + (int64_t)r * d4 + f);
                 else if (r <= kRowMiss)
@@ -778,16 +791,16 @@ static int32_t pool_geom(int h, int w, int c, int cell, int out_h, int out_w, Po
     return VN_OK;
 }
 
-// The list kernel loops over a device-resident list that is almost always short (episode resets: ~0.1 % of the
-// transitions): two CTAs per SM are plenty, and a grid sized from max_count (all transitions) only paid for launching
-// hundreds of large-shared-memory CTAs that found nothing to do (14 us per call at C2's size).
+// The list kernel loops over a device-resident list (episode resets: ~0.1 % of an A2C rollout's transitions, ~2 % at
+// C5's short episodes).  512 threads: one per output cell (20 x 20) in a single round - the kernel sits on the critical
+// path between the row lookup and the back-up.
 static int32_t launch_pc_list(const vn_store_t *store, int plane, const int32_t *states, int t, int64_t sn, int64_t st,
                               const PoolGeom &g, const int32_t *pos, const int32_t *count, int max_count, int compact,
                               float *out, int smem, int per_sm, cudaStream_t stream, bool chained) {
     VN_ENSURE_SMEM(vn_pixel_control_list_kernel, smem);
-    const int want = sm_count() * (per_sm < 2 ? per_sm : 2);
+    const int want = sm_count() * (per_sm < 4 ? per_sm : 4);
     const int grid = max_count < want ? max_count : want;
-    launch_chain(vn_pixel_control_list_kernel, dim3(grid), dim3(256), (size_t)smem, stream, *store, plane, states, t, sn,
+    launch_chain(vn_pixel_control_list_kernel, dim3(grid), dim3(512), (size_t)smem, stream, *store, plane, states, t, sn,
                  st, g, pos, count, max_count, compact, out, chained ? 1 : 0);
     return check_launch("vn_pixel_control_list_kernel");
 }
@@ -832,8 +845,9 @@ int32_t vn_discounted_backup(const float *reward, const uint8_t *done, int64_t d
     return vn::check_launch("vn_backup_kernel");
 }
 
-int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int32_t *rows, const float *miss_rows,
-                                 const uint8_t *done, int64_t done_stride_n, int64_t done_stride_t,
+int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int32_t *rows, int64_t row_stride_n,
+                                 int64_t row_stride_t, const float *miss_rows, const uint8_t *done,
+                                 int64_t done_stride_n, int64_t done_stride_t,
                                  const float *bootstrap, float gamma, int32_t n, int32_t t, float *out_returns,
                                  float *out_reward, void *stream) {
     VN_REQUIRE(pc_table && rows && miss_rows && done && bootstrap && out_returns, "pixel_control_returns: null pointer");
@@ -847,9 +861,10 @@ int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int
     const int d4 = cells >> 2;
     const int64_t total = (int64_t)n * d4;
     vn::vn_pc_returns_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4 *>(pc_table), rows, reinterpret_cast<const float4 *>(miss_rows), done,
-        done_stride_n, done_stride_t, reinterpret_cast<const float4 *>(bootstrap), gamma, n, t, d4,
-        reinterpret_cast<float4 *>(out_returns), reinterpret_cast<float4 *>(out_reward), nullptr);
+        reinterpret_cast<const float4 *>(pc_table), rows, row_stride_n, row_stride_t,
+        reinterpret_cast<const float4 *>(miss_rows), done, done_stride_n, done_stride_t,
+        reinterpret_cast<const float4 *>(bootstrap), gamma, n, t, d4, reinterpret_cast<float4 *>(out_returns),
+        reinterpret_cast<float4 *>(out_reward), nullptr);
     return vn::check_launch("vn_pc_returns_kernel");
 }
 
@@ -895,8 +910,11 @@ int32_t vn_pixel_control_returns_from_states(const vn_store_t *store, int32_t pl
     // (1) table row of every transition; the misses (episode resets) go to a list.  *miss_count must be 0 on entry:
     //     zero it once when the scratch is allocated - kernel (3) re-arms it for the next call
     const int64_t total = (int64_t)n * t;
+    // the scratch `rows` follows the layout of `states`: time-major storage in, time-major row indices out
+    const bool tm = state_stride_t > state_stride_n;
+    const int64_t rsn = tm ? 1 : t, rst = tm ? n : 1;
     vn::launch_chain(vn::vn_transition_rows_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, st, adj, states, n,
-                     t, state_stride_n, state_stride_t, rows, miss_pos, miss_count, 1);
+                     t, state_stride_n, state_stride_t, rsn, rst, rows, miss_pos, miss_count, 1);
     rc = vn::check_launch("vn_transition_rows_kernel");
     if (rc) return rc;
     // (2) the misses computed directly from their two frames into the compact side buffer
@@ -911,8 +929,9 @@ int32_t vn_pixel_control_returns_from_states(const vn_store_t *store, int32_t pl
     const int d4 = cells >> 2;
     const int64_t threads = (int64_t)n * d4;
     vn::launch_chain(vn::vn_pc_returns_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st,
-                     reinterpret_cast<const float4 *>(pc_table), rows, reinterpret_cast<const float4 *>(miss_rows), done,
-                     done_stride_n, done_stride_t, reinterpret_cast<const float4 *>(bootstrap), gamma, n, t, d4,
+                     reinterpret_cast<const float4 *>(pc_table), rows, rsn, rst,
+                     reinterpret_cast<const float4 *>(miss_rows), done, done_stride_n, done_stride_t,
+                     reinterpret_cast<const float4 *>(bootstrap), gamma, n, t, d4,
                      reinterpret_cast<float4 *>(out_returns), reinterpret_cast<float4 *>(out_reward), miss_count);
     return vn::check_launch("vn_pc_returns_kernel");
 }
@@ -940,8 +959,8 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
 }
 
 int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int64_t state_stride_n,
-                           int64_t state_stride_t, int32_t *rows, int32_t *miss_pos, int32_t *miss_count,
-                           void *stream) {
+                           int64_t state_stride_t, int32_t *rows, int64_t row_stride_n, int64_t row_stride_t,
+                           int32_t *miss_pos, int32_t *miss_count, void *stream) {
     VN_REQUIRE(adj && states && rows && miss_pos && miss_count, "transition_rows: null pointer");
     VN_REQUIRE(n >= 0 && t >= 1, "transition_rows: n=%d t=%d", n, t);
     VN_REQUIRE((reinterpret_cast<uintptr_t>(adj) & 15) == 0, "transition_rows: adj must be 16-byte aligned");
@@ -950,7 +969,7 @@ int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n,
     cudaMemsetAsync(miss_count, 0, sizeof(int32_t), st);
     const int64_t total = (int64_t)n * t;
     vn::vn_transition_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        adj, states, n, t, state_stride_n, state_stride_t, rows, miss_pos, miss_count, 0);
+        adj, states, n, t, state_stride_n, state_stride_t, row_stride_n, row_stride_t, rows, miss_pos, miss_count, 0);
     return vn::check_launch("vn_transition_rows_kernel");
 }
 

@@ -140,11 +140,11 @@ def load(build_if_missing=True):
         "vn_nstep_returns_scan": (i32, [_P, _P, _P, f32, i32, i32, i64, i64, _P, i64, i64, _P]),
         "vn_discounted_backup": (i32, [_P, _P, i64, i64, _P, f32, i32, i32, i32, _P, _P]),
         "vn_pixel_control": (i32, [S, i32, _P, i32, i32, i64, i64, i32, i32, i32, i32, i32, i32, _P, _P]),
-        "vn_transition_rows": (i32, [_P, _P, i32, i32, i64, i64, _P, _P, _P, _P]),
+        "vn_transition_rows": (i32, [_P, _P, i32, i32, i64, i64, _P, i64, i64, _P, _P, _P]),
         "vn_gather_rows": (i32, [_P, i64, _P, i64, i32, i64, i64, _P, _P]),
         "vn_pixel_control_list": (i32, [S, i32, _P, i32, i32, i64, i64, i32, i32, i32, i32, i32, i32, _P, _P, i32, i32,
                                         _P, _P]),
-        "vn_pixel_control_returns": (i32, [_P, i32, _P, _P, _P, i64, i64, _P, f32, i32, i32, _P, _P, _P]),
+        "vn_pixel_control_returns": (i32, [_P, i32, _P, i64, i64, _P, _P, i64, i64, _P, f32, i32, i32, _P, _P, _P]),
         "vn_pixel_control_returns_from_states": (i32, [S, i32, _P, _P, _P, i64, i64, _P, i64, i64, _P, f32, i32, i32, i32,
                                                        i32, i32, i32, i32, i32, _P, _P, _P, _P, i32, _P, _P, _P]),
         "vn_replay_sample": (i32, [C.POINTER(Replay), i32, i32, u64, C.c_uint32, i32, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -740,9 +740,7 @@ def run_cuda(args):
             rb.start(env)
             for t in range(T_roll):
                 rb.step(env, act(i * T_roll + t), actions_ready=True)
-            ret = rb.returns(v_last, 0.99)
-            pcr = rb.pixel_control_returns(q_last, 0.9, 4, (20, 20))
-            return ret, pcr, rb.reward_prediction()
+            return rb.targets(v_last, 0.99, q_last, 0.9, 4, (20, 20))
 
         def steps_only(i):
             for t in range(T_roll):

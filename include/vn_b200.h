@@ -362,7 +362,9 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
  * function of the state pair, so it is computed ONCE per (state, action) into a table
  * pc_table[n_states * 4][out_h * out_w] (vn_pixel_control over the pairs (s, adj[s][a])) and a rollout's
  * rewards become row gathers:
- *   vn_transition_rows   rows[n][k] = s*4 + a with adj[s][a] == s' ; -1 (zeros) when s' == s (collision /
+ *   vn_transition_rows   rows(n, k) = s*4 + a with adj[s][a] == s' (element (n, k) of the scratch lives at
+ *                        n * row_stride_n + k * row_stride_t: give it the layout of `states` and both are accessed
+ *                        coalesced); -1 (zeros) when s' == s (collision /
  *                        no-op: identical frames); -(2 + m) for transitions the table cannot serve (resets):
  *                        their positions n*t + k are appended to miss_pos[m] and counted in miss_count[0]
  *   vn_gather_rows       out[i] = table[idx(i)] (rows of row_bytes, multiple of 16); idx -1 writes zeros,
@@ -377,16 +379,17 @@ int32_t vn_pixel_control(const vn_store_t *store, int32_t plane, const int32_t *
  *                        pc(n, k) = table[rows] | 0 | miss_rows[m] read on the fly; out_returns [n][t][cells],
  *                        out_reward (optional) receives pc itself.  cells must be a multiple of 4. */
 int32_t vn_transition_rows(const int32_t *adj, const int32_t *states, int32_t n, int32_t t, int64_t state_stride_n,
-                           int64_t state_stride_t, int32_t *rows, int32_t *miss_pos, int32_t *miss_count,
-                           void *stream);
+                           int64_t state_stride_t, int32_t *rows, int64_t row_stride_n, int64_t row_stride_t,
+                           int32_t *miss_pos, int32_t *miss_count, void *stream);
 int32_t vn_gather_rows(const void *table, int64_t row_bytes, const int32_t *idx, int64_t n, int32_t idx_t,
                        int64_t idx_stride_n, int64_t idx_stride_t, void *out, void *stream);
 int32_t vn_pixel_control_list(const vn_store_t *store, int32_t plane, const int32_t *states, int32_t n, int32_t t,
                               int64_t state_stride_n, int64_t state_stride_t, int32_t h, int32_t w, int32_t c,
                               int32_t cell, int32_t out_h, int32_t out_w, const int32_t *pos, const int32_t *count,
                               int32_t max_count, int32_t compact, float *out, void *stream);
-int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int32_t *rows, const float *miss_rows,
-                                 const uint8_t *done, int64_t done_stride_n, int64_t done_stride_t,
+int32_t vn_pixel_control_returns(const float *pc_table, int32_t cells, const int32_t *rows, int64_t row_stride_n,
+                                 int64_t row_stride_t, const float *miss_rows, const uint8_t *done,
+                                 int64_t done_stride_n, int64_t done_stride_t,
                                  const float *bootstrap, float gamma, int32_t n, int32_t t, float *out_returns,
                                  float *out_reward, void *stream);
 /* The three steps above as ONE call for a rollout's states: vn_transition_rows, vn_pixel_control_list (compact, into

@@ -353,6 +353,11 @@ def test_builders_read_time_major_storage_in_place(dw):
     assert torch.equal(got, want) and torch.equal(rew, pc.view(N, Tn, 400))
     assert torch.equal(buf.pixel_control_returns(q, 0.9, 4, (20, 20)), want)
     assert torch.equal(R.discounted_backup(pc.view(N, Tn, 400), buf.dones.t(), q, 0.9), want)
+    # all targets in one go (small builders on a side stream): same bits
+    t_ret, t_pcr, (t_lab, t_z, t_nz, t_cnt) = buf.targets(v, 0.99, q, 0.9, 4, (20, 20))
+    cz, cn = t_cnt.tolist()
+    assert torch.equal(t_ret, buf.returns(v, 0.99)) and torch.equal(t_pcr, want)
+    assert torch.equal(t_lab, lab_c) and torch.equal(t_z[:cz], z_c) and torch.equal(t_nz[:cn], nz_c)
     # against the oracle as well
     scene = dw.world.scenes[0]
     fr = scene.plane_frames("rgb", st_c.cpu().numpy().reshape(-1)).reshape(N, Tn + 1, 84, 84, 3)
@@ -377,7 +382,7 @@ def test_a2c_data_pass_launches_only_library_kernels(dw):
         buf.start(env)
         for t in range(Tn):
             buf.step(env, acts[t], actions_ready=True)
-        return buf.returns(v, 0.99), buf.pixel_control_returns(q, 0.9, 4, (20, 20)), buf.reward_prediction()
+        return buf.targets(v, 0.99, q, 0.9, 4, (20, 20))
 
     data_pass()
     torch.cuda.synchronize()

@@ -34,9 +34,12 @@ def main():
         rb.start(env)
         for t in range(T):
             rb.step(env, acts[(p * T + t) % 256], actions_ready=True)
-        rb.returns(v, 0.99)
-        rb.pixel_control_returns(q, 0.9, 4, (20, 20))
-        rb.reward_prediction()
+        if os.environ.get("A2C_SERIAL"):
+            rb.returns(v, 0.99)
+            rb.pixel_control_returns(q, 0.9, 4, (20, 20))
+            rb.reward_prediction()
+        else:
+            rb.targets(v, 0.99, q, 0.9, 4, (20, 20))
     e1.record()
     torch.cuda.synchronize()
     print("a2c pass: %.1f us (%d passes)" % (1e3 * e0.elapsed_time(e1) / max(1, passes - 5), passes))
