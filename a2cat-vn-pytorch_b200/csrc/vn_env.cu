@@ -835,7 +835,9 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         }
         int per_sm = max(1, min(32, (220 * 1024) / (smem + 1024)));
         if (env_per_sm > 0) per_sm = min(per_sm, env_per_sm);
-        const int grid = (int)min((int64_t)gp.n * split, (int64_t)sm_count() * per_sm);
+        int grid = (int)min((int64_t)gp.n * split, (int64_t)sm_count() * per_sm);
+        static const int env_grid = getenv("VN_BULK_GRID") ? atoi(getenv("VN_BULK_GRID")) : 0;   // development
+        if (env_grid > 0) grid = min(grid, env_grid);
         launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, split,
                    (env_dynamic && gp.sched) ? gp.sched + (gp.parity & 1) : nullptr, env_hints);
         return check_launch("vn_gather_bulk_kernel");
