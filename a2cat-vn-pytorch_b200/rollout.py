@@ -191,8 +191,7 @@ def pixel_control_reward(dw: DeviceWorld, states, cell_size=4, output_size=None,
     sn, st_ = states.stride()
     with torch.cuda.device(dw.device):
         st = _stream(states)
-        # the row scratch takes the layout of `states` (coalesced on both sides); the gather reads it through strides
-        rsn, rst = (1, b) if st_ > sn else (t, 1)
+        rsn, rst = t, 1          # batch-major row scratch (the lookup kernel orders its threads for coalesced state reads)
         L.check(lib.vn_transition_rows(dw.adj.data_ptr(), states.data_ptr(), b, t, sn, st_, rows.data_ptr(), rsn, rst,
                                        miss_pos.data_ptr(), miss_count.data_ptr(), st))
         L.check(lib.vn_gather_rows(tab.pc.data_ptr(), oh * ow * 4, rows.data_ptr(), b * t, t, rsn, rst, out.data_ptr(), st))
