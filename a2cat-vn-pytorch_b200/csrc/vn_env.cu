@@ -96,7 +96,10 @@ __device__ __forceinline__ void step_env(const StepParams &p, const int i, EnvSt
     if (kReset) {
         do_reset = p.mask ? (p.mask[i] != 0) : true;
     } else {
-        const int a = p.actions[i];  // may live in mapped pinned host memory (vn_env_step_host)
+        // may live in mapped pinned host memory (vn_env_step_host).  Carrying the host's actions in the kernel parameters
+        // instead (one byte per env, packed by the CPU) was measured: no PCIe read in front of the dependent loads, but
+        // packing + an 8 KB parameter block cost more than that saved (RGB-only e2e 145.4 -> 141.2 M env-steps/s)
+        const int a = p.actions[i];
         if (p.actions_copy) p.actions_copy[i] = a;
         const int s_old = s;
         bool terminal = false, collided = false;
@@ -1179,6 +1182,7 @@ int32_t vn_abi_struct_size(int32_t which) {
         case 5: return (int32_t)sizeof(vn_step_out_t);
         case 6: return (int32_t)sizeof(vn_replay_t);
         case 7: return (int32_t)sizeof(vn_float_leaf_t);
+        case 8: return (int32_t)sizeof(vn_host_call_t);
         default: return -1;
     }
 }
@@ -1341,6 +1345,13 @@ int32_t vn_env_step_host_sync(const vn_store_t *store, const vn_tables_t *tables
     if (reward_copy) memcpy(reward_copy, out->host_pack, 4 * n);
     if (done_copy) memcpy(done_copy, out->host_pack + 16 * n, n);
     return VN_OK;
+}
+
+int32_t vn_env_step_host_call(const vn_host_call_t *call, float *reward_copy, uint8_t *done_copy, void *stream) {
+    VN_REQUIRE(call, "step_host_call: null descriptor");
+    return vn_env_step_host_sync(call->store, call->tables, call->envs, call->rules, call->inject, call->host_actions,
+                                 call->dev_actions_copy, call->out, nullptr, reward_copy, done_copy, call->seq_words,
+                                 call->gather_variant, stream, call->timeout_us);
 }
 
 int32_t vn_event_create(void **event) {

@@ -331,6 +331,7 @@ class GraphVecEnv:
                 o.float_leaves = C.cast(self._float_leaves, C.c_void_p)
                 o.n_float_leaves, o.float_h, o.float_w = len(self._float_leaves), h, w
         self._pending = False
+        self._hc = None
         self._h2d_done = None
         self._serial_next = False
         self._obs_cache = None
@@ -651,28 +652,54 @@ class GraphVecEnv:
         fetch = lambda: self._unpack(self._pack.cpu().numpy())
         return self._obs_out(), self.reward, self.done.bool(), LazyInfos(self, fetch, noop)
 
+    def _bind_host_call(self):
+        """The constant arguments of the host-facing step bound once (vn_host_call_t): the per-step call converts
+        four arguments instead of fifteen."""
+        hc = L.HostCall()
+        hc.store = C.cast(C.pointer(self.dw.store), C.c_void_p)
+        hc.tables = C.cast(C.pointer(self.dw.tables), C.c_void_p)
+        hc.envs = C.cast(C.pointer(self._c_envs), C.c_void_p)
+        hc.rules = C.cast(C.pointer(self._c_rules), C.c_void_p)
+        hc.inject = C.cast(C.pointer(self._c_inject), C.c_void_p) if self._c_inject is not None else None
+        hc.host_actions, hc.dev_actions_copy = self._actions_ptr, self._actions_dev_ptr
+        hc.out = C.cast(C.pointer(self._c_out_host), C.c_void_p)
+        hc.seq_words, hc.gather_variant, hc.timeout_us = self._seq_words, self.gather, 60_000_000
+        self._hc, self._hc_ptr = hc, C.addressof(hc)
+        self._hc_inject = self._c_inject
+        self._hc_fn = self.lib.vn_env_step_host_call
+
     def step(self, actions):
         if self.host_outputs and type(actions) is np.ndarray and not self._pending and not self.closed \
                 and actions.size == self.num_envs and self.num_envs and \
                 (not self.scaled_float or self._float_leaves is not None):
-            # the reference-facing call, numpy in / numpy out, as ONE C call: stage the actions, enqueue both
-            # kernels, spin until the scalars are in pinned memory, copy them out (vn_env_step_host_sync)
+            # the reference-facing call, numpy in / numpy out, as ONE C call: stage the actions, enqueue the kernels,
+            # spin until the scalars are in pinned memory, copy rewards / dones out (vn_env_step_host_call)
             n = self.num_envs
-            np.copyto(self._actions_np, actions.reshape(-1), casting="same_kind")
+            np.copyto(self._actions_np, actions if actions.ndim == 1 else actions.reshape(-1), casting="same_kind")
+            if self._hc is None or self._hc_inject is not self._c_inject:
+                self._bind_host_call()
             out = self._c_out_host
-            self._tick(out, L.STEP_ACTIONS_READY | self._step_flags)
-            self._seq = (self._seq % 0x7FFFFFFF) + 1
-            out.seq = self._seq
+            self._calls += 1
+            out.parity = self._calls & 1
+            if self._serial_next:       # the previous launch was a graph replay: do not overlap its gather
+                out.flags, self._serial_next = self._step_flags, False
+            else:
+                out.flags = L.STEP_ACTIONS_READY | self._step_flags
+            self._seq = out.seq = (self._seq % 0x7FFFFFFF) + 1
             self._next_pack()
-            rew, done = np.empty(n, np.float32), np.empty(n, np.bool_)
-            r = self._ref
-            self._call(self.lib.vn_env_step_host_sync, r["store"], r["tables"], r["envs"], r["rules"],
-                       C.byref(self._c_inject) if self._c_inject is not None else None,
-                       self._actions_ptr, self._actions_dev_ptr, r["out_host"], None,
-                       rew.__array_interface__["data"][0], done.__array_interface__["data"][0],
-                       self._seq_words, self.gather, _raw_stream(self._dev_index), 60_000_000)
+            res = np.empty(5 * n, np.uint8)         # rewards (4n bytes) + dones (n bytes) in one allocation
+            ptr = res.__array_interface__["data"][0]
+            if torch.cuda.current_device() == self._dev_index:
+                rc = self._hc_fn(self._hc_ptr, ptr, ptr + 4 * n, _raw_stream(self._dev_index))
+            else:
+                with torch.cuda.device(self.device):
+                    rc = self._hc_fn(self._hc_ptr, ptr, ptr + 4 * n, _raw_stream(self._dev_index))
+            if rc:
+                L.check(rc)
             noop = (self._actions_np < 0) if self.family.noop_action else None
-            return (self._obs_out(),) + self._host_results(rew, done, noop)
+            infos = LazyInfos(self, self._pack_np, noop, True)
+            self._infos_refs[self._slot] = weakref.ref(infos)
+            return self._obs_out(), res[:4 * n].view(np.float32), res[4 * n:].view(np.bool_), infos
         self.step_async(actions)
         return self.step_wait()
 

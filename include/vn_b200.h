@@ -221,7 +221,8 @@ typedef struct vn_step_out {
 
 int32_t vn_abi_version(void);
 /* sizeof of the descriptor structs as compiled into the library (0 store, 1 tables, 2 envs, 3 rules, 4 inject,
- * 5 step_out, 6 replay, 7 float_leaf; -1 otherwise): a binding checks its mirrors against these at load time. */
+ * 5 step_out, 6 replay, 7 float_leaf, 8 host_call; -1 otherwise): a binding checks its mirrors against these at load
+ * time. */
 int32_t vn_abi_struct_size(int32_t which);
 const char *vn_last_error(void);
 /* Kernels enqueued by the library so far (process-wide, monotonically increasing; statistics only). */
@@ -292,6 +293,25 @@ int32_t vn_env_step_host_sync(const vn_store_t *store, const vn_tables_t *tables
                               int32_t *dev_actions_copy, const vn_step_out_t *out, uint8_t *pack_copy,
                               float *reward_copy, uint8_t *done_copy, int32_t seq_words, int32_t gather_variant,
                               void *stream, int64_t timeout_us);
+/* The same call with its constant arguments bound once: a host loop that steps the same env batch thousands of times per
+ * second (a Python binding pays per argument it converts) fills this descriptor once, updates out->parity / flags / seq /
+ * host_pack in place between calls and passes four arguments per step.  All pointers are [host]; the structs they point
+ * to must outlive the calls. */
+typedef struct vn_host_call {
+    const vn_store_t *store;
+    const vn_tables_t *tables;
+    const vn_envs_t *envs;
+    const vn_rules_t *rules;
+    const vn_inject_t *inject;        /* may be NULL */
+    const int32_t *host_actions;      /* pinned */
+    int32_t *dev_actions_copy;        /* device, may be NULL */
+    const vn_step_out_t *out;
+    int32_t seq_words;
+    int32_t gather_variant;
+    int64_t timeout_us;
+} vn_host_call_t;
+int32_t vn_env_step_host_call(const vn_host_call_t *call, float *reward_copy, uint8_t *done_copy, void *stream);
+
 int32_t vn_event_create(void **event);   /* cudaEventDisableTiming */
 int32_t vn_event_destroy(void *event);
 int32_t vn_event_wait(void *event);      /* cudaEventSynchronize; releases the GIL under ctypes */

@@ -1356,3 +1356,34 @@ def test_drop_in_under_the_reference_trainer_contract():
     assert [tuple(b.shape) for b in sp.spaces[0].spaces] == [tuple(s[1:]) for s in g["obs_shapes"]]
     H.check_trainer_contract_run(g, env, lambda x, i: H.crc(x[i].cpu().numpy()), env.set_hardness)
     assert env.episode_stats()["episodes"] == g["dones"].sum()
+
+
+def test_host_route_equals_device_route_for_any_action_value():
+    """The host-facing step (actions read by the scalar kernel from mapped pinned memory) and the device-resident step
+    give the same states / rewards / dones for every int32 action value - out-of-range ones have collision semantics -
+    and both record the action actually sent (rollout record, device copy of the host's actions)."""
+    import torch
+    scene = H.scenes.make_thor_scene(120, (14, 18), seed=5, n_goals=3, planes=("rgb",))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    N = 700
+    host = vn.GraphVecEnv(world, N, seed=4, max_episode_steps=7, obs_layout="frame")
+    dev = vn.GraphVecEnv(world, N, seed=4, max_episode_steps=7, obs_layout="frame", host_outputs=False, device_world=host.dw)
+    host.reset()
+    dev.reset()
+    rng = np.random.RandomState(2)
+    rec = torch.zeros((2, N), dtype=torch.int32, device="cuda")
+    for t in range(30):
+        a = rng.randint(-2, 6, N).astype(np.int32)              # includes actions outside [0, 4)
+        if t % 3 == 1:
+            a[rng.randint(N)] = 1000
+        if t % 3 == 2:
+            a[rng.randint(N)] = -129
+        host._c_out_host.rec_action = rec[0].data_ptr()
+        _, r, d, _ = host.step(a)
+        dev._c_out.rec_action = rec[1].data_ptr()
+        _, rd, dd, _ = dev.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(r.view(np.uint32), rd.cpu().numpy().view(np.uint32)) and np.array_equal(d, dd.cpu().numpy()), t
+        assert torch.equal(host.state, dev.state), t
+        assert torch.equal(rec[0], rec[1]) and np.array_equal(rec[0].cpu().numpy(), a), t
+        assert torch.equal(host.actions_dev, torch.from_numpy(a).cuda()), t      # the device copy of the host's actions
+    assert host.episode_stats() == dev.episode_stats()

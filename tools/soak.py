@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main(steps=200000, block=5000):
+def main(steps=200000, block=1000):
     import torch
     vn = importlib.import_module("a2cat-vn-pytorch_b200")
     scene = vn.scenes.make_thor_scene(400, (30, 30), seed=3, n_goals=4, planes=("rgb", "depth", "segmentation"))
@@ -20,6 +20,8 @@ def main(steps=200000, block=5000):
     for name, n, kw in (("uint8 aux5 pipelined", 2048, dict(obs_layout="aux5")),
                         ("float rgbd_goal", 1024, dict(obs_layout="rgbd_goal", scaled_float=True)),
                         ("fused 200 envs", 200, dict(obs_layout="aux5")),
+                        ("persistent launch 600 envs", 600, dict(obs_layout="rgbd_goal")),
+                        ("persistent launch 3000 envs", 3000, dict(obs_layout="rgbd_goal", gather="persistent")),
                         ("hardness 0.01 (reset-heavy)", 4096, dict(obs_layout="rgbd_goal"))):
         env = vn.GraphVecEnv(world, n, seed=11, max_episode_steps=37, host_outputs=False, device_world=dw, **kw)
         if "hardness" in name:
