@@ -22,6 +22,7 @@
 namespace vn {
 
 static thread_local std::string g_error;
+static unsigned long long *g_gather_trace = nullptr;  // development: vn_debug_gather_trace
 static std::atomic<long long> g_launches{0};  // statistics only: kernels enqueued by this library, all threads
 
 void set_error(const char *fmt, ...) {
@@ -327,7 +328,15 @@ struct GatherParams {
     // memory - often env.state / obs_state / goal themselves - that a following step kernel REWRITES, so the successor
     // must not start before this grid has completed.
     int32_t early_release;
+    // development: per-CTA timeline (vn_debug_gather_trace): [grid][8] globaltimer stamps, NULL = off
+    unsigned long long *trace;
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 // ---- variant A: 16-byte vector loads / stores through registers -------------------------------------
 template <int kThreads, int kUnroll>
@@ -468,11 +477,20 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     if (threadIdx.x != 0) return;
+    unsigned long long *tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
+    if (tr) {
+        tr[0] = globaltimer_ns();   // CTA resident
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        tr[6] = smid;
+    }
     mbar_init(&bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the prologue above overlapped the scalar kernel; its results are needed from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p.early_release) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (tr) tr[1] = globaltimer_ns();   // predecessor complete
+    int n_units = 0;
     uint32_t parity = 0;
     BulkHints hints;
     // bits: 1 loads evict_last, 2 stores evict_first, 4 loads evict_first, 8 stores evict_last
@@ -516,10 +534,20 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
             bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints, fetch_next);
         }
         fetch_next();
+        if (tr) {
+            if (n_units == 0) tr[2] = globaltimer_ns();   // first unit issued (its stores are in flight)
+            tr[3] = globaltimer_ns();                      // last unit issued
+            if (n_units < 8) tr[8 + n_units] = tr[3] | ((unsigned long long)(d.x < 0 && d.y < 0) << 63);  // bit 63: nothing copied
+            ++n_units;
+        }
         u = u_next;
         d = d_next;
     }
     bulk_wait_read<0>();
+    if (tr) {
+        tr[4] = globaltimer_ns();   // shared memory drained
+        tr[5] = (unsigned long long)n_units;
+    }
     // no epilogue: the ticket counter of this launch (sched[parity]) is zeroed by the scalar half of the step that
     // next uses it - a fence + atomic + re-arm here sat on the critical path of every launch (~1 us)
 }
@@ -919,6 +947,7 @@ static int32_t make_gather_params(GatherParams &gp, const vn_store_t *store, con
     gp.sched = out->sched;
     gp.parity = out->parity;
     gp.early_release = 1;
+    gp.trace = g_gather_trace;
     gp.desc = out->gather_desc
                   ? reinterpret_cast<const int2 *>(out->gather_desc) + (size_t)(out->parity & 1) * envs->n_envs
                   : nullptr;
@@ -1354,6 +1383,11 @@ int32_t vn_env_step_host_call(const vn_host_call_t *call, float *reward_copy, ui
                                  call->gather_variant, stream, call->timeout_us);
 }
 
+int32_t vn_debug_gather_trace(uint64_t *device_buffer) {
+    vn::g_gather_trace = reinterpret_cast<unsigned long long *>(device_buffer);
+    return VN_OK;
+}
+
 int32_t vn_event_create(void **event) {
     VN_REQUIRE(event, "event_create: null");
     cudaEvent_t ev;
@@ -1396,6 +1430,7 @@ int32_t vn_gather_plane(const vn_store_t *store, int32_t plane, const int32_t *i
     gp.sched = nullptr;  // static unit assignment: no scratch in this signature
     gp.parity = 0;
     gp.early_release = 0;  // idx is caller memory a following step may rewrite: no early start of the successor
+    gp.trace = nullptr;
     gp.n = n;
     for (int pl = 0; pl < VN_MAX_PLANES; ++pl) {
         gp.obs[pl] = (pl == plane) ? out : nullptr;

@@ -91,7 +91,7 @@ _lib = None
 
 #: every symbol include/vn_b200.h declares
 EXPORTS = ("vn_abi_version", "vn_abi_struct_size", "vn_last_error", "vn_launch_count", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
-           "vn_env_gather", "vn_env_step_host", "vn_env_step_host_sync", "vn_env_step_host_call", "vn_env_host_seq_words", "vn_host_wait_seq", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
+           "vn_env_gather", "vn_env_step_host", "vn_env_step_host_sync", "vn_env_step_host_call", "vn_debug_gather_trace", "vn_env_host_seq_words", "vn_host_wait_seq", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_gather_plane_f32_chw_rows", "vn_gather_leaves_f32_chw", "vn_nstep_returns", "vn_nstep_returns_scan", "vn_discounted_backup", "vn_pixel_control",
            "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_pixel_control_returns", "vn_pixel_control_returns_from_states", "vn_replay_sample",
            "vn_aux_target", "vn_rp_labels")
@@ -134,6 +134,7 @@ def load(build_if_missing=True):
         "vn_env_step_host": (i32, [S, T, E, R, I, _P, _P, O, _P, i32, _P]),
         "vn_env_step_host_sync": (i32, [S, T, E, R, I, _P, _P, O, _P, _P, _P, i32, i32, _P, i64]),
         "vn_env_step_host_call": (i32, [_P, _P, _P, _P]),
+        "vn_debug_gather_trace": (i32, [_P]),
         "vn_env_host_seq_words": (i32, [S, E, O, i32]),
         "vn_host_wait_seq": (i32, [_P, i32, C.c_uint32, _P, i64]),
         "vn_event_create": (i32, [C.POINTER(_P)]),

@@ -312,6 +312,12 @@ typedef struct vn_host_call {
 } vn_host_call_t;
 int32_t vn_env_step_host_call(const vn_host_call_t *call, float *reward_copy, uint8_t *done_copy, void *stream);
 
+/* Development aid: when device_buffer is not NULL every CTA of the step path's bulk gather writes 16 uint64 there
+ * ([grid][16]: globaltimer ns when resident, when its predecessor had completed, after its first and last unit, when its
+ * shared memory had drained; [5] = units it handled, [6] = SM id, [8..15] = time after each of its first 8 units, bit 63
+ * set when the unit copied nothing) - tools/gather_timeline.py.  NULL switches it off.  Process-wide. */
+int32_t vn_debug_gather_trace(uint64_t *device_buffer);
+
 int32_t vn_event_create(void **event);   /* cudaEventDisableTiming */
 int32_t vn_event_destroy(void *event);
 int32_t vn_event_wait(void *event);      /* cudaEventSynchronize; releases the GIL under ctypes */
