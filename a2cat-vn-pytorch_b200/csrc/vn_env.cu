@@ -15,6 +15,9 @@
 
 #include "vn_common.cuh"
 
+#ifndef VN_BULK_GROUPS_DEFAULT
+#define VN_BULK_GROUPS_DEFAULT 1  // chunks (own mbarrier each) per record slice in the bulk copies, see bulk_copy_slice
+#endif
 #ifndef VN_PERSISTENT_DEFAULT
 #define VN_PERSISTENT_DEFAULT 1  // VN_GATHER_AUTO beyond one wave: 0 never, 1 mid-size device-resident batches, 2 always
 #endif
@@ -414,6 +417,9 @@ __global__ void __launch_bounds__(kThreads) vn_gather_ldg_kernel(const GatherPar
 struct BulkHints {
     int mode;  // bit 0: loads evict_last, bit 1: stores evict_first
     uint64_t load_policy, store_policy;
+    int groups = 1;  // chunks per record slice, each with its own mbarrier (1 .. kCopyGroups)
+    int whole_record = 0;  // bit 0 / 1: the observation / goal plane set is contiguous in the record and shared memory was
+                           // sized for its SPAN: one load per record (see bulk_copy_slice)
 };
 
 struct NoPrefetch {
@@ -422,60 +428,116 @@ struct NoPrefetch {
 
 // `while_loading()` runs after the global->shared copies of the slice have been issued and before the wait for them: the
 // place to fetch whatever the NEXT unit needs (ticket, descriptor) so that its latency hides behind this transfer.
+// One record slice through shared memory in kCopyGroups chunks, each with its own mbarrier: all loads are issued at once,
+// and the stores of chunk g go out as soon as chunk g has landed - while chunks g+1.. are still loading.  With ONE barrier
+// for the whole record (round 1) a CTA alternated between a pure load phase and a pure store phase: the first 6.5 us of
+// every launch were reads only, and every unit paid load latency + store drain back to back.
+constexpr int kCopyGroups = 4;
+
+// Calls op(group, plane, first 16-byte unit in the plane, units, shared-memory offset in units) for every piece of the
+// slice; pieces are cut at plane ends and at group boundaries (gsize units of shared memory per group).
+template <typename Op>
+__device__ __forceinline__ void for_each_piece(const vn_store_t &st, uint8_t *const *dst, int slice, int split, int gsize,
+                                               int groups, Op op) {
+    int off = 0;
+    for (int pl = 0; pl < st.n_planes; ++pl)
+        if (dst[pl]) {
+            const int n16 = st.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
+            const int lo = min(slice * per, n16), hi = min(lo + per, n16);
+            int pos = lo;
+            while (pos < hi) {
+                const int g = min(off / gsize, groups - 1);
+                const int room = g == groups - 1 ? hi - pos : (g + 1) * gsize - off;
+                const int cnt = min(hi - pos, room);
+                op(g, pl, pos, cnt, off);
+                pos += cnt;
+                off += cnt;
+            }
+        }
+}
+
 template <typename F = NoPrefetch>
 __device__ __forceinline__ void bulk_copy_slice(const vn_store_t &st, const uint8_t *src, uint8_t *const *dst,
                                                 int env, int slice, int split, uint8_t *smem, uint64_t *bar,
-                                                uint32_t &parity, const BulkHints &hints, F while_loading = F()) {
+                                                uint32_t &parity, const BulkHints &hints, F while_loading = F(),
+                                                bool whole = false) {
     // the previous shared->global reads of this buffer must have drained before it is refilled
     bulk_wait_read<0>();
-    uint32_t total = 0;
+    int total = 0;
     for (int pl = 0; pl < st.n_planes; ++pl)
         if (dst[pl]) {
             const int n16 = st.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
             const int lo = min(slice * per, n16), hi = min(lo + per, n16);
-            total += (uint32_t)(hi - lo) << 4;
+            total += hi - lo;
         }
     if (total == 0) return;
-    mbar_expect_tx(bar, total);
-    uint32_t off = 0;
-    for (int pl = 0; pl < st.n_planes; ++pl)
-        if (dst[pl]) {
-            const int n16 = st.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
-            const int lo = min(slice * per, n16), hi = min(lo + per, n16);
-            if (hi > lo) {
-                if (hints.mode & 1)
-                    bulk_g2s_hint(smem + off, src + st.plane_off[pl] + ((size_t)lo << 4), (uint32_t)(hi - lo) << 4, bar,
-                                  hints.load_policy);
-                else
-                    bulk_g2s(smem + off, src + st.plane_off[pl] + ((size_t)lo << 4), (uint32_t)(hi - lo) << 4, bar);
-                off += (uint32_t)(hi - lo) << 4;
+    if (whole && split == 1) {
+        // The requested planes sit next to each other in the store record (128-byte aligned offsets, a few padding bytes
+        // between them): ONE load brings the whole span, one store per plane sends it out - bulk copies are cheaper the
+        // fewer and larger they are (every extra operation per record cost 0.2 - 1 us per step, profiles/r2_gather_groups.txt)
+        int first = -1, last = -1;
+        for (int pl = 0; pl < st.n_planes; ++pl)
+            if (dst[pl]) {
+                if (first < 0) first = pl;
+                last = pl;
             }
-        }
-    while_loading();
-    mbar_wait(bar, parity);
-    parity ^= 1;
-    off = 0;
-    for (int pl = 0; pl < st.n_planes; ++pl)
-        if (dst[pl]) {
-            const int n16 = st.plane_bytes[pl] >> 4, per = (n16 + split - 1) / split;
-            const int lo = min(slice * per, n16), hi = min(lo + per, n16);
-            if (hi > lo) {
+        const uint32_t base = (uint32_t)st.plane_off[first];
+        const uint32_t span = (uint32_t)st.plane_off[last] + (uint32_t)st.plane_bytes[last] - base;
+        mbar_expect_tx(bar, span);
+        if (hints.mode & 1)
+            bulk_g2s_hint(smem, src + base, span, bar, hints.load_policy);
+        else
+            bulk_g2s(smem, src + base, span, bar);
+        while_loading();
+        mbar_wait(bar, parity & 1u);
+        parity ^= 1u;
+        for (int pl = first; pl <= last; ++pl)
+            if (dst[pl]) {
+                uint8_t *to = dst[pl] + (size_t)env * st.plane_bytes[pl];
+                const uint8_t *from = smem + ((uint32_t)st.plane_off[pl] - base);
                 if (hints.mode & 2)
-                    bulk_s2g_hint(dst[pl] + (size_t)env * st.plane_bytes[pl] + ((size_t)lo << 4), smem + off,
-                                  (uint32_t)(hi - lo) << 4, hints.store_policy);
+                    bulk_s2g_hint(to, from, (uint32_t)st.plane_bytes[pl], hints.store_policy);
                 else
-                    bulk_s2g(dst[pl] + (size_t)env * st.plane_bytes[pl] + ((size_t)lo << 4), smem + off,
-                             (uint32_t)(hi - lo) << 4);
-                off += (uint32_t)(hi - lo) << 4;
+                    bulk_s2g(to, from, (uint32_t)st.plane_bytes[pl]);
             }
-        }
+        bulk_commit();
+        return;
+    }
+    const int groups = hints.groups;
+    const int gsize = (total + groups - 1) / groups;
+    for (int g = 0; g < groups; ++g) {
+        const int units = min(total, g == groups - 1 ? total : (g + 1) * gsize) - min(total, g * gsize);
+        if (units > 0) mbar_expect_tx(bar + g, (uint32_t)units << 4);
+    }
+    for_each_piece(st, dst, slice, split, gsize, groups, [&](int g, int pl, int pos, int cnt, int off) {
+        const uint8_t *from = src + st.plane_off[pl] + ((size_t)pos << 4);
+        if (hints.mode & 1)
+            bulk_g2s_hint(smem + ((size_t)off << 4), from, (uint32_t)cnt << 4, bar + g, hints.load_policy);
+        else
+            bulk_g2s(smem + ((size_t)off << 4), from, (uint32_t)cnt << 4, bar + g);
+    });
+    while_loading();
+#pragma unroll 1
+    for (int g = 0; g < groups; ++g) {
+        if (min(total, g * gsize) >= total) break;   // no bytes in this group (tiny slices)
+        mbar_wait(bar + g, (parity >> g) & 1u);
+        parity ^= 1u << g;
+        for_each_piece(st, dst, slice, split, gsize, groups, [&](int pg, int pl, int pos, int cnt, int off) {
+            if (pg != g) return;
+            uint8_t *to = dst[pl] + (size_t)env * st.plane_bytes[pl] + ((size_t)pos << 4);
+            if (hints.mode & 2)
+                bulk_s2g_hint(to, smem + ((size_t)off << 4), (uint32_t)cnt << 4, hints.store_policy);
+            else
+                bulk_s2g(to, smem + ((size_t)off << 4), (uint32_t)cnt << 4);
+        });
+    }
     bulk_commit();
 }
 
 __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p, int split, unsigned int *sched,
                                                             int hint_mode) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[kCopyGroups];
     if (threadIdx.x != 0) return;
     unsigned long long *tr = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;
     if (tr) {
@@ -484,7 +546,8 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
         asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
         tr[6] = smid;
     }
-    mbar_init(&bar, 1);
+#pragma unroll
+    for (int g = 0; g < kCopyGroups; ++g) mbar_init(bar + g, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // the prologue above overlapped the scalar kernel; its results are needed from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -497,6 +560,8 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     hints.load_policy = (hint_mode & 1) ? l2_policy_evict_last() : (hint_mode & 4) ? l2_policy_evict_first() : 0;
     hints.store_policy = (hint_mode & 2) ? l2_policy_evict_first() : (hint_mode & 8) ? l2_policy_evict_last() : 0;
     hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
+    hints.groups = max(1, min(kCopyGroups, (hint_mode >> 8) & 7));
+    hints.whole_record = (hint_mode >> 16) & 3;
     const int units = p.n * split;
     const bool dynamic = sched != nullptr;
     static_assert(sizeof(int2) == 8, "descriptor layout");
@@ -527,11 +592,13 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
         };
         if (d.x >= 0) {  // < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
             const uint8_t *src = p.store.base + (size_t)d.x * p.store.state_pitch;
-            bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, &bar, parity, hints, fetch_next);
+            bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, bar, parity, hints, fetch_next,
+                            (hints.whole_record & 1) != 0);
         }
         if (d.y >= 0) {
             const uint8_t *gsrc = p.store.base + (size_t)d.y * p.store.state_pitch;
-            bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, &bar, parity, hints, fetch_next);
+            bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, bar, parity, hints, fetch_next,
+                            (hints.whole_record & 2) != 0);
         }
         fetch_next();
         if (tr) {
@@ -643,10 +710,11 @@ __global__ void __launch_bounds__(kFusedWarps * 32) vn_step_fused_kernel(const S
 template <bool kReset>
 __global__ void __launch_bounds__(32) vn_step_gather_kernel(const StepParams sp, const GatherParams gp, int hint_mode) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar[kCopyGroups];
     const int lane = threadIdx.x;
     if (lane == 0) {
-        mbar_init(&bar, 1);
+#pragma unroll
+        for (int g = 0; g < kCopyGroups; ++g) mbar_init(bar + g, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // everything above overlapped the previous kernel of the stream; its env state is needed from here on
@@ -710,6 +778,8 @@ __global__ void __launch_bounds__(32) vn_step_gather_kernel(const StepParams sp,
     hints.load_policy = (hint_mode & 1) ? l2_policy_evict_last() : (hint_mode & 4) ? l2_policy_evict_first() : 0;
     hints.store_policy = (hint_mode & 2) ? l2_policy_evict_first() : (hint_mode & 8) ? l2_policy_evict_last() : 0;
     hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
+    hints.groups = max(1, min(kCopyGroups, (hint_mode >> 8) & 7));
+    hints.whole_record = (hint_mode >> 16) & 3;
     int2 d = desc[b];
     for (int e = b; e < n; e += G) {
         int2 d_next = make_int2(-1, -1);
@@ -719,11 +789,11 @@ __global__ void __launch_bounds__(32) vn_step_gather_kernel(const StepParams sp,
             have_next = true;
         };
         if (d.x >= 0)  // < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
-            bulk_copy_slice(gp.store, gp.store.base + (size_t)d.x * gp.store.state_pitch, gp.obs, e, 0, 1, smem, &bar,
-                            parity, hints, fetch_next);
+            bulk_copy_slice(gp.store, gp.store.base + (size_t)d.x * gp.store.state_pitch, gp.obs, e, 0, 1, smem, bar,
+                            parity, hints, fetch_next, (hints.whole_record & 1) != 0);
         if (d.y >= 0 && gp.goal)
-            bulk_copy_slice(gp.store, gp.store.base + (size_t)d.y * gp.store.state_pitch, gp.goal_obs, e, 0, 1, smem, &bar,
-                            parity, hints, fetch_next);
+            bulk_copy_slice(gp.store, gp.store.base + (size_t)d.y * gp.store.state_pitch, gp.goal_obs, e, 0, 1, smem, bar,
+                            parity, hints, fetch_next, (hints.whole_record & 2) != 0);
         fetch_next();
         d = d_next;
     }
@@ -812,6 +882,22 @@ int sm_count() {
     return cached[dev];
 }
 
+// Shared memory a CTA needs for one whole record of a plane set, and whether that set is CONTIGUOUS in the record
+// (nothing but alignment padding between its planes): then *span covers it with one load.
+static int plane_set_bytes(const vn_store_t &st, uint8_t *const *dst, bool use, int *span, bool *contiguous) {
+    int sum = 0, first = -1, last = -1;
+    for (int pl = 0; pl < st.n_planes; ++pl)
+        if (use && dst[pl]) {
+            sum += st.plane_bytes[pl];
+            if (first < 0) first = pl;
+            last = pl;
+        }
+    *span = first < 0 ? 0 : st.plane_off[last] + st.plane_bytes[last] - st.plane_off[first];
+    static const bool off = getenv("VN_NO_WHOLE_RECORD") && atoi(getenv("VN_NO_WHOLE_RECORD"));
+    *contiguous = !off && first >= 0 && last > first && *span - sum <= 128 * (last - first);
+    return sum;
+}
+
 static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream_t stream) {
     if (gp.n == 0) return VN_OK;
     for (int pl = 0; pl < gp.store.n_planes; ++pl) {
@@ -835,20 +921,23 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         static const int env_per_sm = getenv("VN_BULK_PER_SM") ? atoi(getenv("VN_BULK_PER_SM")) : 0;
         static const int env_dynamic = getenv("VN_BULK_DYNAMIC") ? atoi(getenv("VN_BULK_DYNAMIC")) : 1;
         // L2 policy hints: loads evict_last + stores evict_first measured +2.5 % (C2) / +4 % (hardness 0.01)
-        static const int env_hints = getenv("VN_BULK_L2_HINTS") ? atoi(getenv("VN_BULK_L2_HINTS")) : 3;
+        static const int env_groups = getenv("VN_BULK_GROUPS") ? atoi(getenv("VN_BULK_GROUPS")) : VN_BULK_GROUPS_DEFAULT;
+        static const int env_hints =
+            (getenv("VN_BULK_L2_HINTS") ? atoi(getenv("VN_BULK_L2_HINTS")) : 3) | (max(1, min(7, env_groups)) << 8);
         // small batches (C1: 16 envs) cannot fill 148 SMs with one record per CTA: cut each record into
         // slices until there are ~2 units per SM (latency-bound regime; one slice >= 2 KB)
         int split = env_split > 0 ? env_split : 1;
         if (env_split <= 0 && gp.n < 2 * sm_count()) split = min(16, (2 * sm_count() + gp.n - 1) / gp.n);
         if (env_split <= 0) {
             // large records (the reference's native 174 x 174 frames: 212 KB for rgb + depth + segmentation) are
-            // cut into slices of at most ~48 KB so that at least 4 CTAs stay resident per SM
+            // cut into slices of at most 52 KB so that at least 4 CTAs stay resident per SM (84 x 84 rgb + depth +
+            // segmentation = 49.6 KB stays whole: one load per record instead of two slices of three)
             int per_env = 0, per_goal = 0;
             for (int pl = 0; pl < gp.store.n_planes; ++pl) {
                 if (gp.obs[pl]) per_env += gp.store.plane_bytes[pl];
                 if (gp.goal && gp.goal_obs[pl]) per_goal += gp.store.plane_bytes[pl];
             }
-            split = max(split, (max(per_env, per_goal) + 48 * 1024 - 1) / (48 * 1024));
+            split = max(split, (max(per_env, per_goal) + 52 * 1024 - 1) / (52 * 1024));
         }
         int smem_obs = 0, smem_goal = 0;
         for (int pl = 0; pl < gp.store.n_planes; ++pl) {
@@ -856,7 +945,16 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
             if (gp.obs[pl]) smem_obs += per << 4;
             if (gp.goal && gp.goal_obs[pl]) smem_goal += per << 4;
         }
-        const int smem = max(smem_obs, smem_goal);
+        int smem = max(smem_obs, smem_goal), whole = 0;
+        if (split == 1) {
+            int span_o, span_g;
+            bool co, cg;
+            plane_set_bytes(gp.store, gp.obs, true, &span_o, &co);
+            plane_set_bytes(gp.store, gp.goal_obs, gp.goal != nullptr, &span_g, &cg);
+            if (co) smem = max(smem, span_o);
+            if (cg) smem = max(smem, span_g);
+            whole = (co ? 1 : 0) | (cg ? 2 : 0);
+        }
         VN_REQUIRE(smem <= 200 * 1024, "gather(bulk): %d bytes of planes per env exceed shared memory", smem);
         static int configured[kMaxDevices] = {0};  // the attribute is per device
         const int dev = current_device();
@@ -870,7 +968,7 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         static const int env_grid = getenv("VN_BULK_GRID") ? atoi(getenv("VN_BULK_GRID")) : 0;   // development
         if (env_grid > 0) grid = min(grid, env_grid);
         launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, split,
-                   (env_dynamic && gp.sched) ? gp.sched + (gp.parity & 1) : nullptr, env_hints);
+                   (env_dynamic && gp.sched) ? gp.sched + (gp.parity & 1) : nullptr, env_hints | (whole << 16));
         return check_launch("vn_gather_bulk_kernel");
     }
     set_error("gather: unknown variant %d", variant);
@@ -1016,14 +1114,16 @@ static int32_t run_fused(const vn_store_t *store, const vn_tables_t *tab, const 
 // Shared memory of one CTA of the persistent single launch (largest of the observation / goal plane sets), or 0 when
 // the batch does not qualify: needs the descriptor and scheduler scratch, whole records per CTA (no slicing) and at
 // least two CTAs per SM.
-static int32_t persistent_smem_bytes(const vn_store_t *store, const vn_step_out_t *out) {
+static int32_t persistent_smem_bytes(const vn_store_t *store, const vn_step_out_t *out, int *whole = nullptr) {
     if (!out || !out->gather_desc || !out->sched) return 0;
-    int obs = 0, goal = 0;
-    for (int pl = 0; pl < store->n_planes; ++pl) {
-        if (out->obs[pl]) obs += store->plane_bytes[pl];
-        if (out->goal_obs[pl]) goal += store->plane_bytes[pl];
-    }
-    const int smem = max(obs, goal);
+    int span_o, span_g;
+    bool co, cg;
+    const int obs = plane_set_bytes(*store, out->obs, true, &span_o, &co);
+    const int goal = plane_set_bytes(*store, out->goal_obs, true, &span_g, &cg);
+    int smem = max(obs, goal);
+    if (co) smem = max(smem, span_o);
+    if (cg) smem = max(smem, span_g);
+    if (whole) *whole = (co ? 1 : 0) | (cg ? 2 : 0);
     if (smem == 0 || smem > 52 * 1024) return 0;   // >= 4 CTAs per SM; larger records are sliced by the two-kernel path
     return smem;
 }
@@ -1053,16 +1153,20 @@ static int32_t run_persistent(const vn_store_t *store, const vn_tables_t *tab, c
             cudaFuncSetAttribute(vn_step_gather_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured[dev][reset] = smem;
     }
+    int whole = 0;
+    persistent_smem_bytes(store, out, &whole);
     static const int env_per_sm = getenv("VN_BULK_PER_SM") ? atoi(getenv("VN_BULK_PER_SM")) : 0;
-    static const int env_hints = getenv("VN_BULK_L2_HINTS") ? atoi(getenv("VN_BULK_L2_HINTS")) : 3;
+    static const int env_groups = getenv("VN_BULK_GROUPS") ? atoi(getenv("VN_BULK_GROUPS")) : VN_BULK_GROUPS_DEFAULT;
+    static const int env_hints =
+        (getenv("VN_BULK_L2_HINTS") ? atoi(getenv("VN_BULK_L2_HINTS")) : 3) | (max(1, min(7, env_groups)) << 8);
     int per_sm = max(1, min(32, (220 * 1024) / (smem + 1024)));
     if (env_per_sm > 0) per_sm = min(per_sm, env_per_sm);
     const int grid = (int)min((int64_t)envs->n_envs, (int64_t)sm_count() * per_sm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (reset)
-        launch_pdl(vn_step_gather_kernel<true>, dim3(grid), dim3(32), (size_t)smem, st, sp, gp, env_hints);
+        launch_pdl(vn_step_gather_kernel<true>, dim3(grid), dim3(32), (size_t)smem, st, sp, gp, env_hints | (whole << 16));
     else
-        launch_pdl(vn_step_gather_kernel<false>, dim3(grid), dim3(32), (size_t)smem, st, sp, gp, env_hints);
+        launch_pdl(vn_step_gather_kernel<false>, dim3(grid), dim3(32), (size_t)smem, st, sp, gp, env_hints | (whole << 16));
     return check_launch("vn_step_gather_kernel");
 }
 

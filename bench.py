@@ -559,7 +559,7 @@ def run_cuda(args):
         for i in range(k0, k0 + k):
             # the action stream is pre-computed and resident: VN_STEP_ACTIONS_READY lets the scalar part of
             # step i + 1 run while the gather of step i is still copying
-            env.step_enqueue(actions[i % n_rows], actions_ready=True)
+            env.step_enqueue(actions[i % n_rows], actions_ready=not args.serial)
 
     device_loop(0, args.mix)      # un-timed: lets the state distribution settle (random-walk mixing)
     device_loop(0, W)
@@ -952,6 +952,9 @@ def main():
     ap.add_argument("--cpu-budget", type=int, default=100_000, help="reference arm: env-steps per leg (bounded sample)")
     ap.add_argument("--cuda-graph", action="store_true", help="replay 64-step CUDA graphs in the device-resident loop")
     ap.add_argument("--quick", action="store_true", help="development: device-resident number + roofline only")
+    ap.add_argument("--serial", action="store_true", help="development: steps without VN_STEP_ACTIONS_READY (as when a policy "
+                                                          "kernel produces the actions between two steps: no overlap of the "
+                                                          "scalar part with the previous gather)")
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "rgb", "aux5"],
                     help="BASELINE.json config; c2 is the headline, the others are secondary lines")
     ap.add_argument("--hardness", default="none", help="curriculum hardness (set_complexity); 'none' = uniform starts")
