@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(kStepThreads) vn_step_kernel(const StepParams 
     // immediate predecessor - the previous gather - and what it writes for the next gather goes to the other
     // half of the double-buffered descriptor, so it runs WHILE the previous gather is still copying and only
     // waits for it at the very end (which also orders the next gather behind the previous one).
-    const bool defer_wait = (p.out.flags & VN_STEP_ACTIONS_READY) && p.out.gather_desc != nullptr;
+    const bool defer_wait = (p.out.flags & VN_STEP_ACTIONS_READY) && !(p.out.flags & VN_STEP_NO_OVERLAP) &&
+                            p.out.gather_desc != nullptr;
     if (!defer_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1228,21 +1229,27 @@ static StepMode choose_mode(const vn_store_t *store, const vn_envs_t *envs, cons
         return kModeFused;
     }
     if (variant == VN_GATHER_AUTO) {
-        // Measured on B200 (profiles/r2a_launch_modes.txt, r2c_small_batches.txt; C2 records, device-resident loop): the
-        // persistent launch wins while the batch fills at most ~3/4 of one wave of its CTAs (300 envs 9.3 -> 6.8 us per
-        // step, 512: 9.1 -> 7.1, 768: 9.2 -> 9.0) - there the step is bound by launches and dependency hops.  Beyond that
-        // the two-kernel path wins (1,024: 9.5 vs 9.9 us; 4,096: 33.3 vs 35.8; 16,384: 120 vs 137): its scalar kernel
-        // hides behind the previous gather and its tickets balance the copies, while the persistent launch exposes its
-        // stepping phase and owns envs statically.  A HOST caller (out->host_pack) always takes two kernels: the stepping
-        // phase of a persistent grid cannot become resident before the previous launch's CTAs release their shared
-        // memory, so the host would get its rewards a whole gather late, and lanes that own strided envs read / write
-        // the mapped host buffers 4 bytes at a time.
+        // Measured on B200 (profiles/r2a_launch_modes.txt, r2c_small_batches.txt, r2_serial_modes.txt; C2 records):
+        //  * PIPELINED steps (VN_STEP_ACTIONS_READY: the scalar kernel of the two-kernel path hides behind the previous
+        //    gather): the persistent launch wins while the batch fills at most ~3/4 of one wave of its CTAs (300 envs
+        //    9.3 -> 6.8 us per step, 512: 9.1 -> 7.1, 768: 9.2 -> 9.0) and loses beyond (1,024: 9.5 vs 9.9 us; 4,096: 33.3
+        //    vs 35.8) - its stepping phase is exposed;
+        //  * SERIAL steps (the actions were produced just now, e.g. by a policy kernel between two steps - nothing can
+        //    overlap the previous gather): one launch beats scalar kernel + hand-off + gather up to about four envs per CTA
+        //    (1,024 envs: 11.8 -> 10.1 us, 2,048: 19.2 -> 16.6, 4,096: 37.4 -> 36.9, RGB-only 4,096: 27.4 -> 24.9) and
+        //    loses beyond (8,192: 66.0 vs 70.2, 16,384: 122.6 vs 135.5): the two-kernel path's tickets balance skipped rows
+        //    and L2 hits, the persistent launch owns envs statically.
+        // A HOST caller (out->host_pack) always takes two kernels: the stepping phase of a persistent grid cannot become
+        // resident before the previous launch's CTAs release their shared memory, so the host would get its rewards a
+        // whole gather late, and lanes that own strided envs read / write the mapped host buffers 4 bytes at a time.
         // VN_PERSISTENT=0 / 2 (development): never / whenever the batch qualifies.
         static const int env_persistent = getenv("VN_PERSISTENT") ? atoi(getenv("VN_PERSISTENT")) : VN_PERSISTENT_DEFAULT;
         const int32_t ps = env_persistent ? persistent_smem_bytes(store, out) : 0;
         if (ps > 0) {
             const int per_sm = max(1, min(32, (220 * 1024) / (ps + 1024)));
-            const bool mid_size = !out->host_pack && 4 * (int64_t)envs->n_envs <= 3 * (int64_t)sm_count() * per_sm;
+            const int64_t wave = (int64_t)sm_count() * per_sm, n = envs->n_envs;
+            const bool pipelined = (out->flags & VN_STEP_ACTIONS_READY) != 0;
+            const bool mid_size = !out->host_pack && (pipelined ? 4 * n <= 3 * wave : n <= 4 * wave);
             if (env_persistent >= 2 || mid_size) {
                 *smem = ps;
                 return kModePersistent;
@@ -1408,6 +1415,16 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
         if (rc) return rc;
     }
     return vn::run_float_leaves(store, envs, out, stream);
+}
+
+int32_t vn_env_step_mode(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
+                         int32_t gather_variant) {
+    VN_REQUIRE(envs && envs->n_envs >= 0, "envs: null or negative n_envs");
+    int32_t rc = vn::validate_store(store);
+    if (rc) return rc;
+    int32_t smem = 0;
+    const vn::StepMode mode = vn::choose_mode(store, envs, out, gather_variant, &smem);
+    return mode == vn::kModeError ? VN_EINVAL : (int32_t)mode;
 }
 
 int32_t vn_env_host_seq_words(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,

@@ -22,6 +22,8 @@ RULE_AUTO_RESET = 0x40
 GATHER_AUTO, GATHER_LDG, GATHER_BULK, GATHER_FUSED, GATHER_PERSISTENT = 0, 1, 2, 3, 4
 STEP_ACTIONS_READY = 0x01
 STEP_SKIP_UNCHANGED = 0x02
+STEP_NO_OVERLAP = 0x04
+MODE_SPLIT, MODE_FUSED, MODE_PERSISTENT = 0, 1, 2
 ABI_VERSION = 3
 STAT_NAMES = ("episodes", "return_sum", "length_sum", "successes", "collisions", "steps", "truncations", "resets",
               "rows_skipped")
@@ -91,7 +93,7 @@ _lib = None
 
 #: every symbol include/vn_b200.h declares
 EXPORTS = ("vn_abi_version", "vn_abi_struct_size", "vn_last_error", "vn_launch_count", "vn_fill_store", "vn_env_reset", "vn_env_step", "vn_env_step_scalar",
-           "vn_env_gather", "vn_env_step_host", "vn_env_step_host_sync", "vn_env_step_host_call", "vn_debug_gather_trace", "vn_env_host_seq_words", "vn_host_wait_seq", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
+           "vn_env_gather", "vn_env_step_host", "vn_env_step_host_sync", "vn_env_step_host_call", "vn_env_step_mode", "vn_debug_gather_trace", "vn_env_host_seq_words", "vn_host_wait_seq", "vn_event_create", "vn_event_destroy", "vn_event_wait", "vn_gather_plane",
            "vn_gather_plane_f32_chw", "vn_gather_plane_f32_chw_rows", "vn_gather_leaves_f32_chw", "vn_nstep_returns", "vn_nstep_returns_scan", "vn_discounted_backup", "vn_pixel_control",
            "vn_transition_rows", "vn_gather_rows", "vn_pixel_control_list", "vn_pixel_control_returns", "vn_pixel_control_returns_from_states", "vn_replay_sample",
            "vn_aux_target", "vn_rp_labels")
@@ -136,6 +138,7 @@ def load(build_if_missing=True):
         "vn_env_step_host_call": (i32, [_P, _P, _P, _P]),
         "vn_debug_gather_trace": (i32, [_P]),
         "vn_env_host_seq_words": (i32, [S, E, O, i32]),
+        "vn_env_step_mode": (i32, [S, E, O, i32]),
         "vn_host_wait_seq": (i32, [_P, i32, C.c_uint32, _P, i64]),
         "vn_event_create": (i32, [C.POINTER(_P)]),
         "vn_event_destroy": (i32, [_P]),

@@ -331,6 +331,7 @@ class GraphVecEnv:
                 o.float_leaves = C.cast(self._float_leaves, C.c_void_p)
                 o.n_float_leaves, o.float_h, o.float_w = len(self._float_leaves), h, w
         self._pending = False
+        self._modes, self._prev_mode = {}, None
         self._hc = None
         self._h2d_done = None
         self._serial_next = False
@@ -481,15 +482,32 @@ class GraphVecEnv:
             self._convert_float_leaves()
         return self._obs_out()
 
+    def _mode_of(self, out, flags):
+        """How the library runs a call with these flags on this output block (0 two kernels / 1 fused / 2 persistent),
+        asked once per (block, pipelined or not) - under VN_GATHER_AUTO the answer depends on both."""
+        key = (id(out), bool(flags & L.STEP_ACTIONS_READY))
+        m = self._modes.get(key)
+        if m is None:
+            saved = out.flags
+            out.flags = flags
+            m = self.lib.vn_env_step_mode(C.byref(self.dw.store), C.byref(self._c_envs), C.byref(out), self.gather)
+            out.flags = saved
+            if m < 0:
+                L.check(m)
+            self._modes[key] = m
+        return m
+
     def _tick(self, out, flags):
         self._calls += 1
         out.parity = self._calls & 1
-        if self._serial_next:
-            # the previous launch on this env was a graph replay: its descriptor parity is not the host's, so this
-            # step must not overlap that gather
-            flags &= ~L.STEP_ACTIONS_READY
-            self._serial_next = False
+        if flags & L.STEP_ACTIONS_READY and (self._serial_next or self._prev_mode != L.MODE_SPLIT):
+            # A pipelined step's scalar kernel overlaps the launch before it.  That is only sound when that launch is the
+            # gather half of this env batch's previous two-kernel step; after a reset, a one-launch step (which WRITES the
+            # env state this step reads) or a graph replay (whose descriptor parity is not the host's) it waits instead.
+            flags |= L.STEP_NO_OVERLAP
+        self._serial_next = False
         out.flags = flags
+        self._prev_mode = self._mode_of(out, flags)
 
     def step_async(self, actions, actions_ready=False):
         """``actions_ready=True`` promises that the action buffer was complete before the previous step's
@@ -681,10 +699,12 @@ class GraphVecEnv:
             out = self._c_out_host
             self._calls += 1
             out.parity = self._calls & 1
-            if self._serial_next:       # the previous launch was a graph replay: do not overlap its gather
-                out.flags, self._serial_next = self._step_flags, False
+            if self._serial_next or self._prev_mode != L.MODE_SPLIT:    # see _tick
+                out.flags = L.STEP_ACTIONS_READY | L.STEP_NO_OVERLAP | self._step_flags
+                self._serial_next = False
+                self._prev_mode = self._mode_of(out, out.flags)
             else:
-                out.flags = L.STEP_ACTIONS_READY | self._step_flags
+                out.flags = L.STEP_ACTIONS_READY | self._step_flags     # previous and this step: two kernels (host caller)
             self._seq = out.seq = (self._seq % 0x7FFFFFFF) + 1
             self._next_pack()
             res = np.empty(5 * n, np.uint8)         # rewards (4n bytes) + dones (n bytes) in one allocation

@@ -543,7 +543,7 @@ def run_cuda(args):
 
     graph_len = 0
     l0 = env.kernel_launches
-    env.step_enqueue(actions[0])
+    env.step_enqueue(actions[0], actions_ready=not args.serial)
     launches_per_step = env.kernel_launches - l0        # 1 (one fused launch) or 2 (scalar + gather)
     if args.cuda_graph:
         # launch-bound batches (C1): replay CUDA graphs of `graph_len` steps instead of 2 launches per step

@@ -54,6 +54,10 @@ extern "C" {
                                       call's gather was enqueued (e.g. a pre-computed action stream, or host actions
                                       written after the previous ready_event): with gather_desc set, the scalar
                                       kernel then overlaps the previous gather instead of waiting for it */
+#define VN_STEP_NO_OVERLAP 0x04 /* with VN_STEP_ACTIONS_READY: the step is still part of a pipelined loop (which decides how
+                                   VN_GATHER_AUTO runs it) but must NOT overlap the launch before it - that launch was not the
+                                   gather half of these envs' previous two-kernel step (it was a reset, a one-launch step, a
+                                   graph replay, ...) and may still be writing the env state this step reads */
 #define VN_STEP_SKIP_UNCHANGED 0x02 /* the caller guarantees that out->obs[] are the SAME buffers as in the previous
                                        reset / step call on these envs and that nothing else wrote to them: the row of
                                        an env whose record did not change (collision, no-op action) is then not copied
@@ -272,6 +276,13 @@ int32_t vn_env_step_host(const vn_store_t *store, const vn_tables_t *tables, con
                          const vn_rules_t *rules, const vn_inject_t *inject, const int32_t *host_actions,
                          int32_t *dev_actions_copy, const vn_step_out_t *out, void *ready_event,
                          int32_t gather_variant, void *stream);
+/* How vn_env_reset / vn_env_step / vn_env_step_host would run for these arguments (out->flags and out->host_pack
+ * matter under VN_GATHER_AUTO): 0 = scalar kernel + gather kernel, 1 = CTA-per-env fused launch, 2 = persistent launch;
+ * negative on error.  A caller that pipelines steps (VN_STEP_ACTIONS_READY) uses it to know whether the PREVIOUS call
+ * ended in a gather kernel it may overlap (mode 0) or not (then it adds VN_STEP_NO_OVERLAP). */
+int32_t vn_env_step_mode(const vn_store_t *store, const vn_envs_t *envs, const vn_step_out_t *out,
+                         int32_t gather_variant);
+
 /* Number of host_seq words vn_env_step_host will publish for this batch (= thread blocks of its scalar half:
  * one per env when the step runs as the fused launch, ONE for the persistent launch, one per 128 envs otherwise);
  * <= 0 on error. */
