@@ -710,6 +710,17 @@ def run_cuda(args):
             r.update({"traffic": tr, "dram_frac": tr / (r["ms_per_step"] * 1e-3) / 1e9 / peak})
         secondary["rgb_only"] = r
         del env_r
+        # the same steps WITHOUT the promise that the actions were ready early - what a training loop with a GPU policy
+        # between two steps gets: nothing can overlap the previous gather, VN_GATHER_AUTO runs the step as ONE launch
+        env_s = vn.GraphVecEnv(world, n_total, seed=5, obs_layout=layout, host_outputs=False, device_world=env.dw, **mk)
+        env_s.reset()
+        [env_s.step_enqueue(act(i)) for i in range(300)]
+        l0 = env_s.kernel_launches
+        sr_ = H.steps_per_s(lambda i: env_s.step_enqueue(act(i)), 500, n_total)
+        sr_.update({"launches_per_step": (env_s.kernel_launches - l0) / (500.0 * (sr_["blocks"] + 2) + 50),
+                    "note": "serial steps (no VN_STEP_ACTIONS_READY): persistent single launch"})
+        secondary["serial_steps"] = sr_
+        del env_s
         # float32 CHW observations in [0, 1] - what the reference's wrappers hand to its model (TransposeImage +
         # ScaledFloatFrame, thor_cached_auxiliary.py:61-62) - converted straight from the store into persistent
         # batches (no uint8 batch in this mode): 4 bytes written per byte read

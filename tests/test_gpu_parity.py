@@ -1387,3 +1387,52 @@ def test_host_route_equals_device_route_for_any_action_value():
         assert torch.equal(rec[0], rec[1]) and np.array_equal(rec[0].cpu().numpy(), a), t
         assert torch.equal(host.actions_dev, torch.from_numpy(a).cuda()), t      # the device copy of the host's actions
     assert host.episode_stats() == dev.episode_stats()
+
+
+def test_auto_mode_switches_between_launch_modes_safely():
+    """Under VN_GATHER_AUTO the launch mode of a step depends on whether it is pipelined (VN_STEP_ACTIONS_READY) - serial
+    steps of a few thousand envs run as the persistent single launch, pipelined ones as scalar kernel + gather - so one
+    env batch may switch modes from step to step.  A pipelined scalar kernel may only overlap its own batch's previous
+    GATHER, never a one-launch step that is still writing the env state it reads (VN_STEP_NO_OVERLAP, set by the
+    wrapper from the previous call's mode).  Random mode switching, resets and graph replays in between: every step
+    equals an always-serial two-kernel twin."""
+    import torch
+    scene = H.scenes.make_thor_scene(150, (16, 20), seed=1, n_goals=3, planes=("rgb", "depth"))
+    world = T.compile_world([scene], T.GYM_GRAPH)
+    N, S = 3000, 300
+    ref = vn.GraphVecEnv(world, N, seed=6, max_episode_steps=11, host_outputs=False, obs_layout="rgbd_goal", gather="bulk")
+    auto = vn.GraphVecEnv(world, N, seed=6, max_episode_steps=11, host_outputs=False, obs_layout="rgbd_goal",
+                          device_world=ref.dw)
+    ref.reset()
+    auto.reset()
+    rng = np.random.RandomState(0)
+    acts = torch.randint(0, 4, (S, N), device="cuda", dtype=torch.int32)
+    graph = auto.capture_steps(acts[:3])
+    modes = set()
+    t = 0
+    while t < S - 3:
+        if rng.rand() < 0.05:                                   # a 3-step graph replay in the middle
+            acts[:3].copy_(acts[t:t + 3])
+            graph.replay()
+            for k in range(3):
+                ref.step_enqueue(acts[t + k])
+            t += 3
+        else:
+            ready = bool(rng.rand() < 0.5)
+            auto.step_enqueue(acts[t], actions_ready=ready)
+            modes.add((ready, auto._prev_mode))
+            ref.step_enqueue(acts[t])
+            t += 1
+        if rng.rand() < 0.02:
+            mask = torch.from_numpy(rng.rand(N) < 0.3).cuda()
+            auto.reset(mask)
+            ref.reset(mask)
+        if t % 7 == 0:
+            torch.cuda.synchronize()
+            assert torch.equal(ref._pack, auto._pack) and torch.equal(ref.state, auto.state), t
+            for x, y in zip(list(ref.obs_buf.values()) + list(ref.goal_buf.values()),
+                            list(auto.obs_buf.values()) + list(auto.goal_buf.values())):
+                assert torch.equal(x, y), t
+    # both modes were exercised: serial -> persistent launch, pipelined -> two kernels
+    assert (False, vn.lib.MODE_PERSISTENT) in modes and (True, vn.lib.MODE_SPLIT) in modes
+    assert ref.episode_stats()["episodes"] > N

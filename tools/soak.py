@@ -22,6 +22,7 @@ def main(steps=200000, block=1000):
                         ("fused 200 envs", 200, dict(obs_layout="aux5")),
                         ("persistent launch 600 envs", 600, dict(obs_layout="rgbd_goal")),
                         ("persistent launch 3000 envs", 3000, dict(obs_layout="rgbd_goal", gather="persistent")),
+                        ("auto, random serial / pipelined", 3000, dict(obs_layout="rgbd_goal")),
                         ("hardness 0.01 (reset-heavy)", 4096, dict(obs_layout="rgbd_goal"))):
         env = vn.GraphVecEnv(world, n, seed=11, max_episode_steps=37, host_outputs=False, device_world=dw, **kw)
         if "hardness" in name:
@@ -30,8 +31,10 @@ def main(steps=200000, block=1000):
         acts = torch.randint(0, 4, (1024, n), device="cuda", dtype=torch.int32)
         t0 = time.perf_counter()
         for b0 in range(0, steps, block):
+            mixed = name.startswith("auto, random")
+            flips = torch.rand(block).tolist() if mixed else None
             for i in range(block):
-                env.step_enqueue(acts[(b0 + i) % 1024], actions_ready=True)
+                env.step_enqueue(acts[(b0 + i) % 1024], actions_ready=(flips[i] < 0.5) if mixed else True)
             torch.cuda.synchronize()
             s, g = env.state.long(), env.goal.long()
             if env.scaled_float:
