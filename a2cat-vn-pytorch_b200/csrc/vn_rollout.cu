@@ -712,9 +712,18 @@ struct ReplayParams {
 // transition except possibly the last one ends an episode (sequences never straddle an episode boundary).
 // In RP mode the window is 3 history transitions + the transition whose reward is classified, and the
 // candidates are split by that reward being zero / non-zero (50/50 skewed sampling).
+//
+// One WARP per env: the ring column is scanned 32 slots at a time.  A window ending at transition i is valid iff
+// i >= L - 1 and the last episode end strictly before i lies before the window (index < i - L + 1); "the last episode
+// end before i" is a prefix maximum, taken inside a chunk from the ballot of the done bits (31 - clz of the bits below
+// the lane) and across chunks from a carried index.  Pass 0 counts the valid windows per class with ballot + popc, pass
+// 1 walks the chunks again until the running count passes the drawn rank and picks the bit with __fns - the k-th valid
+// window in chronological order, exactly what the one-thread-per-env loop of round 1 selected, in O(cap / 32) steps
+// instead of O(cap).
 __global__ void __launch_bounds__(128) vn_replay_sample_kernel(const ReplayParams p) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.n) return;
+    const int lane = threadIdx.x & 31;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= p.n) return;   // whole warps leave together
     const int L = p.mode == 1 ? 4 : p.length;
     const int oldest = (p.head - p.count + p.cap) % p.cap;
     const Philox4 d = philox4x32_10((uint32_t)(p.env_id_base + e), p.call, 0x5EB1A7u, (uint32_t)p.mode,
@@ -733,30 +742,37 @@ __global__ void __launch_bounds__(128) vn_replay_sample_kernel(const ReplayParam
             }
             want = (int)__umulhi(d.v[0], (uint32_t)n_valid[cls]);
         }
-        int clean = 0;  // consecutive non-terminal transitions ending just before the current one
-        int seen[2] = {0, 0};
-        for (int i = 0; i < p.count; ++i) {
-            const int slot = (oldest + i) % p.cap;
-            // window [i - L + 1, i] ends at i: valid iff the L - 1 transitions before i are non-terminal
-            if (i >= L - 1 && clean >= L - 1) {
-                int c = 0;
-                if (p.mode == 1) c = p.reward[(size_t)slot * p.n + e] != 0.0f;
-                if (pass == 0) {
-                    n_valid[c]++;
-                } else if (c == cls) {
-                    if (seen[c] == want) {
-                        start = i - L + 1;
-                        break;
-                    }
-                    seen[c]++;
+        int carry = -1;   // chronological index of the last episode end seen in earlier chunks
+        int seen = 0;     // valid windows of class `cls` in earlier chunks (pass 1)
+        for (int base = 0; base < p.count; base += 32) {
+            const int i = base + lane;
+            const bool in = i < p.count;
+            const size_t at = (size_t)((oldest + (in ? i : 0)) % p.cap) * p.n + e;
+            const bool dn = in && p.done[at] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, dn);
+            const unsigned below = m & ((1u << lane) - 1u);
+            const int last = below ? base + 31 - __clz((int)below) : carry;
+            const bool valid = in && i >= L - 1 && last < i - L + 1;
+            const int c = (p.mode == 1 && valid) ? (p.reward[at] != 0.0f) : 0;
+            if (pass == 0) {
+                n_valid[0] += __popc(__ballot_sync(0xffffffffu, valid && c == 0));
+                n_valid[1] += __popc(__ballot_sync(0xffffffffu, valid && c == 1));
+            } else {
+                const unsigned b = __ballot_sync(0xffffffffu, valid && c == cls);
+                const int here = __popc(b);
+                if (seen + here > want) {
+                    start = base + (int)__fns(b, 0, want - seen + 1) - L + 1;
+                    break;
                 }
+                seen += here;
             }
-            clean = p.done[(size_t)slot * p.n + e] ? 0 : clean + 1;
+            if (m) carry = base + 31 - __clz((int)m);
         }
     }
-    p.o_start[e] = start;
+    if (lane == 0) p.o_start[e] = start;
     if (start < 0) return;
-    for (int k = 0; k < L; ++k) {
+    // lanes write the L transitions (and the closing observation) of the window
+    for (int k = lane; k < L; k += 32) {
         const size_t at = (size_t)((oldest + start + k) % p.cap) * p.n + e;
         p.o_states[(size_t)e * (L + 1) + k] = p.before[at];
         // goal of the episode the BEFORE observation belongs to (ring.goal is the goal after the step, i.e. the next
@@ -1048,7 +1064,7 @@ int32_t vn_replay_sample(const vn_replay_t *ring, int32_t length, int32_t mode, 
     p.o_dones = o_dones;
     p.o_start = o_start;
     p.o_label = o_label;
-    vn::vn_replay_sample_kernel<<<(ring->n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    vn::vn_replay_sample_kernel<<<(ring->n + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);   // warp per env
     return vn::check_launch("vn_replay_sample_kernel");
 }
 
