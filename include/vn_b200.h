@@ -221,7 +221,10 @@ typedef struct vn_step_out {
                                 persistent grid of one-warp CTAs, each owning a fixed set of envs - its lanes step them,
                                 then lane 0 moves their records with bulk copies.  Needs out->gather_desc and out->sched
                                 and plane sets of at most 52 KB per env; a host caller polls ONE host_seq word.  In the
-                                gather-only entry points it means VN_GATHER_BULK. */
+                                gather-only entry points it means VN_GATHER_BULK.  VN_GATHER_AUTO picks it beyond the
+                                fused launch's wave for device callers: serial steps (no VN_STEP_ACTIONS_READY) of up to
+                                four envs per CTA, pipelined steps of up to 3/4 of a wave; a host caller (out->host_pack)
+                                and everything larger run as scalar kernel + gather kernel.  vn_env_step_mode tells. */
 
 int32_t vn_abi_version(void);
 /* sizeof of the descriptor structs as compiled into the library (0 store, 1 tables, 2 envs, 3 rules, 4 inject,
