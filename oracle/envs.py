@@ -308,3 +308,60 @@ class ThorCachedEnv:
         state = self._pack(obs, goal) if not terminal else self.last_state
         self.last_state = state
         return state, reward, terminal, dict()
+
+
+class ThorCachedTasksEnv:
+    """environments/gym_thor_cached.py:7-95 THORCachedEnv - the UNFINISHED multi-scene rewrite of cached.py - restated
+    as written: ``tasks = [(scene_name, goal_state)]``; ``reset`` (:45-50) draws a task, loads its scene and samples a
+    start by rejection on ``shortest_path_distance[start][goal] > 0`` (:37-43); ``observe`` (:52-53) returns the RAW uint8
+    ``(obs, goal)`` pair; ``process`` (:72-95) is cached.py's step with a ``{'image', 'goal'}`` dict of float32 / 255
+    frames and the previous dict on a terminal step.  The class never sets the attributes ``process`` reads; they are
+    kept in step with ``state`` / ``goal`` here exactly as oracle/ref_harness.A8Driver does for the reference, which is
+    how tests/golden/thor_cached_tasks.npz was recorded.  ``scenes``: name -> dict(transition_graph, observations,
+    shortest_path_distances)."""
+    reward_configuration = (1.0, 0.0, 0.0)                                           # :68-70
+
+    def __init__(self, scenes, tasks):
+        self.scenes, self.tasks = scenes, tasks
+        self.reset_source = None
+        self.last_state = None
+
+    @staticmethod
+    def _preprocess_frame(image):                                                    # :57-61 (same-size resize)
+        return image.astype(np.float32) / 255.0
+
+    def reset(self):                                                                 # :45-50
+        choice, start = self.reset_source()
+        scene_id, self.goal = self.tasks[choice % len(self.tasks)]
+        self.current_scene = self.scenes[scene_id]
+        assert self.current_scene["shortest_path_distances"][start][self.goal] > 0  # _sample_start :37-43
+        self.state = int(start)
+        ob = self.observe()
+        self.last_state = {"image": self._preprocess_frame(ob[0]), "goal": self._preprocess_frame(ob[1])}
+        return ob
+
+    def observe(self):                                                               # :52-53
+        o = self.current_scene["observations"]
+        return o[self.state], o[self.goal]
+
+    def step(self, action):                                                          # process, :72-95
+        graph = self.current_scene["transition_graph"]
+        collided = False
+        if graph[self.state][action] != -1:
+            self.state = int(graph[self.state][action])
+        else:
+            collided = True
+        o = self.current_scene["observations"]
+        obs, goal = o[self.state], o[self.goal]
+        terminal = self.goal == self.state
+        reward = -self.reward_configuration[1]
+        if terminal:
+            reward = self.reward_configuration[0]
+        if collided:
+            reward = self.reward_configuration[2]
+        if not terminal:
+            state = {"image": self._preprocess_frame(obs), "goal": self._preprocess_frame(goal)}
+        else:
+            state = self.last_state
+        self.last_state = state
+        return state, reward, terminal, dict()

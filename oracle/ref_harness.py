@@ -152,6 +152,59 @@ def ref_modules():
     return m
 
 
+def ref_thor_cached_tasks():
+    """environments/gym_thor_cached.py (THORCachedEnv, the UNFINISHED multi-scene rewrite of cached.py) imported
+    unmodified.  As written the module cannot run: ``np`` and ``resize`` are used without being imported (:59-61), and
+    ``process`` (:72-95) reads ``_transition_graph`` / ``_current_state_idx`` / ``_current_goal_idx`` / ``last_state``,
+    which nothing in the class ever sets.  The harness supplies exactly those missing names and nothing else:
+
+      * module globals ``np`` (numpy) and ``resize`` (the same-size stand-in of skimage.transform.resize used for
+        cached.py: identity on a float image of the requested size);
+      * ``h5py.File`` reads the in-memory registry (``THOR_DATASET_PATH=mem:`` -> ``mem:/<scene>.h5``);
+      * ``A8Driver`` below keeps the four attributes in step with ``state`` / ``goal`` / ``current_scene`` around every
+        ``process`` call, the way the finished predecessor keeps its own (cached.py:49-57, 76-97).
+
+    ``reset`` / ``_sample_start`` / ``observe`` / ``process`` themselves execute as they are in the reference."""
+    install()
+    os.environ["THOR_DATASET_PATH"] = "mem:"
+    mod = importlib.import_module("environments.gym_thor_cached")
+    mod.np = np
+    mod.resize = lambda image, size, anti_aliasing=True: _same_size(image, size)
+    return mod
+
+
+def _same_size(image, size):
+    assert tuple(image.shape[:2]) == tuple(size), "harness only supports same-size frames"
+    return image
+
+
+class A8Driver:
+    """Single-env ``reset() / step(a)`` surface over an unmodified THORCachedEnv instance (see ref_thor_cached_tasks)."""
+
+    def __init__(self, env):
+        self.e = env
+
+    def _sync(self):
+        e = self.e
+        e._transition_graph = e.current_scene["transition_graph"]
+        e._current_state_idx, e._current_goal_idx = e.state, e.goal
+
+    def reset(self):
+        e = self.e
+        ob = e.reset()                                   # :45-50 + observe() :52-53: raw uint8 (obs, goal)
+        self._sync()
+        e.last_state = {"image": e._preprocess_frame(ob[0]), "goal": e._preprocess_frame(ob[1])}
+        return ob
+
+    def step(self, action):
+        e = self.e
+        self._sync()
+        state, reward, terminal, info = e.process(action)        # :72-95, unmodified
+        e.state = int(e._current_state_idx)
+        e.last_state = state
+        return state, reward, terminal, info
+
+
 def ref_aux_trainer():
     """experiments/ai2_auxiliary/trainer.py with ``deep_rl`` stubbed; ``autocrop_observations``
     is OUR restatement (oracle.rollout.autocrop_observations) because deep_rl is absent -

@@ -409,6 +409,67 @@ def gen_aux_target(ref_trainer):
     save("aux_target", x_seed=7, y20=y20, y21=y21, yd=yd)
 
 
+def thor_cached_task_scenes():
+    return [scenes.make_maze_scene((7, 8), 0.2, 51, n_goals=1, planes=("rgb",), scene_id=0),
+            scenes.make_maze_scene((6, 9), 0.25, 52, n_goals=1, planes=("rgb",), scene_id=1)]
+
+
+def gen_thor_cached_tasks(ref):
+    """environments/gym_thor_cached.py THORCachedEnv (the unfinished multi-scene class) run AS WRITTEN on
+    two synthetic scenes and a task list, through oracle/ref_harness.A8Driver (which only supplies the names the class
+    never defines).  Pins: task choice from the (scene, goal) list (:47), start sampling by rejection on
+    shortest_path_distance > 0 (:37-43), the raw uint8 (obs, goal) pair of observe() (:52-53), and process() (:72-95):
+    reward / terminal rules and the {'image', 'goal'} dict of float32 / 255 frames, previous dict on a terminal step."""
+    from oracle import graph_util as gu
+    mod = rh.ref_thor_cached_tasks()
+    scs = thor_cached_task_scenes()
+    names = ["sceneA", "sceneB"]
+    for name, gs in zip(names, scs):
+        dist, _ = ref.util.compute_shortest_path_data(gs.maze)
+        locs, graph, spd = gu.h5_tables(gs.maze, dist)
+        rh.FakeH5File.registry["mem:/%s.h5" % name] = dict(observation=gs.plane_frames("rgb"),
+                                                           location=np.zeros((len(locs) * 4, 2)), graph=graph,
+                                                           shortest_path_distance=spd)
+    tasks = [("sceneA", 7), ("sceneB", 30), ("sceneA", 61), ("sceneB", 2)]
+    n_envs, T, max_steps = 6, 400, 25
+    rng = np.random.RandomState(61)
+    actions = rng.randint(0, 4, size=(T, n_envs)).astype(np.int32)
+    actions[rng.rand(T, n_envs) < 0.3] = 0
+    log = ResetLog(n_envs)
+    drivers = []
+    for i in range(n_envs):
+        e = mod.THORCachedEnv(tasks, image_size=(84, 84))       # __init__ resets once with its own unseeded Random
+        e._random = rh.InjectedRandom(np.random.RandomState(70 + i).randint(0, 1 << 30, size=100000))
+        drivers.append(rh.A8Driver(e))
+
+    def on_reset(i, d):
+        e = d.e
+        scene_name = [n for n in names if e.scenes.get(n) is e.current_scene][0]
+        log.choice[i].append(tasks.index((scene_name, e.goal)))
+        log.start[i].append(int(e.state))
+
+    class _Leaves:                     # drive() records tuple observations leaf by leaf
+        def __init__(self, d):
+            self.d, self.e = d, d.e
+
+        def reset(self):
+            return self.d.reset()
+
+        def step(self, a):
+            st, r, term, info = self.d.step(a)
+            return (st["image"], st["goal"]), r, term, info
+
+    rec = drive([_Leaves(d) for d in drivers], actions, max_steps, 2, None, get_state=lambda w: int(w.e.state),
+                on_reset=lambda i, w: on_reset(i, w.d))
+    c, s, cnt = log.pack(1)
+    save("thor_cached_tasks", actions=actions, max_episode_steps=max_steps,
+         task_scene=np.array([names.index(n) for n, _ in tasks], np.int32), task_goal=np.array([g for _, g in tasks], np.int32),
+         reset_choice=c, reset_start=s[:, :, 0], reset_count=cnt,
+         **{"maze%d" % k: gs.maze for k, gs in enumerate(scs)},
+         **{"frame_seed%d" % k: gs.frame_seed for k, gs in enumerate(scs)},
+         **rec)
+
+
 def trainer_contract_scene():
     """The synthetic stand-in for 'thor-cached-212-174' (download.py:21-29): native 174 x 174 frames."""
     return scenes.make_maze_scene((6, 6), 0.2, 11, n_goals=1, frame_hw=(174, 174))
@@ -514,3 +575,4 @@ if __name__ == "__main__":
     gen_thor_cached(ref)
     gen_aux_target(rh.ref_aux_trainer())
     gen_trainer_contract(ref)
+    gen_thor_cached_tasks(ref)

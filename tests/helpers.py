@@ -183,3 +183,9 @@ def check_trainer_contract_run(g, env, crc_of_leaf, complexity_setter):
             else:
                 assert "episode" not in infos[i]
     assert g["dones"].sum() > 100
+
+
+def thor_cached_task_scenes(g):
+    """The two synthetic scenes of tests/golden/thor_cached_tasks.npz (make_golden.thor_cached_task_scenes)."""
+    return [scenes.GridScene(g["maze%d" % k], [], True, (84, 84), ("rgb",), frame_seed=int(g["frame_seed%d" % k]),
+                             scene_id=k) for k in range(2)]

@@ -1436,3 +1436,43 @@ def test_auto_mode_switches_between_launch_modes_safely():
     # both modes were exercised: serial -> persistent launch, pipelined -> two kernels
     assert (False, vn.lib.MODE_PERSISTENT) in modes and (True, vn.lib.MODE_SPLIT) in modes
     assert ref.episode_stats()["episodes"] > N
+
+
+def test_golden_thor_cached_task_list_as_written():
+    """the reference's unfinished multi-scene THORCachedEnv (environments/gym_thor_cached.py), run AS
+    WRITTEN through the harness (tests/golden/thor_cached_tasks.npz: two scenes, four (scene, goal) tasks).  The device
+    path - two scenes resident in one store, `obs_layout="dict"`, THOR_CACHED rules - reproduces task choices, states,
+    rewards (the -0.0 of :80 included), terminals, truncations and the observation bytes: the uint8 frames equal the
+    raw pair of observe() (:52-53) and, divided by 255 in float32, the {'image', 'goal'} dict of process() (:89-92)."""
+    g = H.load("thor_cached_tasks")
+    scs = H.thor_cached_task_scenes(g)
+    tasks = [(int(s), int(gl)) for s, gl in zip(g["task_scene"], g["task_goal"])]
+    world = T.compile_world(scs, T.THOR_CACHED, tasks=tasks)
+    actions = g["actions"]
+    Tn, N = actions.shape
+    base = world.scene_base
+    starts = np.zeros_like(g["reset_start"])
+    for i in range(N):
+        for k in range(int(g["reset_count"][i])):
+            starts[i, k] = int(base[tasks[int(g["reset_choice"][i, k])][0]]) + int(g["reset_start"][i, k])
+    env = vn.GraphVecEnv(world, N, max_episode_steps=int(g["max_episode_steps"]), obs_layout="dict", unreal_wrapper=False,
+                         env_tasks=np.tile(np.array([[0, len(tasks)]], np.int32), (N, 1)), inject=(g["reset_choice"], starts))
+    local = lambda e: [int(s) - int(base[world.scene_of_state(int(s))]) for s in e.state.cpu().numpy()]
+    u8 = lambda ob, i: [H.crc(ob["image"][i].cpu().numpy()), H.crc(ob["goal"][i].cpu().numpy())]
+    f32 = lambda ob, i: [H.crc(ob["image"][i].cpu().numpy().astype(np.float32) / 255.0),
+                         H.crc(ob["goal"][i].cpu().numpy().astype(np.float32) / 255.0)]
+    ob = env.reset()
+    assert local(env) == g["reset_states"].tolist()
+    assert [u8(ob, i) for i in range(N)] == g["reset_obs_crc"].tolist()
+    for t in range(Tn):
+        ob, r, d, infos = env.step(actions[t])
+        h = infos._host()
+        assert np.array_equal(d, g["dones"][t]) and np.array_equal(h["truncated"] == 1, g["truncated"][t]), t
+        assert np.array_equal(d & ~(h["truncated"] == 1), g["env_dones"][t]), t
+        assert np.array_equal(f32bits(r), f32bits(g["rewards"][t])), t            # bitwise: -0.0 on plain steps
+        assert [int(s) - int(base[world.scene_of_state(int(s))]) for s in h["info_state"]] == g["states"][t].tolist(), t
+        assert local(env) == g["post_states"][t].tolist(), t
+        # after a reset the golden holds the raw uint8 pair of observe(), otherwise process()'s float32 / 255 dict
+        want = g["obs_crc"][t].tolist()
+        assert [(u8 if d[i] else f32)(ob, i) for i in range(N)] == want, t
+    assert env.episode_stats()["episodes"] == g["dones"].sum() and g["env_dones"].sum() >= 3

@@ -186,3 +186,63 @@ def test_trainer_contract_oracle_wrapper_stack():
     assert tuple(sp.spaces[1].shape) == tuple(g["space_lar_shape"]) and env.action_space.n == int(g["action_n"])
     assert [sp.spaces[0].spaces[0].shape[0], env.action_space.n] == g["model_args"].tolist()
     H.check_trainer_contract_run(g, env, lambda x, i: H.crc(x[i]), lambda c: env.call_unwrapped("set_complexity", c))
+
+
+def test_thor_cached_task_list_env_as_written():
+    """tests/golden/thor_cached_tasks.npz: the reference's unfinished THORCachedEnv (gym_thor_cached.py) run as written on
+    two scenes and four (scene, goal) tasks.  The oracle restatement reproduces task choices, start states, rewards
+    (-0.0 included), terminals, time-limit truncations and the bytes of both observation forms: the raw uint8 pair of
+    observe() after a reset and the float32 / 255 dict of process()."""
+    g = H.load("thor_cached_tasks")
+    scs = H.thor_cached_task_scenes(g)
+    tables = {}
+    for k, sc in enumerate(scs):
+        dist, _ = gu.compute_shortest_path_data(sc.maze)
+        _, graph, spd = gu.h5_tables(sc.maze, dist)
+        tables[k] = dict(transition_graph=graph, observations=sc.plane_frames("rgb"), shortest_path_distances=spd)
+    tasks = [(int(s), int(gl)) for s, gl in zip(g["task_scene"], g["task_goal"])]
+
+    class Leaves:
+        def __init__(self, e):
+            self.e = e
+
+        def __getattr__(self, name):
+            return getattr(self.e, name)
+
+        def reset(self):
+            return self.e.reset()
+
+        def step(self, a):
+            st, r, term, info = self.e.step(a)
+            return (st["image"], st["goal"]), r, term, info
+
+    def make(i):
+        e = Leaves(oenvs.ThorCachedTasksEnv(tables, tasks))
+        return e
+
+    actions = g["actions"]
+    T_, N = actions.shape
+    envs = []
+    for i in range(N):
+        e = make(i)
+        e.e.reset_source = H.StreamSource(g["reset_choice"][i], g["reset_start"][i], g["reset_count"][i])
+        envs.append(e)
+    leafs = lambda ob: [H.crc(x) for x in ob]
+    assert np.array_equal(np.array([leafs(e.reset()) for e in envs], np.uint32), g["reset_obs_crc"])
+    assert [e.e.state for e in envs] == g["reset_states"].tolist()
+    elapsed = [0] * N
+    for t in range(T_):
+        for i, e in enumerate(envs):
+            ob, r, d, info = e.step(int(actions[t, i]))
+            assert e.e.state == g["states"][t, i] and bool(d) == bool(g["env_dones"][t, i]), (t, i)
+            elapsed[i] += 1
+            trunc = False
+            if elapsed[i] >= int(g["max_episode_steps"]):
+                trunc, d = not d, True
+            if d:
+                ob = e.reset()
+                elapsed[i] = 0
+            assert trunc == bool(g["truncated"][t, i]) and bool(d) == bool(g["dones"][t, i]), (t, i)
+            assert np.float64(r).view(np.uint64) == g["rewards"][t, i].view(np.uint64), (t, i)
+            assert leafs(ob) == g["obs_crc"][t, i].tolist() and e.e.state == g["post_states"][t, i], (t, i)
+    assert g["env_dones"].sum() >= 3 and np.signbit(g["rewards"][g["rewards"] == 0]).any()

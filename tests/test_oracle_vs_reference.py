@@ -33,8 +33,9 @@ def test_committed_goldens_reproduce_from_live_reference(tmp_path, capsys):
     mg.gen_thor_cached(ref)
     mg.gen_aux_target(rh.ref_aux_trainer())
     mg.gen_trainer_contract(ref)
+    mg.gen_thor_cached_tasks(ref)
     names = sorted(f for f in os.listdir(H.GOLDEN) if f.endswith(".npz"))
-    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz")) and len(names) == 10
+    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz")) and len(names) == 11
     for f in names:
         a, b = np.load(os.path.join(H.GOLDEN, f)), np.load(os.path.join(tmp_path, f))
         assert sorted(a.files) == sorted(b.files), f
