@@ -625,14 +625,18 @@ class GraphVecEnv:
         """Points the step about to be enqueued at the other pinned host pack.  An `infos` object of two steps ago that
         is still alive and still reads that pack in place gets its private copy first."""
         s = self._slot = self._slot ^ 1
+        self._release_pack(s)
+        self._c_out_host.host_pack = self._pack_ptrs[s]
+        self._pack_np = self._pack_nps[s]
+
+    def _release_pack(self, s):
+        """Pinned host pack `s` is about to be overwritten: an `infos` object still reading it in place copies it first."""
         ref = self._infos_refs[s]
         if ref is not None:
             old = ref()
             if old is not None:
                 old._snapshot()
             self._infos_refs[s] = None
-        self._c_out_host.host_pack = self._pack_ptrs[s]
-        self._pack_np = self._pack_nps[s]
 
     def _host_results(self, reward, done, noop):
         """(rewards, dones, infos) of the host-facing step whose scalars have just arrived in the current pack."""
@@ -663,6 +667,7 @@ class GraphVecEnv:
             return (self._obs_out(),) + self._host_results(h[:4 * n].view(np.float32).copy(),
                                                            h[16 * n:17 * n].view(np.bool_).copy(), noop)
         if self.host_outputs:
+            self._release_pack(0)
             self._pack_hosts[0].copy_(self._pack, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
             h = self._unpack(self._pack_nps[0].copy())
