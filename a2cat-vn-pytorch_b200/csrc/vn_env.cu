@@ -18,6 +18,9 @@
 #ifndef VN_BULK_GROUPS_DEFAULT
 #define VN_BULK_GROUPS_DEFAULT 1  // chunks (own mbarrier each) per record slice in the bulk copies, see bulk_copy_slice
 #endif
+#ifndef VN_BULK_TAIL_DEFAULT
+#define VN_BULK_TAIL_DEFAULT 1  // slices per record for the last wave's worth of envs of a bulk gather (1 = whole records)
+#endif
 #ifndef VN_PERSISTENT_DEFAULT
 #define VN_PERSISTENT_DEFAULT 1  // VN_GATHER_AUTO beyond one wave: 0 never, 1 mid-size device-resident batches, 2 always
 #endif
@@ -535,8 +538,12 @@ __device__ __forceinline__ void bulk_copy_slice(const vn_store_t &st, const uint
     bulk_commit();
 }
 
-__global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p, int split, unsigned int *sched,
-                                                            int hint_mode) {
+// Work units: envs [0, n_whole) are one unit each (the whole record); every env from n_whole on is cut into `split`
+// slices, one unit per slice.  n_whole = 0: every record sliced (small batches, records larger than shared memory
+// allows); n_whole = n: no slicing; in between: only the LAST units of a launch are small ("guided" scheduling - the
+// spread of the last units' durations is what a launch pays at its end).
+__global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p, int split, int n_whole,
+                                                            unsigned int *sched, int hint_mode) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar[kCopyGroups];
     if (threadIdx.x != 0) return;
@@ -563,13 +570,13 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     hints.mode = ((hint_mode & 5) ? 1 : 0) | ((hint_mode & 10) ? 2 : 0);
     hints.groups = max(1, min(kCopyGroups, (hint_mode >> 8) & 7));
     hints.whole_record = (hint_mode >> 16) & 3;
-    const int units = p.n * split;
+    const int units = n_whole + (p.n - n_whole) * split;
     const bool dynamic = sched != nullptr;
     static_assert(sizeof(int2) == 8, "descriptor layout");
     // (record, goal record) of a unit; -1 = nothing to copy (row unchanged / no reset / past the end)
     auto unit_desc = [&](int u) -> int2 {
         if (u >= units) return make_int2(-1, -1);
-        const int env = u / split;
+        const int env = u < n_whole ? u : n_whole + (u - n_whole) / split;
         if (p.desc) return p.desc[env];
         int2 d = make_int2(p.obs_state[env], -1);
         if (p.goal && (!p.did_reset || p.did_reset[env])) d.y = p.goal[env];
@@ -581,7 +588,10 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     int u = (int)blockIdx.x;
     int2 d = unit_desc(u);
     while (u < units) {
-        const int env = u / split, slice = u - env * split;
+        const bool whole_unit = u < n_whole;
+        const int env = whole_unit ? u : n_whole + (u - n_whole) / split;
+        const int slice = whole_unit ? 0 : (u - n_whole) % split;
+        const int sp = whole_unit ? 1 : split;
         int u_next = 0;
         int2 d_next = make_int2(-1, -1);
         bool have_next = false;
@@ -593,12 +603,12 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
         };
         if (d.x >= 0) {  // < 0: the row already holds this record (VN_STEP_SKIP_UNCHANGED)
             const uint8_t *src = p.store.base + (size_t)d.x * p.store.state_pitch;
-            bulk_copy_slice(p.store, src, p.obs, env, slice, split, smem, bar, parity, hints, fetch_next,
+            bulk_copy_slice(p.store, src, p.obs, env, slice, sp, smem, bar, parity, hints, fetch_next,
                             (hints.whole_record & 1) != 0);
         }
         if (d.y >= 0) {
             const uint8_t *gsrc = p.store.base + (size_t)d.y * p.store.state_pitch;
-            bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, split, smem, bar, parity, hints, fetch_next,
+            bulk_copy_slice(p.store, gsrc, p.goal_obs, env, slice, sp, smem, bar, parity, hints, fetch_next,
                             (hints.whole_record & 2) != 0);
         }
         fetch_next();
@@ -947,6 +957,7 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
             if (gp.goal && gp.goal_obs[pl]) smem_goal += per << 4;
         }
         int smem = max(smem_obs, smem_goal), whole = 0;
+        int n_whole = split == 1 ? gp.n : 0, k_split = split;
         if (split == 1) {
             int span_o, span_g;
             bool co, cg;
@@ -968,7 +979,14 @@ static int32_t launch_gather(const GatherParams &gp, int32_t variant, cudaStream
         int grid = (int)min((int64_t)gp.n * split, (int64_t)sm_count() * per_sm);
         static const int env_grid = getenv("VN_BULK_GRID") ? atoi(getenv("VN_BULK_GRID")) : 0;   // development
         if (env_grid > 0) grid = min(grid, env_grid);
-        launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, split,
+        // guided scheduling: the last wave's worth of envs in `tail` slices each (development knob, default off = 1)
+        static const int env_tail = getenv("VN_BULK_TAIL_SPLIT") ? atoi(getenv("VN_BULK_TAIL_SPLIT")) : VN_BULK_TAIL_DEFAULT;
+        static const int env_tail_waves16 = getenv("VN_BULK_TAIL_WAVES16") ? atoi(getenv("VN_BULK_TAIL_WAVES16")) : 16;
+        if (split == 1 && env_tail > 1 && gp.n > 2 * grid) {
+            n_whole = gp.n - min(gp.n, grid * env_tail_waves16 / 16);
+            k_split = min(env_tail, 8);
+        }
+        launch_pdl(vn_gather_bulk_kernel, dim3(grid), dim3(32), (size_t)smem, stream, gp, k_split, n_whole,
                    (env_dynamic && gp.sched) ? gp.sched + (gp.parity & 1) : nullptr, env_hints | (whole << 16));
         return check_launch("vn_gather_bulk_kernel");
     }
