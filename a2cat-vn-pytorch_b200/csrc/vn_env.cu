@@ -572,7 +572,6 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     hints.whole_record = (hint_mode >> 16) & 3;
     const int units = n_whole + (p.n - n_whole) * split;
     const bool dynamic = sched != nullptr;
-    static_assert(sizeof(int2) == 8, "descriptor layout");
     // (record, goal record) of a unit; -1 = nothing to copy (row unchanged / no reset / past the end)
     auto unit_desc = [&](int u) -> int2 {
         if (u >= units) return make_int2(-1, -1);
@@ -584,7 +583,7 @@ __global__ void __launch_bounds__(32) vn_gather_bulk_kernel(const GatherParams p
     };
     // the first unit of every CTA is its block index (no atomic round trip before the first copy); the units
     // beyond the grid are handed out by the ticket counter.  The NEXT unit - its ticket and its descriptor, two
-    // dependent round trips through L2 - is fetched while the copies of the current one are in flight (prefetch != 0).
+    // dependent round trips through L2 - is fetched while the copies of the current one are in flight.
     int u = (int)blockIdx.x;
     int2 d = unit_desc(u);
     while (u < units) {
