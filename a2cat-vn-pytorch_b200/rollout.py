@@ -32,7 +32,7 @@ def _strided2d(x, dtype):
     return x
 
 
-def nstep_returns(rewards, dones, last_values, gamma, time_major=False, method="serial"):
+def nstep_returns(rewards, dones, last_values, gamma, time_major=False, method="serial", out=None):
     """A2C n-step returns (deep_rl RolloutStorage.batch).
     rewards float32, dones uint8/bool: [B, T] with ANY strides (``storage.t()`` views are read in place); last_values
     [B].  Returns a contiguous [B, T] tensor.  ``time_major=True``: the arguments are [T, B] and so is the result.
@@ -48,7 +48,8 @@ def nstep_returns(rewards, dones, last_values, gamma, time_major=False, method="
         rewards, dones = rewards.contiguous(), dones.contiguous()
     last_values = last_values.contiguous().float()
     n, t = rewards.shape
-    out = torch.empty((t, n) if time_major else (n, t), dtype=torch.float32, device=rewards.device)
+    if out is None:
+        out = torch.empty((t, n) if time_major else (n, t), dtype=torch.float32, device=rewards.device)
     ob = out.t() if time_major else out
     with torch.cuda.device(rewards.device):
         L.check(fn(rewards.data_ptr(), dones.data_ptr(), last_values.data_ptr(), float(gamma), n, t, rewards.stride(0),
@@ -282,7 +283,7 @@ def policy_input(dw: DeviceWorld, states, plane="rgb"):
     return out
 
 
-def reward_prediction_labels(rewards, with_lists=True, sync=True):
+def reward_prediction_labels(rewards, with_lists=True, sync=True, buffers=None):
     """UNREAL reward-prediction classes (0 zero / 1 positive / 2 negative) and the ascending lists of
     zero / non-zero reward positions (row-major positions of the [B, T] argument, whatever its strides) that the
     50/50 sampler draws from.
@@ -295,6 +296,12 @@ def reward_prediction_labels(rewards, with_lists=True, sync=True):
     if flat:
         r = r.contiguous().view(-1, 1).t()        # [1, n]: positions in storage order
     n = r.numel()
+    if buffers is not None:          # (labels, zero, nonzero, counts, scratch) owned by the caller, reused call after call
+        labels, zero, nonzero, counts, scratch = buffers
+        with torch.cuda.device(r.device):
+            L.check(lib.vn_rp_labels(r.data_ptr(), n, r.shape[1], r.stride(0), r.stride(1), labels.data_ptr(), L.ptr(zero),
+                                     L.ptr(nonzero), counts.data_ptr(), scratch.data_ptr(), _stream(r)))
+        return labels, zero, nonzero, counts
     labels = torch.empty(tuple(rewards.shape), dtype=torch.int8, device=r.device)
     if n == 0:
         e = torch.empty(0, dtype=torch.int32, device=r.device)
@@ -371,15 +378,38 @@ class RolloutBuffer:
     def auxiliary_targets(self, cell_size=4, output_size=None):
         return auxiliary_targets(self.dw, self.states[:-1].t(), self.goals[:-1].t(), cell_size, output_size)
 
-    def targets(self, last_values, gamma, pc_bootstrap, pc_gamma, cell_size=4, output_size=None):
+    def targets(self, last_values, gamma, pc_bootstrap, pc_gamma, cell_size=4, output_size=None, overlap=False):
         """Everything the A2C / UNREAL losses need from one rollout: (n-step returns [B, T], pixel-control returns
-        [B, T, h*w], reward-prediction (labels, zero list, non-zero list, counts)) - seven kernels of this library on
-        the current stream, no host synchronisation, no torch kernel.  (Running the small builders on a side stream
-        was measured and dropped: the event waits break the programmatic launch chain of the steps and tensors handed
-        across streams defeat the caching allocator - 2.6 ms per pass instead of 0.76 ms.)"""
-        return (self.returns(last_values, gamma),
-                self.pixel_control_returns(pc_bootstrap, pc_gamma, cell_size, output_size),
-                self.reward_prediction())
+        [B, T, h*w], reward-prediction (labels, zero list, non-zero list, counts)) - seven kernels of this library, no
+        host synchronisation, no torch kernel.
+
+        overlap=True runs the small builders (returns, RP labels: launch-bound kernels) on a side stream while the
+        pixel-control chain - the only bandwidth-sized one - runs on the current stream, joined by events before this
+        returns.  Their outputs then live in buffers OWNED by this object and are overwritten by the next call (tensors
+        allocated under one stream and consumed under another would defeat torch's caching allocator)."""
+        if not overlap:
+            return (self.returns(last_values, gamma),
+                    self.pixel_control_returns(pc_bootstrap, pc_gamma, cell_size, output_size),
+                    self.reward_prediction())
+        dev = self.dw.device
+        if getattr(self, "_ov", None) is None:
+            n = self.B * self.T
+            i32 = lambda k: torch.empty(k, dtype=torch.int32, device=dev)
+            self._ov = dict(side=torch.cuda.Stream(dev), fork=torch.cuda.Event(), join=torch.cuda.Event(),
+                            ret=torch.empty((self.B, self.T), dtype=torch.float32, device=dev),
+                            rp=(torch.empty((self.B, self.T), dtype=torch.int8, device=dev), i32(n), i32(n), i32(2),
+                                i32((n + 1023) // 1024 + 1)))
+        ov = self._ov
+        cur = torch.cuda.current_stream(dev)
+        ov["fork"].record(cur)
+        ov["side"].wait_event(ov["fork"])
+        with torch.cuda.stream(ov["side"]):
+            ret = nstep_returns(self.rewards.t(), self.dones.t(), last_values, gamma, out=ov["ret"])
+            rp = reward_prediction_labels(self.rewards.t(), sync=False, buffers=ov["rp"])
+            ov["join"].record(ov["side"])
+        pcr = self.pixel_control_returns(pc_bootstrap, pc_gamma, cell_size, output_size)
+        cur.wait_event(ov["join"])
+        return ret, pcr, rp
 
     def reward_prediction(self, sync=False):
         """(labels [B, T], zero positions, non-zero positions, counts) - see reward_prediction_labels; sync=False

@@ -751,7 +751,7 @@ def run_cuda(args):
             rb.start(env)
             for t in range(T_roll):
                 rb.step(env, act(i * T_roll + t), actions_ready=True)
-            return rb.targets(v_last, 0.99, q_last, 0.9, 4, (20, 20))
+            return rb.targets(v_last, 0.99, q_last, 0.9, 4, (20, 20), overlap=True)
 
         def steps_only(i):
             for t in range(T_roll):
@@ -763,7 +763,8 @@ def run_cuda(args):
                                  "ms_20_steps_alone": s20["ms_per_step"], "blocks": p["blocks"], "num_steps": T_roll,
                                  "ratio_to_steps_alone": s20["ms_per_step"] / p["ms_per_step"],
                                  "note": "20 env steps (rollout rows written by the step kernel) + n-step returns + "
-                                         "pixel-control rewards and back-up + RP labels, per pass; no torch kernels"}
+                                         "pixel-control rewards and back-up + RP labels, per pass; no torch kernels; "
+                                         "returns / RP labels on a side stream next to the pixel-control chain"}
 
     # ---- e2e through the public VecEnv API: host actions in, host rewards/dones out, every step
     host_actions = actions[:512].cpu().numpy()

@@ -362,6 +362,13 @@ def test_builders_read_time_major_storage_in_place(dw):
     cz, cn = t_cnt.tolist()
     assert torch.equal(t_ret, buf.returns(v, 0.99)) and torch.equal(t_pcr, want)
     assert torch.equal(t_lab, lab_c) and torch.equal(t_z[:cz], z_c) and torch.equal(t_nz[:cn], nz_c)
+    # the small builders on a side stream (event fork / join, outputs in buffers owned by the rollout buffer): same bits
+    for _ in range(3):
+        o_ret, o_pcr, (o_lab, o_z, o_nz, o_cnt) = buf.targets(v, 0.99, q, 0.9, 4, (20, 20), overlap=True)
+        torch.cuda.current_stream().synchronize()
+        cz2, cn2 = o_cnt.tolist()
+        assert torch.equal(o_ret, t_ret) and torch.equal(o_pcr, want) and torch.equal(o_lab, lab_c)
+        assert torch.equal(o_z[:cz2], z_c) and torch.equal(o_nz[:cn2], nz_c)
     # against the oracle as well
     scene = dw.world.scenes[0]
     fr = scene.plane_frames("rgb", st_c.cpu().numpy().reshape(-1)).reshape(N, Tn + 1, 84, 84, 3)

@@ -39,7 +39,7 @@ def main():
             rb.pixel_control_returns(q, 0.9, 4, (20, 20))
             rb.reward_prediction()
         else:
-            rb.targets(v, 0.99, q, 0.9, 4, (20, 20))
+            rb.targets(v, 0.99, q, 0.9, 4, (20, 20), overlap=bool(os.environ.get("A2C_OVERLAP")))
     e1.record()
     torch.cuda.synchronize()
     print("a2c pass: %.1f us (%d passes)" % (1e3 * e0.elapsed_time(e1) / max(1, passes - 5), passes))
