@@ -669,7 +669,11 @@ def run_cuda(args):
                 "how": "in situ: CUDA events around blocks of K timed steps / K launches, median block (the scalar part "
                        "of a step overlaps the previous gather, so this is the gather's launch-to-launch period)",
                 "rows_skipped_rate": p_skip, "isolated": iso,
-                "same_size_copy_ms": copy_ms, "same_size_copy_gbs": 2 * nb / (copy_ms * 1e-3) / 1e9}
+                "same_size_copy_ms": copy_ms, "same_size_copy_gbs": 2 * nb / (copy_ms * 1e-3) / 1e9,
+                # the DRAM rate of the gather next to what a plain copy of this size reaches on this GPU (a 36 us
+                # transfer does not reach the 2 GiB copy peak either)
+                "dram_rate_vs_same_size_copy": (traffic / (situ_ms * 1e-3) / 1e9) / (2 * nb / (copy_ms * 1e-3) / 1e9)
+                if traffic else None}
 
     run_stats = {"p_reset": p_reset, "collision_rate": coll, "rows_skipped_rate": p_skip,
                  "launches_per_step": launches_per_step, "states": world.n_states, "store_bytes": env.dw.nbytes(),
