@@ -54,5 +54,39 @@ def main(steps=200000, block=1000):
                  steps * n / (time.perf_counter() - t0) / 1e6))
 
 
+def host_twin(steps=30000):
+    """The host-facing step() (numpy in / numpy out, mapped pinned memory, sequence words, alternating host packs, lazy
+    infos) against a device-resident twin, every step."""
+    import numpy as np
+    import torch
+    vn = importlib.import_module("a2cat-vn-pytorch_b200")
+    scene = vn.scenes.make_thor_scene(400, (30, 30), seed=3, n_goals=4, planes=("rgb", "depth"))
+    world = vn.compile_world([scene], vn.GYM_GRAPH)
+    n = 4096
+    host = vn.GraphVecEnv(world, n, seed=11, max_episode_steps=37, obs_layout="rgbd_goal")
+    dev = vn.GraphVecEnv(world, n, seed=11, max_episode_steps=37, obs_layout="rgbd_goal", host_outputs=False, device_world=host.dw)
+    host.reset()
+    dev.reset()
+    acts = np.random.RandomState(0).randint(0, 4, (256, n)).astype(np.int32)
+    dacts = torch.from_numpy(acts).cuda()
+    t0 = time.perf_counter()
+    kept = []
+    for t in range(steps):
+        _, r, d, infos = host.step(acts[t % 256])
+        dev.step_enqueue(dacts[t % 256], actions_ready=True)
+        if t % 50 == 0:
+            torch.cuda.synchronize()
+            assert np.array_equal(r.view(np.uint32), dev.reward.cpu().numpy().view(np.uint32)), t
+            assert np.array_equal(d, dev.done.cpu().numpy().astype(bool)) and torch.equal(host.state, dev.state), t
+            kept.append((infos, [dict(x) for x in infos[:64]]))
+            kept = kept[-8:]
+    for infos, want in kept:                      # lazy infos kept across many later steps are still right
+        assert [dict(x) for x in infos[:64]] == want
+    assert host.episode_stats() == dev.episode_stats()
+    print("host-facing step vs device twin  %d envs x %d steps ok, %.1f M env-steps/s incl. the twin and checks"
+          % (n, steps, steps * n / (time.perf_counter() - t0) / 1e6))
+
+
 if __name__ == "__main__":
     main(int(sys.argv[1]) if len(sys.argv) > 1 else 200000)
+    host_twin()
